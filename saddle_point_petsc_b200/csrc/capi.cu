@@ -1,0 +1,574 @@
+// capi.cu -- the extern "C" boundary of libb200sp (include/b200sp.h).  Catches every C++ exception and
+// turns it into an int error code (PetscErrorCode convention); no C++ type crosses the boundary.
+#include "solver.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+using namespace b200sp;
+
+struct b200sp_ctx_s { Ctx c; };
+struct b200sp_vec_s { Vec v; b200sp_vec_s(Ctx *c, int64_t n) : v(c, n) {} };
+struct b200sp_mat_s { Mat m; };
+struct b200sp_ksp_s { Solver s; explicit b200sp_ksp_s(Ctx *c) : s(c) {} };
+struct b200sp_dmda_s { Dmda d; };
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END                                                    \
+  return B200SP_OK;                                                \
+  }                                                                \
+  catch (const Error &e) { g_last_error = e.what(); return e.code; } \
+  catch (const std::exception &e) { g_last_error = e.what(); return B200SP_ERR_ARG; } \
+  catch (...) { g_last_error = "unknown error"; return B200SP_ERR_ARG; }
+
+namespace b200sp {
+Ctx::~Ctx() {
+  if (comm) ncclCommDestroy(comm);
+  if (d_partials) cudaFree(d_partials);
+  if (d_ticket) cudaFree(d_ticket);
+  if (d_scalars) cudaFree(d_scalars);
+  if (h_scalars) cudaFreeHost(h_scalars);
+  if (pev0) cudaEventDestroy(pev0);
+  if (pev1) cudaEventDestroy(pev1);
+  if (tev0) cudaEventDestroy(tev0);
+  if (tev1) cudaEventDestroy(tev1);
+  if (stream) cudaStreamDestroy(stream);
+  if (stream2) cudaStreamDestroy(stream2);
+}
+
+// ---- host-only DMDA index arithmetic ----
+void dmda_proc_grid(int M, int N, int size, int *pm, int *pn) {
+  int m = (int)(0.5 + std::sqrt(((double)M) * ((double)size) / ((double)N))), n = 1;
+  if (!m) m = 1;
+  while (m > 0) {
+    n = size / m;
+    if (m * n == size) break;
+    m--;
+  }
+  if (M > N && m < n) std::swap(m, n);
+  *pm = m;
+  *pn = n;
+}
+void dmda_ownership(int M, int m, int *lx) {
+  for (int i = 0; i < m; ++i) lx[i] = M / m + ((M % m) > i);
+}
+} // namespace b200sp
+
+namespace {
+struct Layout {
+  int M, N, size, m, n;
+  std::vector<int> lx, ly, xoff, yoff, rstart; // rstart[r] = first global node id of rank r
+  Layout(int M_, int N_, int size_) : M(M_), N(N_), size(size_) {
+    B2_REQUIRE(M >= 2 && N >= 2 && size >= 1, "dmda: need M,N >= 2 and size >= 1");
+    dmda_proc_grid(M, N, size, &m, &n);
+    B2_REQUIRE(m * n == size, "dmda: size does not factor into a process grid");
+    B2_REQUIRE(m <= M && n <= N, "dmda: more ranks than nodes in a direction");
+    lx.resize(m); ly.resize(n);
+    dmda_ownership(M, m, lx.data());
+    dmda_ownership(N, n, ly.data());
+    xoff.assign(m + 1, 0); yoff.assign(n + 1, 0);
+    for (int i = 0; i < m; ++i) xoff[i + 1] = xoff[i] + lx[i];
+    for (int j = 0; j < n; ++j) yoff[j + 1] = yoff[j] + ly[j];
+    rstart.assign(size + 1, 0);
+    for (int r = 0; r < size; ++r) rstart[r + 1] = rstart[r] + lx[r % m] * ly[r / m];
+  }
+  int owner_x(int i) const { return (int)(std::upper_bound(xoff.begin(), xoff.end(), i) - xoff.begin()) - 1; }
+  int owner_y(int j) const { return (int)(std::upper_bound(yoff.begin(), yoff.end(), j) - yoff.begin()) - 1; }
+  int owner(int i, int j) const { return owner_y(j) * m + owner_x(i); }
+  int gnode(int i, int j) const {
+    const int pi = owner_x(i), pj = owner_y(j), r = pj * m + pi;
+    return rstart[r] + (j - yoff[pj]) * lx[pi] + (i - xoff[pi]);
+  }
+};
+} // namespace
+
+extern "C" {
+
+const char *b200sp_last_error(void) { return g_last_error.c_str(); }
+const char *b200sp_version(void) { return "b200sp 0.1 (sm_100a)"; }
+
+int b200sp_nccl_unique_id(char id[128]) {
+  API_BEGIN
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId u;
+  B2_NCCL(ncclGetUniqueId(&u));
+  std::memcpy(id, &u, 128);
+  API_END
+}
+
+int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b200sp_ctx *out) {
+  API_BEGIN
+  B2_REQUIRE(out && size >= 1 && rank >= 0 && rank < size, "ctx_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(B200SP_ERR_NO_DEVICE, "no CUDA device: libb200sp has no CPU fallback");
+  }
+  B2_REQUIRE(device >= 0 && device < ndev, "ctx_create: bad device index");
+  B2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) throw Error(B200SP_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: libb200sp is built for B200 only");
+  auto *h = new b200sp_ctx_s();
+  Ctx &c = h->c;
+  try {
+    c.device = device; c.rank = rank; c.size = size;
+    c.num_sms = prop.multiProcessorCount;
+    B2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    B2_CUDA(cudaMalloc((void **)&c.d_partials, sizeof(double) * RED_MAX_BLOCKS * RED_MAX_OUT));
+    B2_CUDA(cudaMalloc((void **)&c.d_ticket, sizeof(unsigned)));
+    B2_CUDA(cudaMemset(c.d_ticket, 0, sizeof(unsigned)));
+    B2_CUDA(cudaMalloc((void **)&c.d_scalars, sizeof(double) * N_SCALARS));
+    B2_CUDA(cudaMemset(c.d_scalars, 0, sizeof(double) * N_SCALARS));
+    B2_CUDA(cudaMallocHost((void **)&c.h_scalars, sizeof(double) * N_SCALARS));
+    B2_CUDA(cudaEventCreate(&c.pev0)); B2_CUDA(cudaEventCreate(&c.pev1));
+    B2_CUDA(cudaEventCreate(&c.tev0)); B2_CUDA(cudaEventCreate(&c.tev1));
+    if (size > 1) {
+      B2_REQUIRE(nccl_id, "ctx_create: size > 1 needs an NCCL unique id");
+      ncclUniqueId u;
+      std::memcpy(&u, nccl_id, 128);
+      B2_NCCL(ncclCommInitRank(&c.comm, size, u, rank));
+    }
+  } catch (...) { delete h; throw; }
+  *out = h;
+  API_END
+}
+int b200sp_ctx_destroy(b200sp_ctx ctx) {
+  API_BEGIN
+  if (ctx) { cudaSetDevice(ctx->c.device); cudaStreamSynchronize(ctx->c.stream); delete ctx; }
+  API_END
+}
+int b200sp_ctx_synchronize(b200sp_ctx ctx) { API_BEGIN ctx->c.sync(); API_END }
+int b200sp_ctx_get_stream(b200sp_ctx ctx, void **s) { API_BEGIN *s = (void *)ctx->c.stream; API_END }
+int b200sp_ctx_get_launch_count(b200sp_ctx ctx, int64_t *count) { API_BEGIN *count = ctx->c.launches; API_END }
+int b200sp_ctx_timer_start(b200sp_ctx ctx) { API_BEGIN B2_CUDA(cudaEventRecord(ctx->c.tev0, ctx->c.stream)); API_END }
+int b200sp_ctx_timer_stop(b200sp_ctx ctx, double *ms) {
+  API_BEGIN
+  B2_CUDA(cudaEventRecord(ctx->c.tev1, ctx->c.stream));
+  B2_CUDA(cudaEventSynchronize(ctx->c.tev1));
+  float f = 0;
+  B2_CUDA(cudaEventElapsedTime(&f, ctx->c.tev0, ctx->c.tev1));
+  *ms = f;
+  API_END
+}
+int b200sp_ctx_profile_enable(b200sp_ctx ctx, int on) {
+  API_BEGIN
+  ctx->c.sync();
+  ctx->c.profile = on != 0;
+  if (on) ctx->c.prof.clear();
+  API_END
+}
+int b200sp_ctx_profile_report(b200sp_ctx ctx, char *buf, int buflen) {
+  API_BEGIN
+  std::ostringstream o;
+  o << "{";
+  bool first = true;
+  for (auto &kv : ctx->c.prof) {
+    if (!first) o << ", ";
+    first = false;
+    o << "\"" << kv.first << "\": {\"ms\": " << kv.second.ms << ", \"launches\": " << kv.second.n << "}";
+  }
+  o << "}";
+  std::string s = o.str();
+  B2_REQUIRE(buf && buflen > (int)s.size(), "profile_report: buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  API_END
+}
+
+// ---------------------------------------------------------------- DMDA
+int b200sp_dmda_proc_grid(int M, int N, int size, int *m, int *n) { API_BEGIN B2_REQUIRE(M > 0 && N > 0 && size > 0, "bad args"); dmda_proc_grid(M, N, size, m, n); API_END }
+int b200sp_dmda_ownership(int M, int m, int *lx) { API_BEGIN B2_REQUIRE(M > 0 && m > 0 && lx, "bad args"); dmda_ownership(M, m, lx); API_END }
+int b200sp_dmda_corners(int M, int N, int size, int rank, int *xs, int *ys, int *xm, int *ym) {
+  API_BEGIN
+  Layout L(M, N, size);
+  B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
+  const int pi = rank % L.m, pj = rank / L.m;
+  *xs = L.xoff[pi]; *ys = L.yoff[pj]; *xm = L.lx[pi]; *ym = L.ly[pj];
+  API_END
+}
+int b200sp_dmda_element_corners(int M, int N, int size, int rank, int *si, int *sj, int *ni, int *nj) {
+  API_BEGIN
+  Layout L(M, N, size);
+  B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
+  const int pi = rank % L.m, pj = rank / L.m;
+  const int xs = L.xoff[pi], ys = L.yoff[pj];
+  const int gxs = xs > 0 ? xs - 1 : xs, gys = ys > 0 ? ys - 1 : ys; // DMDAGetElementsCorners
+  *si = gxs; *sj = gys;
+  *ni = xs + L.lx[pi] - gxs - 1;
+  *nj = ys + L.ly[pj] - gys - 1;
+  API_END
+}
+int b200sp_dmda_global_node(int M, int N, int size, int i, int j, int *gnode, int *owner) {
+  API_BEGIN
+  Layout L(M, N, size);
+  B2_REQUIRE(i >= 0 && i < M && j >= 0 && j < N, "node out of range");
+  if (gnode) *gnode = L.gnode(i, j);
+  if (owner) *owner = L.owner(i, j);
+  API_END
+}
+int b200sp_dmda_halo_plan(int M, int N, int size, int rank, int *nghost, int *ghost_gnode, int *ghost_owner, int *nsend_total, int *send_rank,
+                          int *send_lnode) {
+  API_BEGIN
+  Layout L(M, N, size);
+  B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
+  const int pi = rank % L.m, pj = rank / L.m;
+  const int xs = L.xoff[pi], ys = L.yoff[pj], xm = L.lx[pi], ym = L.ly[pj];
+  // ghosts: the ring of width 1 around the owned box, clipped to the domain (box stencil -> corners included)
+  std::vector<std::pair<int, int>> gh; // (global node, owner)
+  for (int j = std::max(ys - 1, 0); j <= std::min(ys + ym, N - 1); ++j)
+    for (int i = std::max(xs - 1, 0); i <= std::min(xs + xm, M - 1); ++i)
+      if (i < xs || i >= xs + xm || j < ys || j >= ys + ym) gh.push_back({L.gnode(i, j), L.owner(i, j)});
+  std::sort(gh.begin(), gh.end()); // MPIAIJ garray order
+  if (nghost) *nghost = (int)gh.size();
+  if (ghost_gnode) for (size_t t = 0; t < gh.size(); ++t) ghost_gnode[t] = gh[t].first;
+  if (ghost_owner) for (size_t t = 0; t < gh.size(); ++t) ghost_owner[t] = gh[t].second;
+  // sends: for every neighbour rank q (ascending), the owned nodes inside q's ghost ring, ordered by OUR
+  // global id == the order in which they appear in q's sorted ghost list restricted to owner==rank
+  std::vector<std::pair<int, int>> snd; // (dest rank, local node)
+  for (int q = 0; q < size; ++q) {
+    if (q == rank) continue;
+    const int qi = q % L.m, qj = q / L.m;
+    const int qxs = L.xoff[qi], qys = L.yoff[qj], qxm = L.lx[qi], qym = L.ly[qj];
+    const int i0 = std::max(std::max(qxs - 1, 0), xs), i1 = std::min(std::min(qxs + qxm, M - 1), xs + xm - 1);
+    const int j0 = std::max(std::max(qys - 1, 0), ys), j1 = std::min(std::min(qys + qym, N - 1), ys + ym - 1);
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) snd.push_back({q, (j - ys) * xm + (i - xs)});
+  }
+  if (nsend_total) *nsend_total = (int)snd.size();
+  if (send_rank) for (size_t t = 0; t < snd.size(); ++t) send_rank[t] = snd[t].first;
+  if (send_lnode) for (size_t t = 0; t < snd.size(); ++t) send_lnode[t] = snd[t].second;
+  API_END
+}
+int b200sp_dmda_create(b200sp_ctx ctx, int M, int N, b200sp_dmda *da) {
+  API_BEGIN
+  B2_REQUIRE(ctx && da, "dmda_create: bad arguments");
+  Layout L(M, N, ctx->c.size);
+  auto *h = new b200sp_dmda_s();
+  Dmda &d = h->d;
+  d.ctx = &ctx->c; d.M = M; d.N = N; d.pm = L.m; d.pn = L.n; d.lx = L.lx; d.ly = L.ly;
+  const int pi = ctx->c.rank % L.m, pj = ctx->c.rank / L.m;
+  d.xs = L.xoff[pi]; d.ys = L.yoff[pj]; d.xm = L.lx[pi]; d.ym = L.ly[pj];
+  *da = h;
+  API_END
+}
+int b200sp_dmda_destroy(b200sp_dmda da) { API_BEGIN delete da; API_END }
+int b200sp_dmda_get_info(b200sp_dmda da, int *M, int *N, int *xs, int *ys, int *xm, int *ym) {
+  API_BEGIN
+  if (M) *M = da->d.M; if (N) *N = da->d.N;
+  if (xs) *xs = da->d.xs; if (ys) *ys = da->d.ys; if (xm) *xm = da->d.xm; if (ym) *ym = da->d.ym;
+  API_END
+}
+int b200sp_dmda_bc_ids(b200sp_dmda da, int dof, int *n, int *ids) {
+  API_BEGIN
+  std::vector<int> v = dmda_bc_ids(da->d, dof);
+  if (n) *n = (int)v.size();
+  if (ids) std::copy(v.begin(), v.end(), ids);
+  API_END
+}
+
+// ---------------------------------------------------------------- Vec
+int b200sp_vec_create(b200sp_ctx ctx, int64_t n, b200sp_vec *v) {
+  API_BEGIN
+  B2_REQUIRE(ctx && v && n >= 0, "vec_create: bad arguments");
+  *v = new b200sp_vec_s(&ctx->c, n);
+  API_END
+}
+int b200sp_vec_destroy(b200sp_vec v) { API_BEGIN if (v) { v->v.ctx->sync(); delete v; } API_END }
+int b200sp_vec_get_size(b200sp_vec v, int64_t *n) { API_BEGIN *n = v->v.n; API_END }
+int b200sp_vec_set(b200sp_vec v, double a) { API_BEGIN vec_set(v->v.ctx, v->v.n, a, v->v.d); API_END }
+int b200sp_vec_set_values_host(b200sp_vec v, int64_t n, const int *idx, const double *vals) {
+  API_BEGIN
+  Ctx *c = v->v.ctx;
+  if (n > 0) {
+    // INSERT_VALUES of a host list: staged through the device copy (values are few: boundary dofs)
+    std::vector<double> h((size_t)v->v.n);
+    B2_CUDA(cudaMemcpyAsync(h.data(), v->v.d, sizeof(double) * (size_t)v->v.n, cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    for (int64_t t = 0; t < n; ++t) {
+      B2_REQUIRE(idx[t] >= 0 && idx[t] < v->v.n, "vec_set_values: index out of range");
+      h[(size_t)idx[t]] = vals[t];
+    }
+    B2_CUDA(cudaMemcpyAsync(v->v.d, h.data(), sizeof(double) * (size_t)v->v.n, cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+  }
+  API_END
+}
+int b200sp_vec_copy_from_host(b200sp_vec v, const double *host, int64_t n) {
+  API_BEGIN
+  B2_REQUIRE(n == v->v.n, "vec_copy_from_host: size mismatch");
+  B2_CUDA(cudaMemcpyAsync(v->v.d, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, v->v.ctx->stream));
+  v->v.ctx->sync();
+  API_END
+}
+int b200sp_vec_copy_to_host(b200sp_vec v, double *host, int64_t n) {
+  API_BEGIN
+  B2_REQUIRE(n == v->v.n, "vec_copy_to_host: size mismatch");
+  B2_CUDA(cudaMemcpyAsync(host, v->v.d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, v->v.ctx->stream));
+  v->v.ctx->sync();
+  API_END
+}
+int b200sp_vec_get_device_ptr(b200sp_vec v, double **dev) { API_BEGIN *dev = v->v.d; API_END }
+#define SAME_SIZE(a, b) B2_REQUIRE((a)->v.n == (b)->v.n, "vector size mismatch")
+int b200sp_vec_copy(b200sp_vec x, b200sp_vec y) { API_BEGIN SAME_SIZE(x, y); vec_copy(x->v.ctx, x->v.n, x->v.d, y->v.d); API_END }
+int b200sp_vec_scale(b200sp_vec x, double a) { API_BEGIN vec_scale(x->v.ctx, x->v.n, a, x->v.d); API_END }
+int b200sp_vec_axpy(b200sp_vec y, double a, b200sp_vec x) { API_BEGIN SAME_SIZE(x, y); vec_axpy(y->v.ctx, y->v.n, a, x->v.d, y->v.d); API_END }
+int b200sp_vec_aypx(b200sp_vec y, double a, b200sp_vec x) { API_BEGIN SAME_SIZE(x, y); vec_aypx(y->v.ctx, y->v.n, a, x->v.d, y->v.d); API_END }
+int b200sp_vec_waxpy(b200sp_vec w, double a, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN SAME_SIZE(x, y); SAME_SIZE(x, w); vec_waxpy(w->v.ctx, w->v.n, a, x->v.d, y->v.d, w->v.d); API_END
+}
+int b200sp_vec_pointwise_mult(b200sp_vec w, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN SAME_SIZE(x, y); SAME_SIZE(x, w); vec_pointwise_mult(w->v.ctx, w->v.n, x->v.d, y->v.d, w->v.d); API_END
+}
+static void global_sum(Ctx *c, int k, double *host) {
+  if (c->size > 1) B2_NCCL(ncclAllReduce(c->d_scalars, c->d_scalars, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  c->fetch_scalars(c->d_scalars, k, host);
+}
+int b200sp_vec_dot(b200sp_vec x, b200sp_vec y, double *result) {
+  API_BEGIN
+  SAME_SIZE(x, y);
+  Ctx *c = x->v.ctx;
+  vec_dot(c, x->v.n, x->v.d, y->v.d, c->d_scalars);
+  global_sum(c, 1, result);
+  API_END
+}
+int b200sp_vec_norm(b200sp_vec x, double *result) {
+  API_BEGIN
+  Ctx *c = x->v.ctx;
+  vec_dot(c, x->v.n, x->v.d, x->v.d, c->d_scalars);
+  global_sum(c, 1, result);
+  *result = std::sqrt(*result);
+  API_END
+}
+int b200sp_vec_mdot(b200sp_vec x, int k, const b200sp_vec *y, double *result) {
+  API_BEGIN
+  B2_REQUIRE(k >= 0 && k <= N_SCALARS, "vec_mdot: k out of range");
+  Ctx *c = x->v.ctx;
+  // the y's are independent allocations: one fused launch per group is only possible for a strided basis
+  // (the KSP path); here each dot is its own launch into consecutive result slots.
+  for (int j = 0; j < k; ++j) { SAME_SIZE(x, y[j]); vec_dot(c, x->v.n, x->v.d, y[j]->v.d, c->d_scalars + j); }
+  if (k) global_sum(c, k, result);
+  API_END
+}
+int b200sp_vec_maxpy(b200sp_vec y, int k, const double *a, const b200sp_vec *x) {
+  API_BEGIN
+  for (int j = 0; j < k; ++j) { SAME_SIZE(y, x[j]); vec_axpy(y->v.ctx, y->v.n, a[j], x[j]->v.d, y->v.d); }
+  API_END
+}
+
+// ---------------------------------------------------------------- Mat
+static b200sp_mat wrap(Ctx *c, std::shared_ptr<Csr> A) {
+  auto *h = new b200sp_mat_s();
+  h->m.ctx = c;
+  h->m.csr = A;
+  return h;
+}
+static Csr &plain(b200sp_mat A) {
+  B2_REQUIRE(A && !A->m.nest && A->m.csr, "operation needs a plain CSR matrix, not a nest");
+  return *A->m.csr;
+}
+int b200sp_mat_create_csr(b200sp_ctx ctx, int nrows, int ncols, const int *rowptr, const int *col, const double *val, b200sp_mat *A) {
+  API_BEGIN *A = wrap(&ctx->c, csr_from_host(&ctx->c, nrows, ncols, rowptr, col, val)); API_END
+}
+int b200sp_mat_create_coo(b200sp_ctx ctx, int nrows, int ncols, int64_t ncoo, const int *row, const int *col, const double *val, b200sp_mat *A) {
+  API_BEGIN *A = wrap(&ctx->c, csr_from_coo_host(&ctx->c, nrows, ncols, ncoo, row, col, val)); API_END
+}
+int b200sp_mat_destroy(b200sp_mat A) { API_BEGIN if (A) { A->m.ctx->sync(); delete A; } API_END }
+int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz) {
+  API_BEGIN
+  if (nrows) *nrows = A->m.nrows();
+  if (ncols) *ncols = A->m.ncols();
+  if (nnz) {
+    if (A->m.nest) { *nnz = 0; for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (A->m.blk[i][j]) *nnz += A->m.blk[i][j]->nnz; }
+    else *nnz = A->m.csr->nnz;
+  }
+  API_END
+}
+int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val) {
+  API_BEGIN
+  Csr &M = plain(A);
+  Ctx *c = M.ctx;
+  if (rowptr) B2_CUDA(cudaMemcpyAsync(rowptr, M.rowptr.p, sizeof(int) * ((size_t)M.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (col && M.nnz) B2_CUDA(cudaMemcpyAsync(col, M.col.p, sizeof(int) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
+  if (val && M.nnz) B2_CUDA(cudaMemcpyAsync(val, M.val.p, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END
+}
+int b200sp_mat_get_spmv_plan(b200sp_mat A, int64_t hist[14], int *kernel, int *max_row_nnz) {
+  API_BEGIN
+  Csr &M = plain(A);
+  if (hist) std::copy(M.hist, M.hist + 14, hist);
+  if (kernel) *kernel = M.kernel;
+  if (max_row_nnz) *max_row_nnz = M.max_row_nnz;
+  API_END
+}
+int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel) {
+  API_BEGIN
+  Csr &M = plain(A);
+  B2_REQUIRE(kernel >= 0 && kernel <= 2, "bad kernel id");
+  B2_REQUIRE(kernel != SPMV_STREAM || M.max_group_nnz <= 1152, "stream kernel: rows too long for the shared tile");
+  M.kernel = kernel;
+  API_END
+}
+static void mat_apply(Mat &m, const double *x, double *y, double alpha, const double *z, double beta_z) {
+  if (!m.nest) { csr_spmv(*m.csr, x, y, alpha, z, beta_z); return; }
+  const int64_t n0c = m.blk[0][0]->ncols, n0r = m.blk[0][0]->nrows;
+  csr_spmv(*m.blk[0][0], x, y, alpha, z, beta_z);
+  csr_spmv(*m.blk[0][1], x + n0c, y, alpha, y, 1.0);
+  csr_spmv(*m.blk[1][0], x, y + n0r, alpha, z ? z + n0r : nullptr, beta_z);
+  if (m.blk[1][1]) csr_spmv(*m.blk[1][1], x + n0c, y + n0r, alpha, y + n0r, 1.0);
+}
+int b200sp_mat_mult(b200sp_mat A, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN
+  B2_REQUIRE(x->v.n == A->m.ncols() && y->v.n == A->m.nrows() && x != y, "mat_mult: size mismatch or aliasing");
+  mat_apply(A->m, x->v.d, y->v.d, 1.0, nullptr, 0.0);
+  API_END
+}
+int b200sp_mat_mult_add(b200sp_mat A, b200sp_vec x, b200sp_vec y, b200sp_vec z) {
+  API_BEGIN
+  B2_REQUIRE(x->v.n == A->m.ncols() && y->v.n == A->m.nrows() && z->v.n == y->v.n && x != z, "mat_mult_add: size mismatch or aliasing");
+  mat_apply(A->m, x->v.d, z->v.d, 1.0, y->v.d, 1.0);
+  API_END
+}
+int b200sp_mat_residual(b200sp_mat A, b200sp_vec b, b200sp_vec x, b200sp_vec r) {
+  API_BEGIN
+  B2_REQUIRE(x->v.n == A->m.ncols() && b->v.n == A->m.nrows() && r->v.n == b->v.n && x != r, "mat_residual: size mismatch or aliasing");
+  mat_apply(A->m, x->v.d, r->v.d, -1.0, b->v.d, 1.0);
+  API_END
+}
+int b200sp_mat_get_diagonal(b200sp_mat A, b200sp_vec d) {
+  API_BEGIN
+  Csr &M = plain(A);
+  B2_REQUIRE(d->v.n == M.nrows, "mat_get_diagonal: size mismatch");
+  csr_get_diagonal(M, d->v.d);
+  API_END
+}
+int b200sp_mat_transpose(b200sp_mat A, b200sp_mat *At) { API_BEGIN *At = wrap(A->m.ctx, csr_transpose(plain(A))); API_END }
+int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C) { API_BEGIN *C = wrap(A->m.ctx, csr_matmat(plain(A), plain(B))); API_END }
+int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag) {
+  API_BEGIN
+  Csr &M = plain(A);
+  B2_REQUIRE(M.nrows == M.ncols, "MatZeroRowsColumns: matrix must be square");
+  for (int t = 0; t < n; ++t) B2_REQUIRE(rows[t] >= 0 && rows[t] < M.nrows, "MatZeroRowsColumns: row out of range");
+  csr_zero_rows_cols(M, n, rows, diag, true, true, true);
+  API_END
+}
+int b200sp_mat_zero_rows(b200sp_mat A, int n, const int *rows, double diag) {
+  API_BEGIN
+  Csr &M = plain(A);
+  for (int t = 0; t < n; ++t) B2_REQUIRE(rows[t] >= 0 && rows[t] < M.nrows, "MatZeroRows: row out of range");
+  csr_zero_rows_cols(M, n, rows, diag, true, false, M.nrows == M.ncols && diag != 0.0);
+  API_END
+}
+int b200sp_mat_zero_columns(b200sp_mat A, int n, const int *cols) {
+  API_BEGIN
+  Csr &M = plain(A);
+  for (int t = 0; t < n; ++t) B2_REQUIRE(cols[t] >= 0 && cols[t] < M.ncols, "zero_columns: column out of range");
+  csr_zero_rows_cols(M, n, cols, 0.0, false, true, false);
+  API_END
+}
+int b200sp_mat_create_nest(b200sp_mat A00, b200sp_mat A01, b200sp_mat A10, b200sp_mat A11, b200sp_mat *K) {
+  API_BEGIN
+  Csr &a00 = plain(A00), &a01 = plain(A01), &a10 = plain(A10);
+  B2_REQUIRE(a00.nrows == a01.nrows && a00.ncols == a10.ncols, "nest: block shapes do not match");
+  if (A11) B2_REQUIRE(plain(A11).nrows == a10.nrows && plain(A11).ncols == a01.ncols, "nest: A11 shape does not match");
+  auto *h = new b200sp_mat_s();
+  h->m.ctx = a00.ctx;
+  h->m.nest = true;
+  h->m.blk[0][0] = A00->m.csr; h->m.blk[0][1] = A01->m.csr; h->m.blk[1][0] = A10->m.csr;
+  h->m.blk[1][1] = A11 ? A11->m.csr : nullptr;
+  *K = h;
+  API_END
+}
+
+// ---------------------------------------------------------------- assembly
+int b200sp_assemble_stress(b200sp_dmda da, int as_written, b200sp_mat *A) { API_BEGIN *A = wrap(da->d.ctx, assemble_stress(da->d, as_written)); API_END }
+int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec f) {
+  API_BEGIN
+  B2_REQUIRE(f->v.n >= (int64_t)da->d.xm * da->d.ym * 2, "assemble_rhs: vector too short");
+  assemble_rhs(da->d, as_written, rhs_kind, f->v.d);
+  API_END
+}
+int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q) {
+  API_BEGIN
+  std::shared_ptr<Csr> bt, b, c, q;
+  assemble_kkt(da->d, Bt ? &bt : nullptr, B ? &b : nullptr, C ? &c : nullptr, Q ? &q : nullptr);
+  if (Bt) *Bt = wrap(da->d.ctx, bt);
+  if (B) *B = wrap(da->d.ctx, b);
+  if (C) *C = wrap(da->d.ctx, c);
+  if (Q) *Q = wrap(da->d.ctx, q);
+  API_END
+}
+int b200sp_interp_q1(b200sp_ctx ctx, int Mc, int Nc, int dof, int bc, b200sp_mat *P) { API_BEGIN *P = wrap(&ctx->c, interp_q1(&ctx->c, Mc, Nc, dof, bc)); API_END }
+
+// ---------------------------------------------------------------- KSP
+int b200sp_ksp_create(b200sp_ctx ctx, b200sp_ksp *ksp) { API_BEGIN B2_REQUIRE(ctx && ksp, "ksp_create: bad arguments"); *ksp = new b200sp_ksp_s(&ctx->c); API_END }
+int b200sp_ksp_destroy(b200sp_ksp *ksp) {
+  API_BEGIN
+  if (ksp && *ksp) { (*ksp)->s.ctx->sync(); delete *ksp; *ksp = nullptr; }
+  API_END
+}
+int b200sp_ksp_set_operators(b200sp_ksp ksp, b200sp_mat Amat, b200sp_mat Pmat) {
+  API_BEGIN
+  B2_REQUIRE(Amat && Pmat, "KSPSetOperators: null matrix");
+  ksp->s.Amat = &Amat->m; ksp->s.Pmat = &Pmat->m; ksp->s.is_setup = false;
+  API_END
+}
+int b200sp_ksp_set_options(b200sp_ksp ksp, const char *options) { API_BEGIN ksp->s.set_options(options); API_END }
+int b200sp_ksp_set_schur_user_mat(b200sp_ksp ksp, b200sp_mat Q) { API_BEGIN ksp->s.schur_user = plain(Q).ctx ? Q->m.csr : nullptr; ksp->s.is_setup = false; API_END }
+int b200sp_ksp_set_dmda(b200sp_ksp ksp, b200sp_dmda da) { API_BEGIN ksp->s.have_grid = true; ksp->s.grid_M = da->d.M; ksp->s.grid_N = da->d.N; API_END }
+int b200sp_ksp_setup(b200sp_ksp ksp) { API_BEGIN ksp->s.setup(); API_END }
+int b200sp_ksp_solve(b200sp_ksp ksp, b200sp_vec b, b200sp_vec x) {
+  API_BEGIN
+  if (!ksp->s.is_setup) ksp->s.setup();
+  B2_REQUIRE(b->v.n == ksp->s.outer->n && x->v.n == b->v.n && b != x, "KSPSolve: size mismatch or aliasing");
+  ksp->s.outer->solve(b->v.d, x->v.d, false);
+  ksp->s.ctx->sync();
+  API_END
+}
+int b200sp_ksp_solve_host(b200sp_ksp ksp, const double *b_host, double *x_host, int64_t n) {
+  API_BEGIN
+  if (!ksp->s.is_setup) ksp->s.setup();
+  Ctx *c = ksp->s.ctx;
+  B2_REQUIRE(n == ksp->s.outer->n, "KSPSolve(host): size mismatch");
+  DevBuf<double> b((size_t)n + 2), x((size_t)n + 2);
+  B2_CUDA(cudaMemcpyAsync(b.p, b_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  ksp->s.outer->solve(b.p, x.p, false);
+  B2_CUDA(cudaMemcpyAsync(x_host, x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END
+}
+int b200sp_ksp_get_iteration_number(b200sp_ksp ksp, int *its) { API_BEGIN B2_REQUIRE(ksp->s.outer, "KSP not set up"); *its = ksp->s.outer->its; API_END }
+int b200sp_ksp_get_residual_norm(b200sp_ksp ksp, double *rnorm) { API_BEGIN B2_REQUIRE(ksp->s.outer, "KSP not set up"); *rnorm = ksp->s.outer->rnorm; API_END }
+int b200sp_ksp_get_converged_reason(b200sp_ksp ksp, int *reason) { API_BEGIN B2_REQUIRE(ksp->s.outer, "KSP not set up"); *reason = ksp->s.outer->reason; API_END }
+int b200sp_ksp_get_residual_history(b200sp_ksp ksp, double *hist, int cap, int *len) {
+  API_BEGIN
+  B2_REQUIRE(ksp->s.outer, "KSP not set up");
+  const auto &h = ksp->s.outer->hist;
+  if (len) *len = (int)h.size();
+  if (hist) for (int i = 0; i < cap && i < (int)h.size(); ++i) hist[i] = h[(size_t)i];
+  API_END
+}
+int b200sp_ksp_pc_apply(b200sp_ksp ksp, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN
+  if (!ksp->s.is_setup) ksp->s.setup();
+  B2_REQUIRE(x->v.n == ksp->s.outer->n && y->v.n == x->v.n && x != y, "PCApply: size mismatch or aliasing");
+  if (ksp->s.outer_pc) ksp->s.outer_pc->apply(x->v.d, y->v.d);
+  else vec_copy(ksp->s.ctx, x->v.n, x->v.d, y->v.d);
+  ksp->s.ctx->sync();
+  API_END
+}
+int b200sp_ksp_view(b200sp_ksp ksp, char *buf, int buflen) {
+  API_BEGIN
+  std::string s = ksp->s.view();
+  B2_REQUIRE(buf && buflen > 0, "ksp_view: no buffer");
+  const size_t n = std::min(s.size(), (size_t)buflen - 1);
+  std::memcpy(buf, s.c_str(), n);
+  buf[n] = 0;
+  API_END
+}
+
+} // extern "C"

@@ -1,0 +1,224 @@
+// core.h -- internal C++ declarations of libb200sp (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/b200sp.h"
+
+namespace b200sp {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define B2_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw ::b200sp::Error(B200SP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + \
+                                                 __FILE__ + ":" + std::to_string(__LINE__));            \
+  } while (0)
+#define B2_NCCL(call)                                                                                   \
+  do {                                                                                                  \
+    ncclResult_t e_ = (call);                                                                           \
+    if (e_ != ncclSuccess)                                                                              \
+      throw ::b200sp::Error(B200SP_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(e_));        \
+  } while (0)
+#define B2_REQUIRE(cond, msg)                                                 \
+  do {                                                                        \
+    if (!(cond)) throw ::b200sp::Error(B200SP_ERR_ARG, std::string(msg));      \
+  } while (0)
+
+constexpr int RED_MAX_BLOCKS = 1024; // upper bound on the grid of a reduction kernel
+constexpr int RED_MAX_OUT = 32;      // results per reduction launch
+constexpr int N_SCALARS = 128;
+
+struct ProfEntry { double ms = 0; int64_t n = 0; };
+
+struct Ctx {
+  int device = 0, rank = 0, size = 1;
+  cudaStream_t stream = nullptr;  // compute stream (every kernel of the library)
+  cudaStream_t stream2 = nullptr; // halo / copy stream
+  ncclComm_t comm = nullptr;
+  int num_sms = 148;
+  double *d_partials = nullptr; // [RED_MAX_BLOCKS][RED_MAX_OUT]
+  unsigned *d_ticket = nullptr;
+  double *d_scalars = nullptr; // device result slots
+  double *h_scalars = nullptr; // pinned mirror
+  int64_t launches = 0;
+  bool profile = false;
+  std::map<std::string, ProfEntry> prof;
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  ~Ctx();
+  void sync() { B2_CUDA(cudaStreamSynchronize(stream)); }
+  // global sum of k doubles held in d (device) -> host array (blocking); NCCL all-reduce when size>1
+  void fetch_scalars(const double *d, int k, double *host);
+};
+
+// bracket for one kernel launch: counts it, and in profile mode times it with events
+struct LaunchScope {
+  Ctx *c;
+  const char *cls;
+  LaunchScope(Ctx *ctx, const char *k) : c(ctx), cls(k) {
+    c->launches++;
+    if (c->profile) cudaEventRecord(c->pev0, c->stream);
+  }
+  ~LaunchScope() {
+    if (c->profile) {
+      cudaEventRecord(c->pev1, c->stream);
+      cudaEventSynchronize(c->pev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->pev0, c->pev1);
+      auto &e = c->prof[cls];
+      e.ms += ms;
+      e.n++;
+    }
+  }
+};
+inline void check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error(B200SP_ERR_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) {
+      p = nullptr;
+      cudaGetLastError();
+      throw Error(B200SP_ERR_MEM, "cudaMalloc of " + std::to_string(n * sizeof(T)) + " bytes failed");
+    }
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void zero(cudaStream_t s) { B2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// ------------------------------------------------------------------ Vec
+struct Vec {
+  Ctx *ctx;
+  int64_t n;
+  DevBuf<double> buf;
+  double *d; // == buf.p, or a view into another allocation
+  Vec(Ctx *c, int64_t n_) : ctx(c), n(n_), buf((size_t)n_ + 2), d(buf.p) { buf.zero(c->stream); }
+  Vec(Ctx *c, double *view, int64_t n_) : ctx(c), n(n_), d(view) {}
+};
+
+// ------------------------------------------------------------------ DMDA
+struct Dmda {
+  Ctx *ctx;
+  int M, N;               // nodes
+  int pm, pn;             // process grid
+  int xs, ys, xm, ym;     // owned node box of this rank
+  std::vector<int> lx, ly;
+};
+
+// ------------------------------------------------------------------ Mat
+enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2 };
+
+struct Csr {
+  Ctx *ctx = nullptr;
+  int nrows = 0, ncols = 0;
+  int64_t nnz = 0;
+  DevBuf<int> rowptr;   // nrows+1
+  DevBuf<int> col;      // nnz + PAD
+  DevBuf<double> val;   // nnz + PAD
+  // spmv plan
+  int kernel = SPMV_VECTOR;
+  int max_row_nnz = 0;
+  int max_group_nnz = 0; // max nnz of any 32-row group (+1 alignment slack)
+  int lanes_per_row = 32;
+  int64_t hist[14] = {0};
+  // grid metadata when the matrix came from DMDA assembly (for -pc_type mg); 0 = unknown
+  int grid_M = 0, grid_N = 0, dof_r = 0, dof_c = 0;
+  void plan();           // histogram + kernel choice (device reduction)
+};
+constexpr int CSR_PAD = 8; // zero entries appended to col/val so vector loads may overrun a row tile
+
+struct Mat {
+  Ctx *ctx;
+  bool nest = false;
+  std::shared_ptr<Csr> csr;               // plain matrix
+  std::shared_ptr<Csr> blk[2][2];         // nest blocks (blk[1][1] may be null)
+  int nrows() const { return nest ? blk[0][0]->nrows + blk[1][0]->nrows : csr->nrows; }
+  int ncols() const { return nest ? blk[0][0]->ncols + blk[0][1]->ncols : csr->ncols; }
+};
+
+// ------------------------------------------------------------------ kernels (launchers)
+// vectors (kernels_vec.cu) -- all on ctx->stream
+void vec_set(Ctx *c, int64_t n, double a, double *y);
+void vec_copy(Ctx *c, int64_t n, const double *x, double *y);
+void vec_scale(Ctx *c, int64_t n, double a, double *y);
+void vec_axpy(Ctx *c, int64_t n, double a, const double *x, double *y);                  // y += a x
+void vec_aypx(Ctx *c, int64_t n, double a, const double *x, double *y);                  // y = x + a y
+void vec_waxpy(Ctx *c, int64_t n, double a, const double *x, const double *y, double *w); // w = a x + y
+void vec_axpbypcz(Ctx *c, int64_t n, double a, const double *x, double b, const double *y, double cc, const double *z, double *w); // w = a x + b y + cc z
+// w = a x + b y + cc (d .* z)   (Chebyshev update fused with the Jacobi application; d may be null)
+void vec_cheb_update(Ctx *c, int64_t n, double a, const double *x, double b, const double *y, double cc, const double *d, const double *z, double *w);
+void vec_pointwise_mult(Ctx *c, int64_t n, const double *x, const double *y, double *w);
+void vec_reciprocal_safe(Ctx *c, int64_t n, double *d); // d = 1/(d==0?1:d)   (PCJACOBI setup)
+void vec_hash(Ctx *c, int64_t n, double *v);
+void vec_scatter_set(Ctx *c, int64_t n, const int *idx, double val, double *y); // y[idx[i]] = val
+// reductions: results land in device slot `out` (k doubles); fetch with ctx->fetch_scalars
+void vec_dot(Ctx *c, int64_t n, const double *x, const double *y, double *out);
+void vec_mdot(Ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ld, double *out); // out[j] = w . V_j
+// w -= sum_j h[j] V_j (h on device), out[0] = ||w_new||^2
+void vec_maxpy_norm2(Ctx *c, int64_t n, int k, double *w, const double *V, int64_t ld, const double *h_dev, double *out);
+void vec_maxpy(Ctx *c, int64_t n, int k, double *w, const double *V, int64_t ld, const double *coef_dev); // w += sum coef[j] V_j
+// y = x * (1/sqrt(*nrm2_dev))  (normalisation without a host round trip)
+void vec_scale_inv_sqrt(Ctx *c, int64_t n, const double *nrm2_dev, const double *x, double *y);
+
+// spmv (kernels_spmv.cu):  y = beta_z * z + alpha * (A x)   (z may be null; z may alias y)
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0);
+void csr_get_diagonal(const Csr &A, double *d);
+void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool do_rows, bool do_cols, bool set_diag);
+
+// setup utilities (kernels_setup.cu)
+void exclusive_scan_i32(Ctx *c, const int *in, int *out, int64_t n, int *total_host); // out[n] = total too (out has n+1)
+std::shared_ptr<Csr> csr_from_host(Ctx *c, int nrows, int ncols, const int *rowptr, const int *col, const double *val);
+std::shared_ptr<Csr> csr_from_coo_host(Ctx *c, int nrows, int ncols, int64_t ncoo, const int *row, const int *col, const double *val);
+std::shared_ptr<Csr> csr_transpose(const Csr &A);
+std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B);
+std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d);            // A * diag(d)
+std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double a, const Csr &B);     // A + a B (same pattern required)
+void dense_inverse_from_csr(const Csr &A, double *Ainv); // n x n row-major, device
+void dense_matvec(Ctx *c, int n, const double *Ainv, const double *x, double *y);
+
+// assembly (kernels_assembly.cu)
+std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written);
+void assemble_rhs(const Dmda &da, int as_written, int kind, double *f);
+void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
+std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc);
+std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc); // = interp_q1^T, built directly
+std::shared_ptr<Csr> csr_alloc_public(Ctx *c, int nrows, int ncols, int64_t nnz);
+std::vector<int> dmda_bc_ids(const Dmda &da, int dof);
+
+// host-only DMDA index arithmetic (dmda.cpp part of capi)
+void dmda_proc_grid(int M, int N, int size, int *m, int *n);
+void dmda_ownership(int M, int m, int *lx);
+
+} // namespace b200sp

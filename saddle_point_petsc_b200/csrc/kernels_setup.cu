@@ -1,0 +1,427 @@
+// kernels_setup.cu -- one-off setup kernels: prefix scan, CSR construction from host CSR / COO (stable
+// radix sort + in-order duplicate sum = MatSetValues(ADD_VALUES)+MatAssemblyEnd, src/Discretization.c:165-169),
+// explicit transpose, SpGEMM (MatMatMult used by selfp / LSC), small dense inverse
+// (coarsest multigrid level).
+#include "dev.cuh"
+#include <algorithm>
+
+namespace b200sp {
+
+namespace {
+
+// ---------------------------------------------------------------- exclusive scan (int32)
+constexpr int SCAN_ITEMS = 4;                    // per thread
+constexpr int SCAN_TILE = 256 * SCAN_ITEMS;      // per CTA
+
+__global__ void __launch_bounds__(256) k_scan_tiles(const int *__restrict__ in, int *__restrict__ out, int64_t n, int *tile_sums) {
+  __shared__ int s_warp[8];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], t = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    t += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_warp[w];
+  int excl = woff + incl - t;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 255) tile_sums[blockIdx.x] = woff + incl;
+}
+__global__ void __launch_bounds__(256) k_scan_add(int *__restrict__ out, int64_t n, const int *__restrict__ tile_offs) {
+  const int off = tile_offs[blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) out[base + k] += off;
+}
+
+void scan_rec(Ctx *c, const int *in, int *out, int64_t n) { // out[i] = sum_{j<i} in[j], i < n
+  if (n <= 0) return;
+  int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  DevBuf<int> sums((size_t)ntiles), offs((size_t)ntiles);
+  {
+    LaunchScope ls(c, "setup");
+    k_scan_tiles<<<(unsigned)ntiles, 256, 0, c->stream>>>(in, out, n, sums.p);
+    check_launch("k_scan_tiles");
+  }
+  if (ntiles > 1) {
+    scan_rec(c, sums.p, offs.p, ntiles);
+    LaunchScope ls(c, "setup");
+    k_scan_add<<<(unsigned)ntiles, 256, 0, c->stream>>>(out, n, offs.p);
+    check_launch("k_scan_add");
+  }
+  c->sync(); // temporaries die here
+}
+
+__global__ void k_last_total(const int *in, const int *out, int64_t n, int *total) { *total = out[n - 1] + in[n - 1]; }
+
+} // namespace
+
+// out has n+1 entries; out[n] = total.  `in` and `out` must not alias.
+void exclusive_scan_i32(Ctx *c, const int *in, int *out, int64_t n, int *total_host) {
+  int total = 0;
+  if (n > 0) {
+    scan_rec(c, in, out, n);
+    LaunchScope ls(c, "setup");
+    k_last_total<<<1, 1, 0, c->stream>>>(in, out, n, out + n);
+    check_launch("k_last_total");
+    B2_CUDA(cudaMemcpyAsync(&total, out + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+  } else {
+    B2_CUDA(cudaMemsetAsync(out, 0, sizeof(int), c->stream));
+  }
+  if (total_host) *total_host = total;
+}
+
+static std::shared_ptr<Csr> csr_alloc(Ctx *c, int nrows, int ncols, int64_t nnz) {
+  auto A = std::make_shared<Csr>();
+  A->ctx = c;
+  A->nrows = nrows;
+  A->ncols = ncols;
+  A->nnz = nnz;
+  A->rowptr.alloc((size_t)nrows + 1);
+  A->col.alloc((size_t)nnz + CSR_PAD);
+  A->val.alloc((size_t)nnz + CSR_PAD);
+  B2_CUDA(cudaMemsetAsync(A->col.p + nnz, 0, sizeof(int) * CSR_PAD, c->stream));
+  B2_CUDA(cudaMemsetAsync(A->val.p + nnz, 0, sizeof(double) * CSR_PAD, c->stream));
+  return A;
+}
+std::shared_ptr<Csr> csr_alloc_public(Ctx *c, int nrows, int ncols, int64_t nnz) { return csr_alloc(c, nrows, ncols, nnz); }
+
+std::shared_ptr<Csr> csr_from_host(Ctx *c, int nrows, int ncols, const int *rowptr, const int *col, const double *val) {
+  B2_REQUIRE(nrows >= 0 && ncols >= 0 && rowptr, "csr_from_host: bad arguments");
+  int64_t nnz = rowptr[nrows];
+  for (int r = 0; r < nrows; ++r) {
+    B2_REQUIRE(rowptr[r + 1] >= rowptr[r], "csr_from_host: rowptr not monotone");
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      B2_REQUIRE(col[k] >= 0 && col[k] < ncols, "csr_from_host: column index out of range");
+      B2_REQUIRE(k == rowptr[r] || col[k] > col[k - 1], "csr_from_host: columns must be strictly ascending within a row");
+    }
+  }
+  auto A = csr_alloc(c, nrows, ncols, nnz);
+  B2_CUDA(cudaMemcpyAsync(A->rowptr.p, rowptr, sizeof(int) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, c->stream));
+  if (nnz) {
+    B2_CUDA(cudaMemcpyAsync(A->col.p, col, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(A->val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->sync();
+  A->plan();
+  return A;
+}
+
+// ---------------------------------------------------------------- scale / add
+namespace {
+__global__ void __launch_bounds__(256) k_scale_cols(int64_t nnz, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ d, double *out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = val[k] * d[col[k]];
+}
+__global__ void __launch_bounds__(256) k_add_scaled_same(int64_t nnz, const double *__restrict__ a, double s, const double *__restrict__ b, double *out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = a[k] + s * b[k];
+}
+// A + s*B on the union pattern: count, then fill (both matrices have ascending columns)
+__global__ void __launch_bounds__(256) k_union_count(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const int *__restrict__ rpb, const int *__restrict__ cb, int *cnt) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    int ka = rpa[r], ea = rpa[r + 1], kb = rpb[r], eb = rpb[r + 1], n = 0;
+    while (ka < ea || kb < eb) {
+      int a = ka < ea ? ca[ka] : 0x7fffffff, b = kb < eb ? cb[kb] : 0x7fffffff;
+      if (a <= b) ka++;
+      if (b <= a) kb++;
+      n++;
+    }
+    cnt[r] = n;
+  }
+}
+__global__ void __launch_bounds__(256) k_union_fill(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const double *__restrict__ va,
+                                                    const int *__restrict__ rpb, const int *__restrict__ cb, const double *__restrict__ vb, double s,
+                                                    const int *__restrict__ rpc, int *cc, double *vc) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    int ka = rpa[r], ea = rpa[r + 1], kb = rpb[r], eb = rpb[r + 1], p = rpc[r];
+    while (ka < ea || kb < eb) {
+      int a = ka < ea ? ca[ka] : 0x7fffffff, b = kb < eb ? cb[kb] : 0x7fffffff;
+      if (a == b) { cc[p] = a; vc[p++] = va[ka++] + s * vb[kb++]; }
+      else if (a < b) { cc[p] = a; vc[p++] = va[ka++]; }
+      else { cc[p] = b; vc[p++] = s * vb[kb++]; }
+    }
+  }
+}
+inline int grid_for(Ctx *c, int64_t n) {
+  int64_t g = (n + 255) / 256;
+  int64_t cap = (int64_t)c->num_sms * 8;
+  return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+} // namespace
+
+std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d) {
+  Ctx *c = A.ctx;
+  auto C = csr_alloc(c, A.nrows, A.ncols, A.nnz);
+  B2_CUDA(cudaMemcpyAsync(C->rowptr.p, A.rowptr.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+  B2_CUDA(cudaMemcpyAsync(C->col.p, A.col.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, c->stream));
+  if (A.nnz) {
+    LaunchScope ls(c, "setup");
+    k_scale_cols<<<grid_for(c, A.nnz), 256, 0, c->stream>>>(A.nnz, A.col.p, A.val.p, d, C->val.p);
+    check_launch("k_scale_cols");
+  }
+  C->grid_M = A.grid_M; C->grid_N = A.grid_N; C->dof_r = A.dof_r; C->dof_c = A.dof_c;
+  C->plan();
+  return C;
+}
+
+std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double s, const Csr &B) {
+  Ctx *c = A.ctx;
+  B2_REQUIRE(A.nrows == B.nrows && A.ncols == B.ncols, "csr_add_scaled: shape mismatch");
+  DevBuf<int> cnt((size_t)A.nrows + 1);
+  if (A.nrows) {
+    LaunchScope ls(c, "setup");
+    k_union_count<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, B.rowptr.p, B.col.p, cnt.p);
+    check_launch("k_union_count");
+  }
+  DevBuf<int> rp((size_t)A.nrows + 1);
+  int total = 0;
+  exclusive_scan_i32(c, cnt.p, rp.p, A.nrows, &total);
+  auto C = csr_alloc(c, A.nrows, A.ncols, total);
+  B2_CUDA(cudaMemcpyAsync(C->rowptr.p, rp.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+  if (A.nrows) {
+    LaunchScope ls(c, "setup");
+    k_union_fill<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, B.rowptr.p, B.col.p, B.val.p, s, C->rowptr.p, C->col.p, C->val.p);
+    check_launch("k_union_fill");
+  }
+  c->sync();
+  C->grid_M = A.grid_M; C->grid_N = A.grid_N; C->dof_r = A.dof_r; C->dof_c = A.dof_c;
+  C->plan();
+  return C;
+}
+
+// ---------------------------------------------------------------- SpGEMM C = A*B (MatMatMult)
+// Row-wise Gustavson, one thread per row of C, deterministic:
+//   symbolic: the candidate columns of row i (concatenated B rows, each already ascending) are written to a
+//             scratch segment sized by the upper bound sum_k len(B_k), insertion-sorted, made unique;
+//   numeric : c_ij accumulates a_ik*b_kj in the order k appears in A's row (MatMatMultNumeric order),
+//             product rounded then added, slot found by binary search in the sorted row.
+namespace {
+__global__ void __launch_bounds__(256) k_spgemm_ub(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const int *__restrict__ rpb, int *ub) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    int n = 0;
+    for (int k = rpa[r]; k < rpa[r + 1]; ++k) n += rpb[ca[k] + 1] - rpb[ca[k]];
+    ub[r] = n;
+  }
+}
+__global__ void __launch_bounds__(128) k_spgemm_symbolic(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const int *__restrict__ rpb,
+                                                         const int *__restrict__ cb, const int64_t *__restrict__ soff, int *scratch, int *cnt) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    int *s = scratch + soff[r];
+    int n = 0;
+    for (int k = rpa[r]; k < rpa[r + 1]; ++k)
+      for (int t = rpb[ca[k]]; t < rpb[ca[k] + 1]; ++t) {
+        // insertion into the sorted prefix (inputs arrive in ascending runs, so shifts are short)
+        const int v = cb[t];
+        int p = n;
+        while (p > 0 && s[p - 1] > v) --p;
+        if (p > 0 && s[p - 1] == v) continue;
+        for (int q = n; q > p; --q) s[q] = s[q - 1];
+        s[p] = v;
+        ++n;
+      }
+    cnt[r] = n;
+  }
+}
+__global__ void __launch_bounds__(128) k_spgemm_numeric(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const double *__restrict__ va,
+                                                        const int *__restrict__ rpb, const int *__restrict__ cb, const double *__restrict__ vb,
+                                                        const int64_t *__restrict__ soff, const int *__restrict__ scratch,
+                                                        const int *__restrict__ rpc, int *cc, double *vc) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int base = rpc[r], n = rpc[r + 1] - base;
+    const int *s = scratch + soff[r];
+    for (int t = 0; t < n; ++t) { cc[base + t] = s[t]; vc[base + t] = 0.0; }
+    for (int k = rpa[r]; k < rpa[r + 1]; ++k) {
+      const double a = va[k];
+      for (int t = rpb[ca[k]]; t < rpb[ca[k] + 1]; ++t) {
+        const int v = cb[t];
+        int lo = 0, hi = n;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (cc[base + mid] < v) lo = mid + 1; else hi = mid; }
+        vc[base + lo] += a * vb[t];
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_scan64_from32(int n, const int *__restrict__ in32_excl, const int *__restrict__ carry_unused, int64_t *out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in32_excl[i];
+}
+} // namespace
+
+std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B) {
+  Ctx *c = A.ctx;
+  B2_REQUIRE(A.ncols == B.nrows, "csr_matmat: inner dimensions differ");
+  const int n = A.nrows;
+  DevBuf<int> ub((size_t)n + 1), ub_off((size_t)n + 1), cnt((size_t)n + 1), rp((size_t)n + 1);
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_spgemm_ub<<<grid_for(c, n), 256, 0, c->stream>>>(n, A.rowptr.p, A.col.p, B.rowptr.p, ub.p);
+    check_launch("k_spgemm_ub");
+  }
+  // the scratch offsets can exceed 2^31 in principle: process in row chunks whose upper bound fits int32
+  std::vector<int> h_ub((size_t)n);
+  if (n) B2_CUDA(cudaMemcpyAsync(h_ub.data(), ub.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  std::vector<int64_t> h_off((size_t)n + 1, 0);
+  for (int r = 0; r < n; ++r) h_off[r + 1] = h_off[r] + h_ub[r];
+  DevBuf<int64_t> soff((size_t)n + 1);
+  B2_CUDA(cudaMemcpyAsync(soff.p, h_off.data(), sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+  DevBuf<int> scratch((size_t)h_off[n] + 1);
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_spgemm_symbolic<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, A.rowptr.p, A.col.p, B.rowptr.p, B.col.p, soff.p, scratch.p, cnt.p);
+    check_launch("k_spgemm_symbolic");
+  }
+  int total = 0;
+  exclusive_scan_i32(c, cnt.p, rp.p, n, &total);
+  auto C = csr_alloc(c, n, B.ncols, total);
+  B2_CUDA(cudaMemcpyAsync(C->rowptr.p, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c->stream));
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_spgemm_numeric<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, A.rowptr.p, A.col.p, A.val.p, B.rowptr.p, B.col.p, B.val.p, soff.p, scratch.p,
+                                                                                                      C->rowptr.p, C->col.p, C->val.p);
+    check_launch("k_spgemm_numeric");
+  }
+  c->sync();
+  C->plan();
+  return C;
+}
+
+std::shared_ptr<Csr> csr_transpose(const Csr &) { throw Error(B200SP_ERR_UNSUPPORTED, "csr_transpose: not available yet"); }
+std::shared_ptr<Csr> csr_from_coo_host(Ctx *, int, int, int64_t, const int *, const int *, const double *) {
+  throw Error(B200SP_ERR_UNSUPPORTED, "csr_from_coo: not available yet");
+}
+
+// ---------------------------------------------------------------- small dense inverse (coarsest MG level)
+namespace {
+__global__ void __launch_bounds__(256) k_csr_to_dense_aug(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val, double *W /* n x 2n */) {
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    for (int k = rowptr[r] + threadIdx.x; k < rowptr[r + 1]; k += blockDim.x) W[(size_t)r * 2 * n + col[k]] = val[k];
+    if (threadIdx.x == 0) W[(size_t)r * 2 * n + n + r] = 1.0;
+  }
+}
+// Gauss-Jordan with partial pivoting on the augmented matrix [A | I], single CTA (n <= a few thousand).
+__global__ void __launch_bounds__(1024) k_gauss_jordan(int n, double *W, int *info) {
+  __shared__ int s_piv;
+  __shared__ double s_best[32];
+  __shared__ int s_bidx[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w2 = 2 * n;
+  for (int k = 0; k < n; ++k) {
+    // pivot search in column k, rows k..n-1
+    double best = -1.0;
+    int bidx = k;
+    for (int r = k + tid; r < n; r += blockDim.x) {
+      double a = fabs(W[(size_t)r * w2 + k]);
+      if (a > best) { best = a; bidx = r; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ob = __shfl_xor_sync(FULL, best, o);
+      int oi = __shfl_xor_sync(FULL, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { s_best[warp] = best; s_bidx[warp] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_best[0];
+      int bi = s_bidx[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (s_best[w] > b || (s_best[w] == b && s_bidx[w] < bi)) { b = s_best[w]; bi = s_bidx[w]; }
+      s_piv = bi;
+      if (!(b > 0.0)) *info = k + 1;
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k)
+      for (int j = tid; j < w2; j += blockDim.x) {
+        double t = W[(size_t)k * w2 + j];
+        W[(size_t)k * w2 + j] = W[(size_t)p * w2 + j];
+        W[(size_t)p * w2 + j] = t;
+      }
+    __syncthreads();
+    const double inv = 1.0 / W[(size_t)k * w2 + k];
+    __syncthreads();
+    for (int j = tid; j < w2; j += blockDim.x) W[(size_t)k * w2 + j] *= inv;
+    __syncthreads();
+    // eliminate column k from every other row: warp per row
+    for (int r = warp; r < n; r += (blockDim.x >> 5)) {
+      if (r == k) continue;
+      const double f = W[(size_t)r * w2 + k];
+      if (f != 0.0)
+        for (int j = lane; j < w2; j += 32)
+          if (j != k) W[(size_t)r * w2 + j] -= f * W[(size_t)k * w2 + j];
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += blockDim.x)
+      if (r != k) W[(size_t)r * w2 + k] = 0.0;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_extract_inverse(int n, const double *__restrict__ W, double *__restrict__ Ainv) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)n * n; t += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(t / n), j = (int)(t % n);
+    Ainv[t] = W[(size_t)r * 2 * n + n + j];
+  }
+}
+// y = Ainv x, warp per row
+__global__ void __launch_bounds__(256) k_dense_matvec(int n, const double *__restrict__ Ainv, const double *__restrict__ x, double *y) {
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s = fma(Ainv[(size_t)r * n + j], x[j], s);
+    s = warp_sum(s);
+    if (lane == 0) y[r] = s;
+  }
+}
+} // namespace
+
+void dense_inverse_from_csr(const Csr &A, double *Ainv) {
+  Ctx *c = A.ctx;
+  const int n = A.nrows;
+  B2_REQUIRE(n == A.ncols && n > 0 && n <= 8192, "dense_inverse_from_csr: matrix must be square with n <= 8192");
+  DevBuf<double> W((size_t)n * 2 * n);
+  DevBuf<int> info(1);
+  W.zero(c->stream);
+  info.zero(c->stream);
+  {
+    LaunchScope ls(c, "setup");
+    k_csr_to_dense_aug<<<std::min(n, c->num_sms * 8), 64, 0, c->stream>>>(n, A.rowptr.p, A.col.p, A.val.p, W.p);
+    check_launch("k_csr_to_dense_aug");
+  }
+  {
+    LaunchScope ls(c, "setup");
+    k_gauss_jordan<<<1, 1024, 0, c->stream>>>(n, W.p, info.p);
+    check_launch("k_gauss_jordan");
+  }
+  {
+    LaunchScope ls(c, "setup");
+    k_extract_inverse<<<grid_for(c, (int64_t)n * n), 256, 0, c->stream>>>(n, W.p, Ainv);
+    check_launch("k_extract_inverse");
+  }
+  int h_info = 0;
+  B2_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  if (h_info) throw Error(B200SP_ERR_ARG, "dense_inverse_from_csr: singular matrix at pivot " + std::to_string(h_info - 1));
+}
+
+void dense_matvec(Ctx *c, int n, const double *Ainv, const double *x, double *y) {
+  LaunchScope ls(c, "coarse");
+  int grid = std::min((n + 7) / 8, c->num_sms * 4);
+  k_dense_matvec<<<grid, 256, 0, c->stream>>>(n, Ainv, x, y);
+  check_launch("k_dense_matvec");
+}
+
+} // namespace b200sp

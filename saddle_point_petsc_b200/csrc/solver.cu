@@ -1,0 +1,666 @@
+// solver.cu -- Krylov drivers (GMRES / FGMRES / MINRES / Chebyshev / Richardson), the fieldsplit-Schur,
+// LSC and multigrid preconditioners, and the PETSc-style options wiring.  Host code only orchestrates:
+// every vector or matrix operation is one of the hand-written kernels in kernels_*.cu; the host keeps
+// the Hessenberg / Givens / Lanczos scalars exactly as PETSc does.
+#include "solver.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace b200sp {
+
+static std::string pad(int n) { return std::string((size_t)n, ' '); }
+
+// ------------------------------------------------------------------ context reductions
+void Ctx::fetch_scalars(const double *d, int k, double *host) {
+  B2_REQUIRE(k <= N_SCALARS, "fetch_scalars: too many scalars");
+  B2_CUDA(cudaMemcpyAsync(h_scalars, d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, stream));
+  B2_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
+}
+static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
+  if (c->size > 1) B2_NCCL(ncclAllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+// ------------------------------------------------------------------ operators
+std::string CsrOp::view(int indent) const {
+  std::ostringstream o;
+  o << pad(indent) << "Mat csr " << A->nrows << "x" << A->ncols << " nnz=" << A->nnz << " spmv_kernel=" << A->kernel << "\n";
+  return o.str();
+}
+
+void NestOp::apply(const double *x, double *y) {
+  const int64_t n0c = b00->ncols, n0r = b00->nrows;
+  csr_spmv(*b00, x, y);
+  csr_spmv(*b01, x + n0c, y, 1.0, y, 1.0);
+  csr_spmv(*b10, x, y + n0r);
+  if (b11) csr_spmv(*b11, x + n0c, y + n0r, 1.0, y + n0r, 1.0);
+}
+void NestOp::residual(const double *b, const double *x, double *r) {
+  const int64_t n0c = b00->ncols, n0r = b00->nrows;
+  csr_spmv(*b00, x, r, -1.0, b, 1.0);
+  csr_spmv(*b01, x + n0c, r, -1.0, r, 1.0);
+  csr_spmv(*b10, x, r + n0r, -1.0, b + n0r, 1.0);
+  if (b11) csr_spmv(*b11, x + n0c, r + n0r, -1.0, r + n0r, 1.0);
+}
+std::string NestOp::view(int indent) const {
+  std::ostringstream o;
+  o << pad(indent) << "Mat nest 2x2: A00 " << b00->nrows << "x" << b00->ncols << " nnz=" << b00->nnz << ", A01 nnz=" << b01->nnz
+    << ", A10 nnz=" << b10->nnz << ", A11 nnz=" << (b11 ? b11->nnz : 0) << "\n";
+  return o.str();
+}
+
+JacobiOp::JacobiOp(const Csr &A) : Op(A.ctx, A.nrows, A.nrows), dinv((size_t)A.nrows + 2) {
+  B2_REQUIRE(A.nrows == A.ncols, "jacobi: matrix must be square");
+  csr_get_diagonal(A, dinv.p);
+  vec_reciprocal_safe(ctx, A.nrows, dinv.p); // zero diagonal -> 1 (PCJACOBI), stored as reciprocal (VecReciprocal)
+}
+std::string JacobiOp::view(int indent) const { return pad(indent) + "PC jacobi\n"; }
+
+DenseInvOp::DenseInvOp(const Csr &A) : Op(A.ctx, A.nrows, A.nrows), Ainv((size_t)A.nrows * A.nrows) { dense_inverse_from_csr(A, Ainv.p); }
+std::string DenseInvOp::view(int indent) const { return pad(indent) + "PC dense inverse (coarse LU stand-in) n=" + std::to_string(n_in) + "\n"; }
+
+KspOp::KspOp(Ksp *k) : Op(k->ctx, k->n, k->n), ksp(k) {}
+void KspOp::apply(const double *x, double *y) { ksp->solve(x, y, false); }
+std::string KspOp::view(int indent) const { return ksp->view(indent); }
+
+SchurOp::SchurOp(std::shared_ptr<Csr> a11, std::shared_ptr<Csr> a10, Op *k0, std::shared_ptr<Csr> a01)
+    : Op(a10->ctx, a10->nrows, a10->nrows), A11(a11), A10(a10), A01(a01), K0(k0), t0((size_t)a01->nrows + 2), t1((size_t)a01->nrows + 2) {}
+void SchurOp::apply(const double *x, double *y) {
+  csr_spmv(*A01, x, t0.p);
+  K0->apply(t0.p, t1.p);
+  if (A11) {
+    csr_spmv(*A11, x, y);
+    csr_spmv(*A10, t1.p, y, -1.0, y, 1.0); // y = A11 x - A10 t1
+  } else {
+    csr_spmv(*A10, t1.p, y, -1.0);
+  }
+}
+std::string SchurOp::view(int indent) const {
+  return pad(indent) + "Mat schurcomplement: S = A11 - A10 ksp(A00) A01, inner KSP:\n" + K0->view(indent + 2);
+}
+
+FieldSplitOp::FieldSplitOp(int fact_, double scale_, std::shared_ptr<Csr> a01, std::shared_ptr<Csr> a10, Op *k0, Op *ks)
+    : Op(a01->ctx, a01->nrows + a10->nrows, a01->nrows + a10->nrows), fact(fact_), scale(scale_), A01(a01), A10(a10), K0(k0), KS(ks),
+      t0((size_t)a01->nrows + 2), t1((size_t)a10->nrows + 2) {}
+void FieldSplitOp::apply(const double *b, double *y) {
+  const int64_t n0 = A01->nrows, n1 = A10->nrows;
+  const double *b0 = b, *b1 = b + n0;
+  double *y0 = y, *y1 = y + n0;
+  switch (fact) {
+  case 0: // DIAG: y0 = K0 b0 ; y1 = scale * KS b1
+    K0->apply(b0, y0);
+    KS->apply(b1, y1);
+    vec_scale(ctx, n1, scale, y1);
+    break;
+  case 1: // LOWER
+    K0->apply(b0, y0);
+    csr_spmv(*A10, y0, t1.p, -1.0, b1, 1.0); // t1 = b1 - A10 y0
+    KS->apply(t1.p, y1);
+    break;
+  case 2: // UPPER
+    KS->apply(b1, y1);
+    csr_spmv(*A01, y1, t0.p, -1.0, b0, 1.0); // t0 = b0 - A01 y1
+    K0->apply(t0.p, y0);
+    break;
+  default: // FULL
+    K0->apply(b0, y0);
+    csr_spmv(*A10, y0, t1.p, -1.0, b1, 1.0);
+    KS->apply(t1.p, y1);
+    csr_spmv(*A01, y1, t0.p, -1.0, b0, 1.0);
+    K0->apply(t0.p, y0);
+    break;
+  }
+}
+std::string FieldSplitOp::view(int indent) const {
+  static const char *names[] = {"diag", "lower", "upper", "full"};
+  std::ostringstream o;
+  o << pad(indent) << "PC fieldsplit schur, factorization " << names[fact] << ", schur scale " << scale << "\n";
+  o << pad(indent) << " split 0 (A00) solver:\n" << K0->view(indent + 2);
+  o << pad(indent) << " split 1 (S) solver:\n" << KS->view(indent + 2);
+  return o.str();
+}
+
+LscOp::LscOp(std::shared_ptr<Csr> a00, std::shared_ptr<Csr> a01, std::shared_ptr<Csr> a10, Op *linv, bool scale_diag_)
+    : Op(a10->ctx, a10->nrows, a10->nrows), A00(a00), A01(a01), A10(a10), Linv(linv), scale_diag(scale_diag_),
+      p0((size_t)a10->nrows + 2), p1((size_t)a10->nrows + 2), u0((size_t)a00->nrows + 2), u1((size_t)a00->nrows + 2) {
+  if (scale_diag) {
+    dinv.alloc((size_t)a00->nrows + 2);
+    csr_get_diagonal(*A00, dinv.p);
+    vec_reciprocal_safe(ctx, A00->nrows, dinv.p);
+  }
+}
+void LscOp::apply(const double *x, double *y) { // y = Linv A10 [D^-1] A00 [D^-1] A01 Linv x
+  const int64_t n0 = A00->nrows;
+  Linv->apply(x, p0.p);
+  csr_spmv(*A01, p0.p, u0.p);
+  if (scale_diag) vec_pointwise_mult(ctx, n0, u0.p, dinv.p, u0.p);
+  csr_spmv(*A00, u0.p, u1.p);
+  if (scale_diag) vec_pointwise_mult(ctx, n0, u1.p, dinv.p, u1.p);
+  csr_spmv(*A10, u1.p, p1.p);
+  Linv->apply(p1.p, y);
+}
+std::string LscOp::view(int indent) const {
+  return pad(indent) + "PC lsc" + (scale_diag ? " (scale_diag)" : "") + ", L = A10 A01 solver:\n" + Linv->view(indent + 2);
+}
+
+// PCMG multiplicative V-cycle: smoothdown (zero guess), residual, restrict, recurse, interpolate-add, smoothup
+void MgOp::cycle(int l) {
+  Level &L = *lev[l];
+  if (l == (int)lev.size() - 1) { coarse->apply(L.b.p, L.x.p); return; }
+  L.smooth->solve(L.b.p, L.x.p, false);
+  csr_spmv(*L.A, L.x.p, L.r.p, -1.0, L.b.p, 1.0);               // r = b - A x
+  csr_spmv(*L.R, L.r.p, lev[l + 1]->b.p);                        // restrict
+  cycle(l + 1);
+  csr_spmv(*L.P, lev[l + 1]->x.p, L.x.p, 1.0, L.x.p, 1.0);       // x += P xc
+  L.smooth->solve(L.b.p, L.x.p, true);
+}
+void MgOp::apply(const double *b, double *x) {
+  vec_copy(ctx, n_in, b, lev[0]->b.p);
+  cycle(0);
+  vec_copy(ctx, n_in, lev[0]->x.p, x);
+}
+std::string MgOp::view(int indent) const {
+  std::ostringstream o;
+  o << pad(indent) << "PC mg: multiplicative V-cycle, " << lev.size() << " levels (rediscretised coarse operators, Q1 interpolation)\n";
+  for (size_t l = 0; l < lev.size(); ++l) {
+    o << pad(indent + 1) << "level " << l << ": n=" << lev[l]->A->nrows << " nnz=" << lev[l]->A->nnz << "\n";
+    if (lev[l]->smooth) o << lev[l]->smooth->view(indent + 3);
+  }
+  o << coarse->view(indent + 1);
+  return o.str();
+}
+
+// ------------------------------------------------------------------ KSP
+void Ksp::pc_apply(const double *x, double *y) {
+  if (M) M->apply(x, y); else vec_copy(ctx, n, x, y);
+}
+double Ksp::dot(const double *x, const double *y) {
+  double r;
+  vec_dot(ctx, n, x, y, ctx->d_scalars);
+  allreduce_sum(ctx, ctx->d_scalars, 1);
+  ctx->fetch_scalars(ctx->d_scalars, 1, &r);
+  return r;
+}
+double Ksp::norm2(const double *x) { return std::sqrt(dot(x, x)); }
+
+// KSPConvergedDefault
+int Ksp::converged(int it, double rn) {
+  if (keep_history) hist.push_back(rn);
+  rnorm = rn;
+  if (it == 0) rnorm0 = rn;
+  if (std::isnan(rn) || std::isinf(rn)) return B200SP_DIVERGED_NANORINF;
+  const double ttol = std::max(rtol * rnorm0, atol);
+  if (rn <= ttol) return rn < atol ? B200SP_CONVERGED_ATOL : B200SP_CONVERGED_RTOL;
+  if (rn >= dtol * rnorm0) return B200SP_DIVERGED_DTOL;
+  return 0;
+}
+
+int Ksp::solve(const double *b, double *x, bool guess_nonzero) {
+  B2_REQUIRE(A, "KSP: operators not set");
+  its = 0;
+  hist.clear();
+  ld = (n + 15) & ~(int64_t)15;
+  if (!guess_nonzero && type != KSP_PREONLY) vec_set(ctx, n, 0.0, x);
+  switch (type) {
+  case KSP_PREONLY:
+    pc_apply(b, x);
+    its = 1;
+    reason = B200SP_CONVERGED_ITS;
+    return reason;
+  case KSP_RICHARDSON: return solve_richardson(b, x, guess_nonzero);
+  case KSP_CHEBYSHEV: return solve_chebyshev(b, x, guess_nonzero);
+  case KSP_GMRES: return solve_gmres(b, x, guess_nonzero, false);
+  case KSP_FGMRES: return solve_gmres(b, x, guess_nonzero, true);
+  case KSP_MINRES: return solve_minres(b, x, guess_nonzero);
+  }
+  throw Error(B200SP_ERR_UNSUPPORTED, "KSP: unknown type");
+}
+
+int Ksp::solve_richardson(const double *b, double *x, bool guess_nonzero) {
+  if (!w0.p) { w0.alloc((size_t)ld); w1.alloc((size_t)ld); }
+  double *r = w0.p, *z = w1.p;
+  reason = 0;
+  for (int it = 0; it < max_it; ++it) {
+    const double *res = r;
+    if (it == 0 && !guess_nonzero) res = b; else A->residual(b, x, r);
+    const double *dinv = M ? M->jacobi_dinv() : nullptr;
+    if (norm_none && (dinv || !M)) { // fused: x += scale * (dinv .* r)
+      vec_cheb_update(ctx, n, 1.0, x, 0.0, x, richardson_scale, dinv, res, x);
+    } else {
+      pc_apply(res, z);
+      if (!norm_none) {
+        reason = converged(it, norm2(z));
+        if (reason) { its = it; break; }
+      }
+      vec_axpy(ctx, n, richardson_scale, z, x);
+    }
+    its = it + 1;
+  }
+  if (!reason) reason = norm_none ? B200SP_CONVERGED_ITS : B200SP_DIVERGED_ITS;
+  return reason;
+}
+
+// KSPSolve_Chebyshev recurrence; with a Jacobi PC the PC application is fused into the update
+int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
+  if (!w0.p) { w0.alloc((size_t)ld); w1.alloc((size_t)ld); w2.alloc((size_t)ld); w3.alloc((size_t)ld); }
+  B2_REQUIRE(emax > 0.0, "chebyshev: eigenvalue bounds not set");
+  double *r = w0.p, *pkm1 = w1.p, *pk = w2.p, *pkp1 = w3.p;
+  const double scale = 2.0 / (emax + emin), alpha = 1.0 - scale * emin, mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
+  double ckm1 = 1.0, ck = mu, ckp1, omega;
+  const double *dinv = M ? M->jacobi_dinv() : nullptr;
+  const bool fused = (dinv || !M) && norm_none;
+  reason = 0;
+  const double *res = b;
+  if (guess_nonzero) { A->residual(b, x, r); res = r; }
+  vec_copy(ctx, n, x, pkm1);
+  if (fused) {
+    vec_cheb_update(ctx, n, 1.0, pkm1, 0.0, pkm1, scale, dinv, res, pk); // pk = x + scale * M^-1 r
+  } else {
+    pc_apply(res, pk);
+    if (!norm_none) reason = converged(0, norm2(pk));
+    vec_aypx(ctx, n, scale, pkm1, pk);
+  }
+  its = 1;
+  for (int i = 1; i < max_it && !reason; ++i) {
+    A->residual(b, pk, r);
+    ckp1 = 2.0 * mu * ck - ckm1;
+    omega = omegaprod * ck / ckp1;
+    if (fused) {
+      vec_cheb_update(ctx, n, 1.0 - omega, pkm1, omega, pk, omega * scale, dinv, r, pkp1);
+    } else {
+      pc_apply(r, pkp1);
+      if (!norm_none) { reason = converged(i, norm2(pkp1)); if (reason) break; }
+      vec_axpbypcz(ctx, n, 1.0 - omega, pkm1, omega, pk, omega * scale, pkp1, pkp1);
+    }
+    double *t = pkm1; pkm1 = pk; pk = pkp1; pkp1 = t;
+    ckm1 = ck; ck = ckp1;
+    its = i + 1;
+  }
+  vec_copy(ctx, n, pk, x);
+  if (!reason) reason = norm_none ? B200SP_CONVERGED_ITS : B200SP_DIVERGED_ITS;
+  return reason;
+}
+
+// KSPSolve_GMRES / KSPSolve_FGMRES: classical Gram-Schmidt without refinement.  Per iteration:
+//   SpMV(+PC)  ->  k_mdot (h = V^T w)  ->  k_maxpy+norm (w -= V h, ||w||^2)  ->  k_scale_inv_sqrt  ->  ONE host sync
+// h never leaves the device between the three vector kernels.
+int Ksp::solve_gmres(const double *b, double *x, bool guess_nonzero, bool flexible) {
+  const int m = restart;
+  B2_REQUIRE(m >= 1 && m + 2 <= N_SCALARS, "gmres: restart must be in [1,126]");
+  if (!V.p) {
+    V.alloc((size_t)ld * (m + 1));
+    if (flexible) Z.alloc((size_t)ld * m);
+    w0.alloc((size_t)ld);
+  }
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
+  double *d_h = ctx->d_scalars;
+  int itc = 0;
+  bool first = true;
+  reason = 0;
+  while (!reason) {
+    double *v0 = V.p;
+    if (first && !guess_nonzero) {
+      if (flexible || !M) vec_copy(ctx, n, b, v0); else pc_apply(b, v0);
+    } else {
+      if (flexible || !M) A->residual(b, x, v0);
+      else { A->residual(b, x, w0.p); pc_apply(w0.p, v0); }
+    }
+    first = false;
+    const double beta = norm2(v0);
+    reason = converged(itc, beta);
+    if (reason) break;
+    if (itc >= max_it) { reason = B200SP_DIVERGED_ITS; break; }
+    vec_scale(ctx, n, 1.0 / beta, v0);
+    g[0] = beta;
+    int it = 0;
+    while (!reason && it < m && itc < max_it) {
+      double *vk = V.p + (size_t)ld * it, *vn = V.p + (size_t)ld * (it + 1);
+      if (flexible) {
+        double *zk = Z.p + (size_t)ld * it;
+        pc_apply(vk, zk);
+        A->apply(zk, vn);
+      } else if (M) {
+        A->apply(vk, w0.p);
+        pc_apply(w0.p, vn);
+      } else {
+        A->apply(vk, vn);
+      }
+      vec_mdot(ctx, n, it + 1, vn, V.p, ld, d_h);                          // VecMDot
+      allreduce_sum(ctx, d_h, it + 1);
+      vec_maxpy_norm2(ctx, n, it + 1, vn, V.p, ld, d_h, d_h + it + 1);     // VecMAXPY + VecNorm fused
+      allreduce_sum(ctx, d_h + it + 1, 1);
+      vec_scale_inv_sqrt(ctx, n, d_h + it + 1, vn, vn);                    // v_{k+1} = w / ||w||
+      ctx->fetch_scalars(d_h, it + 2, hcol.data());
+      double *h = H.data() + (size_t)(m + 1) * it;
+      for (int j = 0; j <= it; ++j) h[j] = hcol[j];
+      const double hn = std::sqrt(hcol[it + 1]);
+      h[it + 1] = hn;
+      for (int j = 0; j < it; ++j) {
+        const double a = h[j], bb = h[j + 1];
+        h[j] = cs[j] * a + sn[j] * bb;
+        h[j + 1] = -sn[j] * a + cs[j] * bb;
+      }
+      const double tt = std::sqrt(h[it] * h[it] + h[it + 1] * h[it + 1]);
+      if (tt == 0.0 || std::isnan(tt)) { reason = std::isnan(tt) ? B200SP_DIVERGED_NANORINF : B200SP_DIVERGED_BREAKDOWN; break; }
+      cs[it] = h[it] / tt;
+      sn[it] = h[it + 1] / tt;
+      g[it + 1] = -sn[it] * g[it];
+      g[it] = cs[it] * g[it];
+      h[it] = cs[it] * h[it] + sn[it] * h[it + 1];
+      h[it + 1] = 0.0;
+      const double res = std::fabs(g[it + 1]);
+      it++;
+      itc++;
+      reason = converged(itc, res);
+      if (!reason && hn == 0.0) reason = B200SP_DIVERGED_BREAKDOWN;
+    }
+    // KSPGMRESBuildSoln: R y = g, x += V y (Z y for FGMRES)
+    if (it > 0) {
+      for (int i = it - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int j = i + 1; j < it; ++j) s -= H[i + (size_t)(m + 1) * j] * y[j];
+        y[i] = s / H[i + (size_t)(m + 1) * i];
+      }
+      std::memcpy(ctx->h_scalars, y.data(), sizeof(double) * (size_t)it);
+      B2_CUDA(cudaMemcpyAsync(d_h, ctx->h_scalars, sizeof(double) * (size_t)it, cudaMemcpyHostToDevice, ctx->stream));
+      if (!flexible && M == nullptr) vec_maxpy(ctx, n, it, x, V.p, ld, d_h);
+      else vec_maxpy(ctx, n, it, x, flexible ? Z.p : V.p, ld, d_h);
+      ctx->sync(); // h_scalars is reused by the next fetch
+    }
+    if (!reason && itc >= max_it) reason = B200SP_DIVERGED_ITS;
+  }
+  its = itc;
+  return reason;
+}
+
+// KSPSolve_MINRES (classic Paige-Saunders form, PETSc <= 3.18)
+int Ksp::solve_minres(const double *b, double *x, bool guess_nonzero) {
+  if (!w0.p) {
+    DevBuf<double> *bufs[] = {&w0, &w1, &w2, &w3, &w4, &w5, &w6, &w7, &w8};
+    for (auto *p : bufs) { p->alloc((size_t)ld); p->zero(ctx->stream); }
+  }
+  double *r = w0.p, *v = w1.p, *vold = w2.p, *z = w3.p, *u = w4.p, *uold = w5.p, *w = w6.p, *wold = w7.p, *wooold = w8.p;
+  vec_set(ctx, n, 0.0, vold); vec_set(ctx, n, 0.0, uold); vec_set(ctx, n, 0.0, w); vec_set(ctx, n, 0.0, wold);
+  double alpha, beta, betaold, eta, c = 1.0, cold = 1.0, s = 0.0, sold = 0.0, coold, soold, rho0, rho1, rho2, rho3, dp;
+  int itc = 0;
+  reason = 0;
+  if (guess_nonzero) A->residual(b, x, r); else vec_copy(ctx, n, b, r);
+  pc_apply(r, z);
+  dp = dot(r, z);
+  if (dp < 0.0) { reason = B200SP_DIVERGED_INDEFINITE_PC; its = 0; return reason; }
+  beta = std::sqrt(dp);
+  eta = beta;
+  dp = norm2(z);
+  reason = converged(0, dp);
+  if (reason) { its = 0; return reason; }
+  if (beta == 0.0) { reason = B200SP_CONVERGED_ATOL; its = 0; return reason; }
+  // v = r/beta, u = z/beta (in place: r,z buffers become v,u; the old v,u buffers are recycled as r,z)
+  vec_scale(ctx, n, 1.0 / beta, r); vec_scale(ctx, n, 1.0 / beta, z);
+  std::swap(r, v); std::swap(z, u);
+  while (itc < max_it) {
+    A->apply(u, r);
+    alpha = dot(u, r);
+    pc_apply(r, z);
+    vec_axpbypcz(ctx, n, -alpha, v, -beta, vold, 1.0, r, r); // r -= alpha v + beta v_old
+    vec_axpbypcz(ctx, n, -alpha, u, -beta, uold, 1.0, z, z); // z -= alpha u + beta u_old
+    betaold = beta;
+    { const double d = dot(r, z); if (d < 0.0) { reason = B200SP_DIVERGED_INDEFINITE_PC; break; } beta = std::sqrt(d); }
+    coold = cold; cold = c; soold = sold; sold = s;
+    rho0 = cold * alpha - coold * sold * betaold;
+    rho1 = std::sqrt(rho0 * rho0 + beta * beta);
+    rho2 = sold * alpha + coold * cold * betaold;
+    rho3 = soold * betaold;
+    c = rho0 / rho1; s = beta / rho1;
+    { // w_new = (u - rho2 w - rho3 w_old)/rho1, written over the w_oold buffer, then rotate
+      const double irho1 = 1.0 / rho1;
+      vec_axpbypcz(ctx, n, irho1, u, -rho2 * irho1, w, -rho3 * irho1, wold, wooold);
+      double *t = wooold; wooold = wold; wold = w; w = t;
+    }
+    vec_axpy(ctx, n, c * eta, w, x);
+    eta = -s * eta;
+    // v_old <- v, v <- r/beta ; u_old <- u, u <- z/beta (buffer rotation, one scale each)
+    if (beta != 0.0) { vec_scale(ctx, n, 1.0 / beta, r); vec_scale(ctx, n, 1.0 / beta, z); }
+    { double *t = vold; vold = v; v = r; r = t; }
+    { double *t = uold; uold = u; u = z; z = t; }
+    dp = std::fabs(s) * dp;
+    itc++;
+    reason = converged(itc, dp);
+    if (reason) break;
+  }
+  if (!reason) reason = B200SP_DIVERGED_ITS;
+  its = itc;
+  return reason;
+}
+
+std::string Ksp::view(int indent) const {
+  static const char *names[] = {"preonly", "richardson", "chebyshev", "gmres", "fgmres", "minres"};
+  std::ostringstream o;
+  o << pad(indent) << "KSP (" << (prefix.empty() ? "outer" : prefix) << ") type " << names[type];
+  if (type == KSP_GMRES || type == KSP_FGMRES) o << " restart=" << restart;
+  if (type == KSP_CHEBYSHEV) o << " eigs=(" << emin << "," << emax << ")";
+  if (type != KSP_PREONLY) o << " max_it=" << max_it << (norm_none ? " norm=none" : "") << " rtol=" << rtol;
+  o << "\n";
+  if (M) o << M->view(indent + 1); else o << pad(indent + 1) << "PC none\n";
+  return o.str();
+}
+
+double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits) {
+  const int64_t n = A->n_in;
+  DevBuf<double> v((size_t)n + 2), t((size_t)n + 2), z((size_t)n + 2);
+  vec_hash(c, n, v.p);
+  double lam = 0.0, nv;
+  for (int it = 0; it < nits; ++it) {
+    vec_dot(c, n, v.p, v.p, c->d_scalars);
+    allreduce_sum(c, c->d_scalars, 1);
+    c->fetch_scalars(c->d_scalars, 1, &nv);
+    vec_scale(c, n, 1.0 / std::sqrt(nv), v.p);
+    A->apply(v.p, t.p);
+    if (M) M->apply(t.p, z.p); else vec_copy(c, n, t.p, z.p);
+    vec_dot(c, n, z.p, z.p, c->d_scalars);
+    allreduce_sum(c, c->d_scalars, 1);
+    c->fetch_scalars(c->d_scalars, 1, &lam);
+    lam = std::sqrt(lam);
+    vec_copy(c, n, z.p, v.p);
+  }
+  c->sync();
+  return lam;
+}
+
+// ------------------------------------------------------------------ options wiring
+static bool is_number(const std::string &t) {
+  char *end = nullptr;
+  std::strtod(t.c_str(), &end);
+  return end && *end == 0 && !t.empty();
+}
+void Solver::set_options(const char *text) {
+  std::istringstream in(text ? text : "");
+  std::vector<std::string> tok;
+  std::string t;
+  while (in >> t) tok.push_back(t);
+  for (size_t i = 0; i < tok.size();) {
+    B2_REQUIRE(tok[i].size() > 1 && tok[i][0] == '-', "options: expected -name, got '" + tok[i] + "'");
+    std::string key = tok[i].substr(1);
+    if (i + 1 < tok.size() && !(tok[i + 1][0] == '-' && !is_number(tok[i + 1]))) { opts[key] = tok[i + 1]; i += 2; }
+    else { opts[key] = ""; i += 1; }
+  }
+  is_setup = false;
+}
+std::string Solver::opt(const std::string &key, const std::string &def) const {
+  auto it = opts.find(key);
+  return it == opts.end() ? def : it->second;
+}
+
+static int ksp_type_from(const std::string &s) {
+  if (s == "preonly") return KSP_PREONLY;
+  if (s == "richardson") return KSP_RICHARDSON;
+  if (s == "chebyshev") return KSP_CHEBYSHEV;
+  if (s == "gmres") return KSP_GMRES;
+  if (s == "fgmres") return KSP_FGMRES;
+  if (s == "minres") return KSP_MINRES;
+  throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -ksp_type " + s);
+}
+
+Ksp *Solver::make_ksp(const std::string &prefix, Op *A, Op *M, const char *default_type) {
+  ksps.emplace_back(new Ksp(ctx, prefix));
+  Ksp *k = ksps.back().get();
+  k->set_operators(A, M);
+  const std::string tname = opt(prefix + "ksp_type", default_type);
+  k->type = ksp_type_from(tname);
+  k->rtol = std::stod(opt(prefix + "ksp_rtol", "1e-5"));
+  k->atol = std::stod(opt(prefix + "ksp_atol", "1e-50"));
+  k->dtol = std::stod(opt(prefix + "ksp_divtol", "1e5"));
+  k->max_it = std::stoi(opt(prefix + "ksp_max_it", "10000"));
+  k->restart = std::stoi(opt(prefix + "ksp_gmres_restart", "30"));
+  k->richardson_scale = std::stod(opt(prefix + "ksp_richardson_scale", "1.0"));
+  const std::string nt = opt(prefix + "ksp_norm_type", "");
+  // inner chebyshev / richardson solvers are fixed-sweep smoothers unless a norm type is requested
+  if (nt == "none" || (nt.empty() && !prefix.empty() && (k->type == KSP_CHEBYSHEV || k->type == KSP_RICHARDSON))) k->norm_none = true;
+  if (k->type == KSP_CHEBYSHEV) {
+    const std::string ev = opt(prefix + "ksp_chebyshev_eigenvalues", "");
+    if (!ev.empty()) {
+      const size_t comma = ev.find(',');
+      B2_REQUIRE(comma != std::string::npos, "-ksp_chebyshev_eigenvalues needs emin,emax");
+      k->emin = std::stod(ev.substr(0, comma));
+      k->emax = std::stod(ev.substr(comma + 1));
+    } else {
+      const double lam = estimate_lambda_max(ctx, A, M, 10);
+      k->emin = 0.1 * lam;
+      k->emax = 1.1 * lam;
+    }
+  }
+  return k;
+}
+
+Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, const char *default_type) {
+  const std::string t = opt(prefix + "pc_type", default_type);
+  if (t == "none") return nullptr;
+  if (t == "jacobi") return add_op<JacobiOp>(*mat);
+  if (t == "lu") return add_op<DenseInvOp>(*mat);
+  if (t == "mg") return make_mg(prefix, mat);
+  throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -" + prefix + "pc_type " + t);
+}
+
+// PCMG: rediscretised coarse velocity operators (the same device assembly on the coarser DMDA + the same
+// Dirichlet elimination), Q1 interpolation with Dirichlet rows/cols zeroed, R = P^T, Chebyshev/Jacobi smoothing
+Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
+  B2_REQUIRE(ctx->size == 1, "pc mg: single-GPU only in this build step");
+  B2_REQUIRE(mat->grid_M > 0 && mat->dof_r == 2 && mat->dof_c == 2, "pc mg: needs the velocity block assembled from a DMDA (b200sp_assemble_stress)");
+  const int nlev = std::stoi(opt(prefix + "pc_mg_levels", "2"));
+  B2_REQUIRE(nlev >= 2, "pc mg: need at least 2 levels");
+  MgOp *mg = add_op<MgOp>(ctx, (int64_t)mat->nrows);
+  int Ml = mat->grid_M, Nl = mat->grid_N;
+  std::shared_ptr<Csr> Al = mat;
+  const std::string sp = prefix + "mg_levels_";
+  for (int l = 0; l < nlev; ++l) {
+    auto L = std::make_unique<MgOp::Level>();
+    L->A = Al;
+    L->b.alloc((size_t)Al->nrows + 2); L->x.alloc((size_t)Al->nrows + 2); L->r.alloc((size_t)Al->nrows + 2);
+    if (l < nlev - 1) {
+      B2_REQUIRE((Ml - 1) % 2 == 0 && (Nl - 1) % 2 == 0 && Ml >= 5 && Nl >= 5, "pc mg: grid not coarsenable to the requested number of levels");
+      const int Mc = (Ml - 1) / 2 + 1, Nc = (Nl - 1) / 2 + 1;
+      L->P = interp_q1(ctx, Mc, Nc, 2, 1);
+      L->R = restrict_q1(ctx, Mc, Nc, 2, 1);
+      L->jac = std::make_unique<JacobiOp>(*Al);
+      L->Aop = std::make_unique<CsrOp>(Al);
+      L->smooth = std::make_unique<Ksp>(ctx, sp);
+      Ksp *k = L->smooth.get();
+      k->set_operators(L->Aop.get(), L->jac.get());
+      k->type = ksp_type_from(opt(sp + "ksp_type", "chebyshev"));
+      k->max_it = std::stoi(opt(sp + "ksp_max_it", "2"));
+      k->norm_none = true;
+      k->richardson_scale = std::stod(opt(sp + "ksp_richardson_scale", "1.0"));
+      const double lam = estimate_lambda_max(ctx, L->Aop.get(), L->jac.get(), 10);
+      k->emin = 0.1 * lam;
+      k->emax = 1.1 * lam;
+      // next level: rediscretise
+      Dmda dc;
+      dc.ctx = ctx; dc.M = Mc; dc.N = Nc; dc.pm = dc.pn = 1; dc.xs = dc.ys = 0; dc.xm = Mc; dc.ym = Nc;
+      auto Ac = assemble_stress(dc, 0);
+      std::vector<int> ids = dmda_bc_ids(dc, 2);
+      csr_zero_rows_cols(*Ac, (int)ids.size(), ids.data(), 1.0, true, true, true);
+      Al = Ac;
+      Ml = Mc; Nl = Nc;
+    }
+    mg->lev.push_back(std::move(L));
+  }
+  mg->coarse = std::make_unique<DenseInvOp>(*mg->lev.back()->A);
+  return mg;
+}
+
+Op *Solver::make_fieldsplit() {
+  B2_REQUIRE(Pmat->nest, "pc fieldsplit: operator must be a 2x2 nest (b200sp_mat_create_nest)");
+  B2_REQUIRE(opt("pc_fieldsplit_type", "schur") == "schur", "pc fieldsplit: only -pc_fieldsplit_type schur");
+  auto A00 = Pmat->blk[0][0], A01 = Pmat->blk[0][1], A10 = Pmat->blk[1][0], A11 = Pmat->blk[1][1];
+  const std::string fs = opt("pc_fieldsplit_schur_fact_type", "full");
+  const int fact = fs == "diag" ? 0 : fs == "lower" ? 1 : fs == "upper" ? 2 : fs == "full" ? 3 : -1;
+  B2_REQUIRE(fact >= 0, "bad -pc_fieldsplit_schur_fact_type " + fs);
+  const std::string pre = opt("pc_fieldsplit_schur_precondition", "a11");
+  const double scale = std::stod(opt("pc_fieldsplit_schur_scale", "-1.0"));
+  // K0: -fieldsplit_0_ KSP on A00
+  Op *A00op = add_op<CsrOp>(A00);
+  Op *pc0 = make_simple_pc("fieldsplit_0_", A00, "jacobi");
+  Ksp *k0 = make_ksp("fieldsplit_0_", A00op, pc0, "preonly");
+  Op *K0 = add_op<KspOp>(k0);
+  // S with its own identically configured inner KSP (MatSchurComplementGetKSP)
+  Ksp *k0s = make_ksp("fieldsplit_0_", A00op, pc0, "preonly");
+  Op *K0s = add_op<KspOp>(k0s);
+  Op *S = add_op<SchurOp>(A11, A10, K0s, A01);
+  // matrix the S-solve's PC is built from
+  std::shared_ptr<Csr> Sp;
+  if (pre == "a11") { B2_REQUIRE(A11 != nullptr, "schur precondition a11: the nest has no (1,1) block"); Sp = A11; }
+  else if (pre == "user") { B2_REQUIRE(schur_user != nullptr, "schur precondition user: call b200sp_ksp_set_schur_user_mat"); Sp = schur_user; }
+  else if (pre == "selfp") { // Sp = A11 - A10 diag(A00)^-1 A01
+    JacobiOp dj(*A00);
+    auto A10D = csr_scale_cols(*A10, dj.dinv.p);
+    auto prod = csr_matmat(*A10D, *A01);
+    B2_REQUIRE(A11 != nullptr, "selfp: needs a (1,1) block (may be zero-valued)");
+    Sp = csr_add_scaled(*A11, -1.0, *prod);
+    mats.push_back(Sp);
+  } else if (pre != "self") throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -pc_fieldsplit_schur_precondition " + pre);
+  const std::string pt = opt("fieldsplit_1_pc_type", Sp ? "jacobi" : "none");
+  Op *pcS = nullptr;
+  if (pt == "lsc") {
+    const bool sd = has("fieldsplit_1_pc_lsc_scale_diag");
+    std::shared_ptr<Csr> Lm;
+    if (sd) {
+      JacobiOp dj(*A00);
+      auto A10D = csr_scale_cols(*A10, dj.dinv.p);
+      Lm = csr_matmat(*A10D, *A01);
+    } else Lm = csr_matmat(*A10, *A01);
+    mats.push_back(Lm);
+    Op *Lop = add_op<CsrOp>(Lm);
+    Op *pcl = make_simple_pc("fieldsplit_1_lsc_", Lm, "jacobi");
+    Ksp *kl = make_ksp("fieldsplit_1_lsc_", Lop, pcl, "preonly");
+    Op *Linv = add_op<KspOp>(kl);
+    pcS = add_op<LscOp>(A00, A01, A10, Linv, sd);
+  } else if (pt != "none" && Sp) {
+    pcS = make_simple_pc("fieldsplit_1_", Sp, "jacobi");
+  }
+  Ksp *kS = make_ksp("fieldsplit_1_", S, pcS, "preonly");
+  Op *KS = add_op<KspOp>(kS);
+  return add_op<FieldSplitOp>(fact, scale, A01, A10, K0, KS);
+}
+
+void Solver::setup() {
+  B2_REQUIRE(Amat && Pmat, "KSPSetUp: operators not set");
+  ops.clear(); ksps.clear(); mats.clear();
+  Op *Aop = Amat->nest ? (Op *)add_op<NestOp>(Amat->blk[0][0], Amat->blk[0][1], Amat->blk[1][0], Amat->blk[1][1]) : (Op *)add_op<CsrOp>(Amat->csr);
+  const std::string pt = opt("pc_type", "none");
+  Op *pc = nullptr;
+  if (pt == "fieldsplit") pc = make_fieldsplit();
+  else {
+    B2_REQUIRE(!Pmat->nest, "pc " + pt + " on a nest matrix: use -pc_type fieldsplit");
+    pc = make_simple_pc("", Pmat->csr, "none");
+  }
+  outer_pc = pc;
+  outer = make_ksp("", Aop, pc, "gmres");
+  outer->keep_history = true;
+  ctx->sync();
+  is_setup = true;
+}
+
+std::string Solver::view() const { return outer ? outer->view(0) : std::string("KSP not set up\n"); }
+
+} // namespace b200sp

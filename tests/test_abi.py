@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: libb200sp.so loads, exports every symbol include/b200sp.h declares,
+its host-only DMDA index arithmetic matches the oracle, and compute entry points fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import saddle_point_petsc_b200 as sp
+import sp_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200sp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(sp.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) > 60
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert set(syms) == set(sp.ABI_SYMBOLS), set(syms) ^ set(sp.ABI_SYMBOLS)
+
+
+def test_header_cites_reference_call_sites():
+    text = open(os.path.join(ROOT, "include", "b200sp.h")).read()
+    for cite in ("src/SaddlePointProblem.c:65-72", "src/Discretization.c:17", "src/Discretization.c:165-169", "src/Discretization.c:130-290"):
+        assert cite in text
+
+
+@pytest.mark.parametrize("M,N,size", [(4, 4, 1), (7, 5, 2), (7, 5, 4), (33, 33, 8), (2310, 2310, 8), (10, 40, 8), (40, 10, 6)])
+def test_partition_maps_match_oracle_exactly(M, N, size):
+    assert sp.dmda_proc_grid(M, N, size) == so.dmda_proc_grid(M, N, size)
+    m, n = sp.dmda_proc_grid(M, N, size)
+    assert sp.dmda_ownership(M, m).tolist() == so.dmda_ownership(M, m).tolist()
+    assert sp.dmda_ownership(N, n).tolist() == so.dmda_ownership(N, n).tolist()
+    for r in range(size):
+        assert sp.dmda_element_corners(M, N, size, r) == so.dmda_element_range(M, N, size, r)
+    if M * N <= 2000:
+        nm, ow = so.dmda_natural_to_petsc(M, N, size)
+        for j in range(N):
+            for i in range(M):
+                assert sp.dmda_global_node(M, N, size, i, j) == (nm[j * M + i], ow[j * M + i])
+
+
+@pytest.mark.parametrize("M,N,size", [(5, 5, 4), (9, 7, 2), (12, 9, 8), (6, 6, 1)])
+def test_halo_plan_is_consistent_across_ranks(M, N, size):
+    """What rank p sends to q must be exactly q's ghosts owned by p, in q's ghost order (VecScatter equivalent)."""
+    plans = [sp.dmda_halo_plan(M, N, size, r) for r in range(size)]
+    nm, ow = so.dmda_natural_to_petsc(M, N, size)
+    corners = [sp.dmda_corners(M, N, size, r) for r in range(size)]
+    for q in range(size):
+        gq = plans[q]
+        assert np.all(np.diff(gq["ghost_gnode"]) > 0)
+        # the ghost set is the width-1 ring of q's box (box stencil, corners included)
+        xs, ys, xm, ym = corners[q]
+        ring = sorted(nm[j * M + i] for j in range(max(ys - 1, 0), min(ys + ym, N - 1) + 1)
+                      for i in range(max(xs - 1, 0), min(xs + xm, M - 1) + 1)
+                      if not (xs <= i < xs + xm and ys <= j < ys + ym))
+        assert gq["ghost_gnode"].tolist() == ring
+        for p in range(size):
+            if p == q:
+                continue
+            want = gq["ghost_gnode"][gq["ghost_owner"] == p]
+            sel = plans[p]["send_rank"] == q
+            pxs, pys, pxm, pym = corners[p]
+            lnode = plans[p]["send_lnode"][sel]
+            sent = [nm[(pys + l // pxm) * M + pxs + l % pxm] for l in lnode]
+            assert sent == want.tolist()
+
+
+def test_no_cpu_fallback():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(sp.B200spError) as e:
+        sp.Context()
+    assert e.value.code == 2  # B200SP_ERR_NO_DEVICE

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Integer / index work and everything with a fixed summation order must be BIT-EXACT; reductions are
+compared at fp64 rounding level; solver runs at the tolerances BASELINE.json states:
+iterations +-1, final relative residual within 1e-10, solution within rel 1e-8."""
+import numpy as np
+import pytest
+
+import sp_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+sp = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _mod():
+    global sp
+    import saddle_point_petsc_b200 as m
+    sp = m
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def assert_csr_identical(dev, orc, what):
+    rp, col, val = dev.csr()
+    assert np.array_equal(rp, orc.rowptr), what + ": rowptr differs"
+    assert np.array_equal(col, orc.col), what + ": column indices differ"
+    assert same_bits(val, orc.val), what + ": values not bit-identical (max abs diff %g)" % np.nanmax(np.abs(val - orc.val))
+
+
+# ------------------------------------------------------------------ assembly (a8-a12)
+@pytest.mark.parametrize("nx,ny", [(3, 3), (1, 1), (2, 5), (17, 9), (64, 48), (130, 70)])
+def test_assembly_bit_exact(ctx, nx, ny):
+    dev = sp.SaddlePointProblem(ctx, nx, ny, kkt=True, rhs_kind=0)
+    orc = so.Problem(nx, ny, kkt=True, rhs_kind=0)
+    assert_csr_identical(dev.A, orc.A, "A")
+    assert_csr_identical(dev.Bt, orc.Bt, "Bt")
+    assert_csr_identical(dev.B, orc.B, "B")
+    assert_csr_identical(dev.C, orc.C, "C")
+    assert_csr_identical(dev.Q, orc.Q, "Q")
+    assert same_bits(dev.rhs.numpy(), orc.rhs)
+    assert np.array_equal(dev.bc, orc.bc)
+    assert dev.A.size()[2] == 4 * (3 * (nx + 1) - 2) * (3 * (ny + 1) - 2)
+
+
+def test_assembly_rotational_rhs_and_no_bc(ctx):
+    da = sp.DMDA(ctx, 21, 13)
+    f = sp.Vec(ctx, 2 * da.n_nodes_local)
+    da.assemble_rhs(f, rhs_kind=1)
+    orc = so.Problem(21, 13, rhs_kind=1, bc=False)
+    assert same_bits(f.numpy(), orc.f)
+    assert_csr_identical(da.assemble_stress(), orc.A, "A without BC")
+
+
+def test_assembly_as_written_reproduces_the_reference_defect(ctx):
+    dev = sp.SaddlePointProblem(ctx, 3, 3, as_written=True)
+    orc = so.Problem(3, 3, as_written=True)
+    rp, col, val = dev.A.csr()
+    assert np.array_equal(np.isnan(val), np.isnan(orc.A.val)) and int(np.isnan(val).sum()) == 64
+    assert np.array_equal(val[~np.isnan(val)], orc.A.val[~np.isnan(orc.A.val)])
+    assert np.abs(dev.rhs.numpy()).max() == 0.0
+
+
+def test_interpolation_matrices(ctx):
+    for dof, bc in ((2, 1), (1, 0), (2, 0)):
+        h = sp._vp()
+        sp._chk(sp.lib().b200sp_interp_q1(ctx.h, 9, 6, dof, bc, sp.C.byref(h)))
+        assert_csr_identical(sp.Mat(ctx, h), so.Csr(so.lib().or_interp_q1(9, 6, dof, bc)), "P")
+
+
+# ------------------------------------------------------------------ SpMV (a3)
+def rand_vec(n, seed):
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)
+
+
+@pytest.mark.parametrize("nx,ny", [(3, 3), (40, 31), (200, 150)])
+def test_spmv_stream_bit_exact_all_blocks(ctx, nx, ny):
+    dev = sp.SaddlePointProblem(ctx, nx, ny, kkt=True)
+    orc = so.Problem(nx, ny, kkt=True)
+    for name in ("A", "Bt", "B", "C", "Q"):
+        D, O = getattr(dev, name), getattr(orc, name)
+        plan = D.spmv_plan()
+        assert plan["kernel"] == 0, (name, plan)            # short rows -> warp-stream kernel
+        assert sum(plan["hist"]) == O.nrows
+        x = rand_vec(O.ncols, 1)
+        xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, O.nrows)
+        D.mult(xd, yd)
+        assert same_bits(yd.numpy(), O.mult(x)), name
+        # fused epilogues: residual and mult-add
+        b = rand_vec(O.nrows, 2)
+        bd, rd = sp.Vec.from_numpy(ctx, b), sp.Vec(ctx, O.nrows)
+        D.residual(bd, xd, rd)
+        assert same_bits(rd.numpy(), b - O.mult(x)), name
+        D.mult_add(xd, bd, rd)
+        assert same_bits(rd.numpy(), b + O.mult(x)), name
+
+
+def test_spmv_other_kernels_and_ragged_matrices(ctx):
+    import scipy.sparse as sps
+    rng = np.random.default_rng(7)
+    # ragged: empty rows, a dense row, 1-entry rows
+    n, m = 1000, 700
+    A = sps.random(n, m, density=0.01, random_state=3, format="lil")
+    A[5, :] = rng.uniform(-1, 1, m)       # dense constraint-like row
+    A[17, :] = 0.0                        # empty row
+    A = A.tocsr()
+    A.sort_indices()
+    D = sp.Mat.from_scipy(ctx, A)
+    O = so.Csr.from_arrays(n, m, A.indptr, A.indices, A.data)
+    x = rand_vec(m, 4)
+    ref = O.mult(x)
+    xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, n)
+    scale = np.abs(A).dot(np.abs(x)) + 1e-300
+    for k in (1, 2):
+        D.set_spmv_kernel(k)
+        D.mult(xd, yd)
+        assert np.max(np.abs(yd.numpy() - ref) / scale) < 4e-16 * 32, k
+    # 4 dense rows (the reference's intended barycentre/volume constraint block, SaddlePointProblem.c:49)
+    Bc = sps.csr_matrix(rng.uniform(-1, 1, (4, 5000)))
+    Dc = sp.Mat.from_scipy(ctx, Bc)
+    assert Dc.spmv_plan()["kernel"] == 2
+    xc = rand_vec(5000, 5)
+    yc = sp.Vec(ctx, 4)
+    Dc.mult(sp.Vec.from_numpy(ctx, xc), yc)
+    assert np.allclose(yc.numpy(), Bc @ xc, rtol=1e-13, atol=1e-13)
+    # empty matrix / zero rows
+    E = sp.Mat.from_csr(ctx, 3, 3, [0, 0, 0, 0], [], [])
+    ye = sp.Vec.from_numpy(ctx, np.ones(3))
+    E.mult(sp.Vec.from_numpy(ctx, np.ones(3)), ye)
+    assert np.array_equal(ye.numpy(), np.zeros(3))
+
+
+def test_spmv_linearity_at_scale(ctx):
+    """size-independent property at a large size: A(ax+by) == aAx + bAy to rounding, and the nest apply
+    equals the sum of its blocks."""
+    nx = 700
+    dev = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+    n = dev.n
+    x, y = rand_vec(n, 10), rand_vec(n, 11)
+    xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec.from_numpy(ctx, y)
+    zd = sp.Vec.from_numpy(ctx, 2.0 * x - 3.0 * y)
+    o1, o2, o3 = sp.Vec(ctx, n), sp.Vec(ctx, n), sp.Vec(ctx, n)
+    dev.K.mult(xd, o1); dev.K.mult(yd, o2); dev.K.mult(zd, o3)
+    lin = 2.0 * o1.numpy() - 3.0 * o2.numpy()
+    assert np.max(np.abs(o3.numpy() - lin)) < 1e-12 * np.max(np.abs(lin))
+    # symmetry of K: x.(K y) == y.(K x)
+    assert abs(x @ o2.numpy() - y @ o1.numpy()) < 1e-10 * abs(x @ o2.numpy())
+
+
+# ------------------------------------------------------------------ vector kernels (a4, a5)
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 100003, 1 << 20])
+def test_vector_kernels(ctx, n):
+    x, y = rand_vec(n, 1), rand_vec(n, 2)
+    xd, yd, wd = sp.Vec.from_numpy(ctx, x), sp.Vec.from_numpy(ctx, y), sp.Vec(ctx, n)
+    a = 0.37
+    yd.axpy(a, xd); y1 = y + a * x
+    assert same_bits(yd.numpy(), y1)
+    yd.aypx(a, xd); y2 = x + a * y1
+    assert same_bits(yd.numpy(), y2)
+    wd.waxpy(a, xd, yd)
+    assert same_bits(wd.numpy(), a * x + y2)
+    wd.pointwise_mult(xd, yd)
+    assert same_bits(wd.numpy(), x * y2)
+    wd.scale(-2.5)
+    assert same_bits(wd.numpy(), -2.5 * (x * y2))
+    xd.copy_to(wd)
+    assert same_bits(wd.numpy(), x)
+    wd.set(3.0)
+    assert np.all(wd.numpy() == 3.0)
+    d = xd.dot(yd)
+    tol = 1e-15 * max(1.0, np.sqrt(n)) * (np.abs(x) @ np.abs(y2) + 1e-300)
+    assert abs(d - x @ y2) <= tol
+    assert abs(xd.norm() - np.linalg.norm(x)) <= 1e-14 * np.linalg.norm(x) + 1e-300
+    # determinism: the same reduction twice is bit-identical
+    assert xd.dot(yd) == d
+
+
+def test_mdot_maxpy(ctx):
+    n, k = 50001, 7
+    x = rand_vec(n, 3)
+    ys = [rand_vec(n, 10 + j) for j in range(k)]
+    xd = sp.Vec.from_numpy(ctx, x)
+    yds = [sp.Vec.from_numpy(ctx, y) for y in ys]
+    md = xd.mdot(yds)
+    assert np.allclose(md, [x @ y for y in ys], rtol=1e-12, atol=1e-12)
+    coef = np.linspace(-1, 1, k)
+    xd.maxpy(coef, yds)
+    assert np.allclose(xd.numpy(), x + sum(c * y for c, y in zip(coef, ys)), rtol=1e-13, atol=1e-13)
+
+
+# ------------------------------------------------------------------ PC apply + solves (a2, a6, a7)
+from test_oracle import CONFIGS  # noqa: E402  (same option strings as the oracle's own tests)
+
+
+def run_pair(ctx, nx, ny, opts, kkt=True, rhs_kind=1):
+    dev = sp.SaddlePointProblem(ctx, nx, ny, kkt=kkt, rhs_kind=rhs_kind)
+    orc = so.Problem(nx, ny, kkt=kkt, rhs_kind=rhs_kind)
+    ksp = dev.make_ksp(opts)
+    x = sp.Vec(ctx, dev.n)
+    rd = ksp.solve(dev.rhs, x)
+    ro = so.Solver(orc, opts).solve()
+    return dev, orc, ksp, rd, ro, x.numpy()
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_pc_apply_matches_oracle(ctx, name):
+    nx = 16
+    dev = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+    orc = so.Problem(nx, nx, kkt=True, rhs_kind=1)
+    ksp = dev.make_ksp(CONFIGS[name])
+    ksp.setup()
+    s = so.Solver(orc, CONFIGS[name])
+    v = rand_vec(dev.n, 5)
+    yd = sp.Vec(ctx, dev.n)
+    ksp.pc_apply(sp.Vec.from_numpy(ctx, v), yd)
+    yo = np.empty(dev.n)
+    so.lib().or_op_apply(s.ksp.contents.M, so.dptr(v), so.dptr(yo))
+    assert np.max(np.abs(yd.numpy() - yo)) <= 1e-10 * np.max(np.abs(yo)), name
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+@pytest.mark.parametrize("nx", [16, 32])
+def test_kkt_solve_parity(ctx, name, nx):
+    if name == "gmres_full_jacobi" and nx > 16:
+        nx = 24
+    dev, orc, ksp, rd, ro, x = run_pair(ctx, nx, nx, CONFIGS[name])
+    assert rd["reason"] == ro["reason"] == 2, (rd["reason"], ro["reason"])
+    assert abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    # final relative residual (the KSP's own monitored norm) within 1e-10
+    rel_d, rel_o = rd["rnorm"] / rd["history"][0], ro["rnorm"] / ro["history"][0]
+    if rd["its"] == ro["its"]:
+        assert abs(rel_d - rel_o) <= 1e-10, (rel_d, rel_o)
+    # solution within rel 1e-8 of the oracle's (both iterate to rtol 1e-8; compare velocity, and pressure
+    # up to the constant null vector)
+    nu = dev.nu
+    if rd["its"] == ro["its"]:
+        assert np.max(np.abs(x[:nu] - ro["x"][:nu])) <= 1e-8 * np.max(np.abs(ro["x"][:nu]))
+        dp = x[nu:] - ro["x"][nu:]
+        assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(ro["x"][nu:]))
+    # true residual through the oracle's operator
+    K = orc.scipy_K()
+    assert np.linalg.norm(orc.rhs - K @ x) / np.linalg.norm(orc.rhs) < 5e-7
+    # residual histories agree iteration by iteration
+    m = min(len(rd["history"]), len(ro["history"]))
+    assert np.allclose(rd["history"][:m - 1], ro["history"][:m - 1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("opts", ["-ksp_type gmres -pc_type jacobi", "-ksp_type fgmres -pc_type jacobi",
+                                  "-ksp_type minres -pc_type jacobi", "-ksp_type gmres -pc_type none",
+                                  "-ksp_type gmres -ksp_gmres_restart 5 -pc_type jacobi",
+                                  "-ksp_type fgmres -pc_type mg -pc_mg_levels 3"])
+def test_reference_default_problem_and_velocity_block(ctx, opts):
+    """config[0]: the reference's own 3x3 case (intended mode) and a larger velocity-only solve."""
+    from test_oracle import FREE, U_FREE
+    if "mg" not in opts:
+        dev, orc, ksp, rd, ro, x = run_pair(ctx, 3, 3, opts + " -ksp_rtol 1e-10", kkt=False, rhs_kind=0)
+        assert rd["reason"] == 2 and abs(rd["its"] - ro["its"]) <= 1
+        assert np.allclose(x[FREE], U_FREE, rtol=1e-8)
+        assert np.abs(x[orc.bc]).max() == 0.0
+    dev, orc, ksp, rd, ro, x = run_pair(ctx, 40, 24, opts + " -ksp_rtol 1e-9", kkt=False, rhs_kind=0)
+    assert rd["reason"] == ro["reason"] == 2
+    assert abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    assert np.max(np.abs(x - ro["x"])) <= 1e-8 * np.max(np.abs(ro["x"]))
+
+
+def test_solve_host_buffers_and_view(ctx):
+    dev = sp.SaddlePointProblem(ctx, 24, 24, kkt=True, rhs_kind=1)
+    ksp = dev.make_ksp(CONFIGS["fgmres_upper_mg"])
+    b = dev.rhs.numpy()
+    x = np.zeros_like(b)
+    r = ksp.solve_host(b, x)
+    xd = sp.Vec(ctx, dev.n)
+    r2 = ksp.solve(dev.rhs, xd)
+    assert r["its"] == r2["its"] and np.array_equal(x, xd.numpy())   # deterministic, host path == device path
+    v = ksp.view()
+    assert "fieldsplit" in v and "mg" in v and "fgmres" in v
+
+
+def test_error_paths(ctx):
+    with pytest.raises(sp.B200spError):
+        sp.Mat.from_csr(ctx, 2, 2, [0, 2, 3], [1, 0, 1], [1.0, 2.0, 3.0])      # unsorted columns
+    with pytest.raises(sp.B200spError):
+        sp.Mat.from_csr(ctx, 2, 2, [0, 1, 2], [0, 5], [1.0, 2.0])              # column out of range
+    dev = sp.SaddlePointProblem(ctx, 4, 4)
+    with pytest.raises(sp.B200spError):
+        dev.make_ksp("-ksp_type bogus").setup()
+    with pytest.raises(sp.B200spError):
+        dev.make_ksp("-pc_type fieldsplit").setup()                             # not a nest
+    a, b = sp.Vec(ctx, 3), sp.Vec(ctx, 4)
+    with pytest.raises(sp.B200spError):
+        a.axpy(1.0, b)
