@@ -16,6 +16,7 @@
 #include <omp.h>
 #endif
 
+#define MINRES_HAPTOL 1e-18 /* KSPMINRES haptol: a tiny negative r.z is rounding, not an indefinite PC */
 #define CHUNK 4096 /* fixed reduction chunk: dot/norm results do not depend on the thread count */
 
 static void *xmalloc(size_t n) {
@@ -898,8 +899,8 @@ static int solve_minres(OrKsp *k, const double *b, double *x, int guess_nonzero)
   if (guess_nonzero) { or_op_apply(k->A, x, r); v_aypx(n, -1.0, b, r); } else v_copy(n, b, r);
   pc_apply(k, r, z);
   dp = or_dot(n, r, z);
-  if (dp < 0.0) { k->reason = OR_DIVERGED_INDEFINITE_PC; goto done; }
-  beta = sqrt(dp);
+  if (dp < 0.0 && fabs(dp) > MINRES_HAPTOL) { k->reason = OR_DIVERGED_INDEFINITE_PC; goto done; }
+  beta = sqrt(fabs(dp));
   eta = beta;
   { double rn = or_norm2(n, z); k->reason = converged(k, 0, rn); if (k->reason) goto done; dp = rn; }
   if (beta == 0.0) { k->reason = OR_CONVERGED_ATOL; goto done; }
@@ -912,7 +913,7 @@ static int solve_minres(OrKsp *k, const double *b, double *x, int guess_nonzero)
     v_axpy(n, -alpha, v, r); v_axpy(n, -beta, vold, r);
     v_axpy(n, -alpha, u, z); v_axpy(n, -beta, uold, z);
     betaold = beta;
-    { double d = or_dot(n, r, z); if (d < 0.0) { k->reason = OR_DIVERGED_INDEFINITE_PC; break; } beta = sqrt(d); }
+    { double d = or_dot(n, r, z); if (d < 0.0 && fabs(d) > MINRES_HAPTOL) { k->reason = OR_DIVERGED_INDEFINITE_PC; break; } beta = sqrt(fabs(d)); }
     coold = cold; cold = c; soold = sold; sold = s;
     rho0 = cold * alpha - coold * sold * betaold;
     rho1 = sqrt(rho0 * rho0 + beta * beta);

@@ -132,8 +132,7 @@ class Csr:
     @classmethod
     def from_arrays(cls, nrows, ncols, rowptr, col, val):
         p = lib().or_csr_alloc(nrows, ncols, len(col))
-        c = cls(p)
-        c.rowptr[:] = rowptr
+        cls(p, own=False).rowptr[:] = rowptr   # the views of an OrCsr are sized from rowptr: fill it first
         c = cls(p)
         c.col[:] = col
         c.val[:] = val

@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libb200sp build failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lnccl", "-Xlinker", "-rpath=/usr/lib/x86_64-linux-gnu"]
+        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-lnccl", "-Xlinker", "-rpath=/usr/lib/x86_64-linux-gnu"]
         subprocess.check_call(cmd)
     return OUT
 

@@ -155,6 +155,7 @@ struct Csr {
   int64_t hist[14] = {0};
   // grid metadata when the matrix came from DMDA assembly (for -pc_type mg); 0 = unknown
   int grid_M = 0, grid_N = 0, dof_r = 0, dof_c = 0;
+  std::string tag = "spmv"; // profile class of this matrix's SpMV launches ("spmv:A", "spmv:Bt", ...)
   void plan();           // histogram + kernel choice (device reduction)
 };
 constexpr int CSR_PAD = 8; // zero entries appended to col/val so vector loads may overrun a row tile

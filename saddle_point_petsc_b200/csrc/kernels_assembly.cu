@@ -378,7 +378,9 @@ std::shared_ptr<Csr> build_box_matrix(const Dmda &da, const ElemArrays &ea, int 
 std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written) {
   ElemArrays ea;
   run_elements(da, as_written, 0, WANT_K, ea);
-  return build_box_matrix(da, ea, 2, 2, 0, ea.Ke.p);
+  auto A = build_box_matrix(da, ea, 2, 2, 0, ea.Ke.p);
+  A->tag = "spmv:A";
+  return A;
 }
 
 void assemble_rhs(const Dmda &da, int as_written, int kind, double *f) {
@@ -397,10 +399,10 @@ void assemble_rhs(const Dmda &da, int as_written, int kind, double *f) {
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q) {
   ElemArrays ea;
   run_elements(da, 0, 0, WANT_KKT, ea);
-  if (Bt) *Bt = build_box_matrix(da, ea, 2, 1, 0, ea.Ge.p);
-  if (B) *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p);
-  if (C) *C = build_box_matrix(da, ea, 1, 1, 0, ea.Ce.p);
-  if (Q) *Q = build_box_matrix(da, ea, 1, 1, 0, ea.Qe.p);
+  if (Bt) { *Bt = build_box_matrix(da, ea, 2, 1, 0, ea.Ge.p); (*Bt)->tag = "spmv:Bt"; }
+  if (B) { *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p); (*B)->tag = "spmv:B"; }
+  if (C) { *C = build_box_matrix(da, ea, 1, 1, 0, ea.Ce.p); (*C)->tag = "spmv:C"; }
+  if (Q) { *Q = build_box_matrix(da, ea, 1, 1, 0, ea.Qe.p); (*Q)->tag = "spmv:Q"; }
 }
 
 std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc) {
@@ -423,6 +425,7 @@ std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc) {
     check_launch("k_interp_fill");
   }
   c->sync();
+  P->tag = "spmv:P";
   P->plan();
   return P;
 }
@@ -447,6 +450,7 @@ std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc) {
     check_launch("k_restrict_fill");
   }
   c->sync();
+  R->tag = "spmv:R";
   R->plan();
   return R;
 }

@@ -193,7 +193,7 @@ void Csr::plan() {
 void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
   Ctx *c = A.ctx;
   if (A.nrows <= 0) return;
-  LaunchScope ls(c, "spmv");
+  LaunchScope ls(c, A.tag.c_str());
   if (A.kernel == SPMV_STREAM) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;

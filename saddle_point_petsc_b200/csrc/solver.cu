@@ -389,8 +389,9 @@ int Ksp::solve_minres(const double *b, double *x, bool guess_nonzero) {
   if (guess_nonzero) A->residual(b, x, r); else vec_copy(ctx, n, b, r);
   pc_apply(r, z);
   dp = dot(r, z);
-  if (dp < 0.0) { reason = B200SP_DIVERGED_INDEFINITE_PC; its = 0; return reason; }
-  beta = std::sqrt(dp);
+  const double haptol = 1e-18; // KSPMINRES haptol: a tiny negative r.z is rounding, not an indefinite PC
+  if (dp < 0.0 && std::fabs(dp) > haptol) { reason = B200SP_DIVERGED_INDEFINITE_PC; its = 0; return reason; }
+  beta = std::sqrt(std::fabs(dp));
   eta = beta;
   dp = norm2(z);
   reason = converged(0, dp);
@@ -406,7 +407,7 @@ int Ksp::solve_minres(const double *b, double *x, bool guess_nonzero) {
     vec_axpbypcz(ctx, n, -alpha, v, -beta, vold, 1.0, r, r); // r -= alpha v + beta v_old
     vec_axpbypcz(ctx, n, -alpha, u, -beta, uold, 1.0, z, z); // z -= alpha u + beta u_old
     betaold = beta;
-    { const double d = dot(r, z); if (d < 0.0) { reason = B200SP_DIVERGED_INDEFINITE_PC; break; } beta = std::sqrt(d); }
+    { const double d = dot(r, z); if (d < 0.0 && std::fabs(d) > haptol) { reason = B200SP_DIVERGED_INDEFINITE_PC; break; } beta = std::sqrt(std::fabs(d)); }
     coold = cold; cold = c; soold = sold; sold = s;
     rho0 = cold * alpha - coold * sold * betaold;
     rho1 = std::sqrt(rho0 * rho0 + beta * beta);
@@ -580,6 +581,7 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
       auto Ac = assemble_stress(dc, 0);
       std::vector<int> ids = dmda_bc_ids(dc, 2);
       csr_zero_rows_cols(*Ac, (int)ids.size(), ids.data(), 1.0, true, true, true);
+      Ac->tag = "spmv:A_coarse";
       Al = Ac;
       Ml = Mc; Nl = Nc;
     }
