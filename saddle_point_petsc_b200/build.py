@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sp.so")
 SOURCES = ["kernels_vec.cu", "kernels_spmv.cu", "kernels_setup.cu", "kernels_assembly.cu", "solver.cu", "capi.cu"]
-HEADERS = ["core.h", "dev.cuh", "solver.h", os.path.join("..", "..", "include", "b200sp.h")]
+HEADERS = ["core.h", "dev.cuh", "solver.h", "nccl_dyn.h", os.path.join("..", "..", "include", "b200sp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libb200sp build failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-lnccl", "-Xlinker", "-rpath=/usr/lib/x86_64-linux-gnu"]
+        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

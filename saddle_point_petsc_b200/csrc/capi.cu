@@ -26,7 +26,7 @@ static thread_local std::string g_last_error;
 
 namespace b200sp {
 Ctx::~Ctx() {
-  if (comm) ncclCommDestroy(comm);
+  if (comm) nccl().CommDestroy(comm);
   if (d_partials) cudaFree(d_partials);
   if (d_ticket) cudaFree(d_ticket);
   if (d_scalars) cudaFree(d_scalars);
@@ -94,7 +94,8 @@ int b200sp_nccl_unique_id(char id[128]) {
   API_BEGIN
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   ncclUniqueId u;
-  B2_NCCL(ncclGetUniqueId(&u));
+  if (!nccl().ok) throw Error(B200SP_ERR_NCCL, "NCCL unavailable: " + nccl().err);
+  B2_NCCL(nccl().GetUniqueId(&u));
   std::memcpy(id, &u, 128);
   API_END
 }
@@ -131,7 +132,8 @@ int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b
       B2_REQUIRE(nccl_id, "ctx_create: size > 1 needs an NCCL unique id");
       ncclUniqueId u;
       std::memcpy(&u, nccl_id, 128);
-      B2_NCCL(ncclCommInitRank(&c.comm, size, u, rank));
+      if (!nccl().ok) throw Error(B200SP_ERR_NCCL, "NCCL unavailable: " + nccl().err);
+      B2_NCCL(nccl().CommInitRank(&c.comm, size, u, rank));
     }
   } catch (...) { delete h; throw; }
   *out = h;
@@ -324,7 +326,7 @@ int b200sp_vec_pointwise_mult(b200sp_vec w, b200sp_vec x, b200sp_vec y) {
   API_BEGIN SAME_SIZE(x, y); SAME_SIZE(x, w); vec_pointwise_mult(w->v.ctx, w->v.n, x->v.d, y->v.d, w->v.d); API_END
 }
 static void global_sum(Ctx *c, int k, double *host) {
-  if (c->size > 1) B2_NCCL(ncclAllReduce(c->d_scalars, c->d_scalars, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->size > 1) B2_NCCL(nccl().AllReduce(c->d_scalars, c->d_scalars, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
   c->fetch_scalars(c->d_scalars, k, host);
 }
 int b200sp_vec_dot(b200sp_vec x, b200sp_vec y, double *result) {

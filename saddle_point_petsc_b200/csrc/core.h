@@ -1,7 +1,7 @@
 // core.h -- internal C++ declarations of libb200sp (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include "nccl_dyn.h"
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -29,7 +29,7 @@ struct Error : std::runtime_error {
   do {                                                                                                  \
     ncclResult_t e_ = (call);                                                                           \
     if (e_ != ncclSuccess)                                                                              \
-      throw ::b200sp::Error(B200SP_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(e_));        \
+      throw ::b200sp::Error(B200SP_ERR_NCCL, std::string(#call) + ": " + ::b200sp::nccl().GetErrorString(e_)); \
   } while (0)
 #define B2_REQUIRE(cond, msg)                                                 \
   do {                                                                        \

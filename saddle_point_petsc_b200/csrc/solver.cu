@@ -20,7 +20,7 @@ void Ctx::fetch_scalars(const double *d, int k, double *host) {
   std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
 }
 static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
-  if (c->size > 1) B2_NCCL(ncclAllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->size > 1) B2_NCCL(nccl().AllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
 // ------------------------------------------------------------------ operators

@@ -1,0 +1,28 @@
+"""Run only the A-block SpMV (for ncu captures): python tools/spmv_only.py [nx] [reps] [block]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import saddle_point_petsc_b200 as sp  # noqa: E402
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2304
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+block = sys.argv[3] if len(sys.argv) > 3 else "A"
+ctx = sp.Context()
+da = sp.DMDA(ctx, nx, nx)
+if block == "A":
+    m = da.assemble_stress()
+else:
+    Bt, B, C, Q = da.assemble_kkt()
+    m = {"Bt": Bt, "B": B, "C": C}[block]
+r, c, nnz = m.size()
+x, y = sp.Vec(ctx, c), sp.Vec(ctx, r)
+x.set(1.0)
+for _ in range(3):
+    m.mult(x, y)
+ctx.timer_start()
+for _ in range(reps):
+    m.mult(x, y)
+ms = ctx.timer_stop() / reps
+byts = 12 * nnz + 4 * (r + 1) + 8 * r + 8 * c
+print("block %s nx %d: %.4f ms  %.1f GB/s (algorithmic)" % (block, nx, ms, byts / ms / 1e6))
