@@ -122,7 +122,8 @@ int b200sp_mat_destroy(b200sp_mat A);
 int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz);
 int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val); /* MatView / parity checks */
 /* row-length histogram (bins 0,1,2,3-4,5-8,...,1025-2048,>2048: 14 bins) and the SpMV kernel chosen from it:
- * 0 = warp-stream (short rows), 1 = warp-per-row vector, 2 = block-per-row (long rows) */
+ * 3 = TMA-staged thread-per-row (short rows, default), 0 = warp-stream (short rows, no TMA),
+ * 1 = lanes-per-row vector (medium rows), 2 = block-per-row (long dense rows) */
 int b200sp_mat_get_spmv_plan(b200sp_mat A, int64_t hist[14], int *kernel, int *max_row_nnz);
 int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel); /* override (tests / sweeps) */
 int b200sp_mat_mult(b200sp_mat A, b200sp_vec x, b200sp_vec y);              /* MatMult */

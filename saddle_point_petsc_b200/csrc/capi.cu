@@ -410,8 +410,8 @@ int b200sp_mat_get_spmv_plan(b200sp_mat A, int64_t hist[14], int *kernel, int *m
 int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel) {
   API_BEGIN
   Csr &M = plain(A);
-  B2_REQUIRE(kernel >= 0 && kernel <= 2, "bad kernel id");
-  B2_REQUIRE(kernel != SPMV_STREAM || M.max_group_nnz <= 1152, "stream kernel: rows too long for the shared tile");
+  B2_REQUIRE(kernel >= 0 && kernel <= 3, "bad kernel id");
+  B2_REQUIRE((kernel != SPMV_STREAM && kernel != SPMV_TMA) || M.max_group_nnz <= 1152, "stream kernel: rows too long for the shared tile");
   M.kernel = kernel;
   API_END
 }

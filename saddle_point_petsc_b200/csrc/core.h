@@ -138,7 +138,8 @@ struct Dmda {
 };
 
 // ------------------------------------------------------------------ Mat
-enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2 };
+enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3 };
+bool csr_spmv_tma(const struct Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z);
 
 struct Csr {
   Ctx *ctx = nullptr;

@@ -184,7 +184,7 @@ void Csr::plan() {
   max_group_nnz = h_max[1] + 2;
   for (int i = 0; i < 14; ++i) hist[i] = (int64_t)h_hist[i];
   const double mean = nrows ? (double)nnz / nrows : 0.0;
-  if (max_group_nnz <= STREAM_MAX_GROUP_NNZ) kernel = SPMV_STREAM;
+  if (max_group_nnz <= STREAM_MAX_GROUP_NNZ) kernel = SPMV_TMA; // short rows: TMA-staged thread-per-row (SPMV_STREAM is the non-TMA alternative)
   else if (mean >= 2048.0) kernel = SPMV_BLOCK;
   else kernel = SPMV_VECTOR;
   lanes_per_row = mean <= 2 ? 2 : mean <= 4 ? 4 : mean <= 8 ? 8 : mean <= 16 ? 16 : 32;
@@ -194,7 +194,8 @@ void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const doub
   Ctx *c = A.ctx;
   if (A.nrows <= 0) return;
   LaunchScope ls(c, A.tag.c_str());
-  if (A.kernel == SPMV_STREAM) {
+  if (A.kernel == SPMV_TMA && csr_spmv_tma(A, x, y, alpha, z, beta_z)) return;
+  if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;
     static bool attr_set = false;

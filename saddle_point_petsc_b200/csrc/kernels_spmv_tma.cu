@@ -1,0 +1,157 @@
+// kernels_spmv_tma.cu -- SPMV_TMA: CSR SpMV whose matrix stream is moved by the TMA engine.
+//
+// A persistent CTA walks row tiles of R = blockDim.x rows.  The tile's val/col segment (one contiguous
+// range of the CSR arrays) is copied into shared memory by two cp.async.bulk (UBLKCP) requests issued by
+// one thread and tracked by an mbarrier (complete_tx); S stages are in flight, so the HBM stream never
+// waits for the arithmetic and costs no registers or issue slots.  Consumers: one thread per row walks its
+// row in CSR order out of shared memory, gathers x through L1/L2 and accumulates product-then-add, i.e.
+// bit-identical to the sequential MatMult_SeqAIJ loop (same result as SPMV_STREAM).
+//   shared memory per stage = 12 B x (max tile nnz + pad); A block (18 nnz/row, R = 512): 110.7 KB x 2 stages.
+//   algorithmic bytes per launch: 12 nnz + 4 (rows+1) + 8 rows + 8 cols  (SURVEY 8d).
+#include "dev.cuh"
+#include <cstdlib>
+
+namespace b200sp {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+constexpr int TMA_MAX_STAGES = 4;
+
+// dynamic shared layout: [S stages][ val: cap doubles | col: cap ints ], then S mbarriers
+template <int UNROLL>
+__global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                           const double *__restrict__ x, double *y, double alpha, const double *z, double beta_z, int cap, int stages) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const int R = blockDim.x;
+  const size_t stage_bytes = (size_t)cap * 12;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + stage_bytes * stages);
+  const int tid = threadIdx.x;
+
+  auto issue = [&](int tile, int stage) { // one thread
+    const int r0 = tile * R;
+    const int r1 = min(r0 + R, nrows);
+    const int s0 = rowptr[r0] & ~3;
+    const int e0 = rowptr[r1];
+    const int cnt = (e0 - s0 + 3) & ~3;
+    unsigned char *base = s_raw + stage_bytes * stage;
+    mbar_expect_tx(&full[stage], (unsigned)cnt * 12u);
+    if (cnt > 0) {
+      bulk_g2s(base, val + s0, (unsigned)cnt * 8u, &full[stage]);
+      bulk_g2s(base + (size_t)cap * 8, col + s0, (unsigned)cnt * 4u, &full[stage]);
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it % stages;
+    const unsigned parity = (unsigned)(it / stages) & 1u;
+    const int r = tile * R + tid;
+    // row bounds are fetched before waiting on the tile so their latency overlaps the TMA
+    const int s_al = rowptr[tile * R] & ~3;
+    const int rs = rowptr[r < nrows ? r : nrows];
+    const int re = rowptr[r + 1 < nrows ? r + 1 : nrows];
+    mbar_wait(&full[stage], parity);
+    const double *sv = reinterpret_cast<const double *>(s_raw + stage_bytes * stage);
+    const int *sc = reinterpret_cast<const int *>(s_raw + stage_bytes * stage + (size_t)cap * 8);
+    if (r < nrows) {
+      double sum = 0.0;
+      int k = rs - s_al;
+      const int ke = re - s_al;
+      for (; k + UNROLL <= ke; k += UNROLL) {
+        double xv[UNROLL], av[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) { av[u] = sv[k + u]; xv[u] = __ldg(x + sc[k + u]); }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) sum += av[u] * xv[u];
+      }
+      for (; k < ke; ++k) sum += sv[k] * __ldg(x + sc[k]);
+      double v = alpha * sum;
+      if (z) v = beta_z * z[r] + v;
+      y[r] = v;
+    }
+    __syncthreads(); // every consumer is done with this stage
+    if (tid == 0) {
+      const int t = tile + stages * gridDim.x;
+      if (t < ntiles) issue(t, stage);
+    }
+  }
+}
+
+} // namespace
+
+// returns false when the matrix does not fit the shared-memory tiling (caller falls back)
+bool csr_spmv_tma(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+  Ctx *c = A.ctx;
+  const size_t budget = 225 * 1024;
+  int R = 0, stages = 0, cap = 0;
+  static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;           // tuning overrides
+  static const int env_S = getenv("B200SP_TMA_STAGES") ? atoi(getenv("B200SP_TMA_STAGES")) : 0;
+  static const int env_U = getenv("B200SP_TMA_UNROLL") ? atoi(getenv("B200SP_TMA_UNROLL")) : 0;
+  // Measured on B200 (profiles/r01_tma_tile_sweep.txt): small tiles with exactly two stages and as many
+  // co-resident CTAs as shared memory allows beat large tiles / deeper pipelines for every block
+  // (A 18 nnz/row: R=128,S=2 -> 97% of the measured HBM peak; R=512,S=2 -> 93%; any S>=3 -> <= 62%).
+  for (int r : {128, 256, 512}) {
+    if (env_R && r != env_R) continue;
+    const int capr = (((r / 32) * A.max_group_nnz + 8) + 3) & ~3;
+    const size_t sb = (size_t)capr * 12;
+    int s = (int)((budget - 64) / sb);
+    if (s >= 2) { R = r; stages = 2; cap = capr; if (env_S && env_S <= s && env_S <= TMA_MAX_STAGES) stages = env_S; break; }
+    if (!env_R) break; // rows too long for a 128-row tile: the vector kernel is the right tool
+  }
+  if (!R) return false;
+  const size_t smem = (size_t)cap * 12 * stages + 8 * TMA_MAX_STAGES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int ntiles = (A.nrows + R - 1) / R;
+  int per_sm = (int)(budget / smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * R > 2048) per_sm = 2048 / R;
+  int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
+  const double mean = A.nrows ? (double)A.nnz / A.nrows : 0.0;
+  (void)mean;
+  if (env_U ? env_U == 6 : true)
+    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z, cap, stages);
+  else
+    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z, cap, stages);
+  check_launch("k_spmv_tma");
+  return true;
+}
+
+} // namespace b200sp

@@ -146,21 +146,18 @@ std::string LscOp::view(int indent) const {
 }
 
 // PCMG multiplicative V-cycle: smoothdown (zero guess), residual, restrict, recurse, interpolate-add, smoothup
-void MgOp::cycle(int l) {
+void MgOp::cycle(int l, const double *b, double *x) {
   Level &L = *lev[l];
-  if (l == (int)lev.size() - 1) { coarse->apply(L.b.p, L.x.p); return; }
-  L.smooth->solve(L.b.p, L.x.p, false);
-  csr_spmv(*L.A, L.x.p, L.r.p, -1.0, L.b.p, 1.0);               // r = b - A x
-  csr_spmv(*L.R, L.r.p, lev[l + 1]->b.p);                        // restrict
-  cycle(l + 1);
-  csr_spmv(*L.P, lev[l + 1]->x.p, L.x.p, 1.0, L.x.p, 1.0);       // x += P xc
-  L.smooth->solve(L.b.p, L.x.p, true);
+  if (l == (int)lev.size() - 1) { coarse->apply(b, x); return; }
+  Level &Lc = *lev[l + 1];
+  L.smooth->solve(b, x, false);
+  csr_spmv(*L.A, x, L.r.p, -1.0, b, 1.0);          // r = b - A x
+  csr_spmv(*L.R, L.r.p, Lc.b.p);                    // restrict
+  cycle(l + 1, Lc.b.p, Lc.x.p);
+  csr_spmv(*L.P, Lc.x.p, x, 1.0, x, 1.0);           // x += P xc
+  L.smooth->solve(b, x, true);
 }
-void MgOp::apply(const double *b, double *x) {
-  vec_copy(ctx, n_in, b, lev[0]->b.p);
-  cycle(0);
-  vec_copy(ctx, n_in, lev[0]->x.p, x);
-}
+void MgOp::apply(const double *b, double *x) { cycle(0, b, x); } // level 0 works on the caller's vectors: no copies
 std::string MgOp::view(int indent) const {
   std::ostringstream o;
   o << pad(indent) << "PC mg: multiplicative V-cycle, " << lev.size() << " levels (rediscretised coarse operators, Q1 interpolation)\n";
@@ -202,7 +199,7 @@ int Ksp::solve(const double *b, double *x, bool guess_nonzero) {
   its = 0;
   hist.clear();
   ld = (n + 15) & ~(int64_t)15;
-  if (!guess_nonzero && type != KSP_PREONLY) vec_set(ctx, n, 0.0, x);
+  if (!guess_nonzero && type != KSP_PREONLY && type != KSP_CHEBYSHEV) vec_set(ctx, n, 0.0, x); // VecSet(x,0): zero initial guess
   switch (type) {
   case KSP_PREONLY:
     pc_apply(b, x);
@@ -254,6 +251,30 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
   reason = 0;
   const double *res = b;
   if (guess_nonzero) { A->residual(b, x, r); res = r; }
+  if (fused) {
+    // Smoother mode (fixed sweeps, Jacobi or no PC): no copies and no zero-fill.  The previous iterate of the
+    // first update is x itself (nonzero guess) or the zero vector (coefficient 0 on a finite dummy operand);
+    // iterates ping-pong between two scratch vectors and the LAST update writes straight into x.  Every
+    // update is elementwise, so writing over the vector that holds p_{k-1} is safe.
+    const double *pm1 = guess_nonzero ? x : b; // b is only a finite dummy when the guess is zero
+    double am1 = guess_nonzero ? 1.0 : 0.0;
+    double *cur = max_it == 1 ? x : w2.p;
+    vec_cheb_update(ctx, n, am1, pm1, 0.0, pm1, scale, dinv, res, cur); // p1 = x0 + scale * M^-1 r0
+    its = 1;
+    for (int i = 1; i < max_it; ++i) {
+      A->residual(b, cur, r);
+      ckp1 = 2.0 * mu * ck - ckm1;
+      omega = omegaprod * ck / ckp1;
+      double *out = (i == max_it - 1) ? x : (cur == w2.p ? w3.p : w2.p);
+      vec_cheb_update(ctx, n, (1.0 - omega) * am1, pm1, omega, cur, omega * scale, dinv, r, out);
+      pm1 = cur; am1 = 1.0; cur = out;
+      ckm1 = ck; ck = ckp1;
+      its = i + 1;
+    }
+    reason = B200SP_CONVERGED_ITS;
+    return reason;
+  }
+  if (!guess_nonzero) vec_set(ctx, n, 0.0, x);
   vec_copy(ctx, n, x, pkm1);
   if (fused) {
     vec_cheb_update(ctx, n, 1.0, pkm1, 0.0, pkm1, scale, dinv, res, pk); // pk = x + scale * M^-1 r

@@ -105,7 +105,7 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   std::vector<std::unique_ptr<Level>> lev;
   std::unique_ptr<DenseInvOp> coarse;
   explicit MgOp(Ctx *c, int64_t n) : Op(c, n, n) {}
-  void cycle(int l);
+  void cycle(int l, const double *b, double *x);
   void apply(const double *b, double *x) override;
   std::string view(int indent) const override;
 };

@@ -84,7 +84,8 @@ def test_spmv_stream_bit_exact_all_blocks(ctx, nx, ny):
     for name in ("A", "Bt", "B", "C", "Q"):
         D, O = getattr(dev, name), getattr(orc, name)
         plan = D.spmv_plan()
-        assert plan["kernel"] == 0, (name, plan)            # short rows -> warp-stream kernel
+        assert plan["kernel"] == 3, (name, plan)            # short rows -> TMA-staged kernel
+        D.set_spmv_kernel(0)                                # first the warp-stream alternative
         assert sum(plan["hist"]) == O.nrows
         x = rand_vec(O.ncols, 1)
         xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, O.nrows)
@@ -97,6 +98,14 @@ def test_spmv_stream_bit_exact_all_blocks(ctx, nx, ny):
         assert same_bits(rd.numpy(), b - O.mult(x)), name
         D.mult_add(xd, bd, rd)
         assert same_bits(rd.numpy(), b + O.mult(x)), name
+        # the TMA-staged kernel (cp.async.bulk + mbarrier pipeline) sums in the same order: bit-exact too
+        D.set_spmv_kernel(3)
+        yd.set(-7.0)
+        D.mult(xd, yd)
+        assert same_bits(yd.numpy(), O.mult(x)), name + " (tma)"
+        D.residual(bd, xd, rd)
+        assert same_bits(rd.numpy(), b - O.mult(x)), name + " (tma)"
+        D.set_spmv_kernel(3)
 
 
 def test_spmv_other_kernels_and_ragged_matrices(ctx):

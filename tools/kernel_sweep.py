@@ -45,7 +45,7 @@ def main():
             r, c, nnz = m.size()
             x, y = sp.Vec(ctx, c), sp.Vec(ctx, r)
             x.set(1.0)
-            for k in ([0, 1] if name == "A" else [0]):
+            for k in ([0, 1, 3] if name == "A" else [0, 3]):
                 m.set_spmv_kernel(k)
                 ms = time_ms(ctx, lambda: m.mult(x, y))
                 gbs = spmv_bytes(m) / ms / 1e6

@@ -8,6 +8,7 @@ import saddle_point_petsc_b200 as sp  # noqa: E402
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2304
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 block = sys.argv[3] if len(sys.argv) > 3 else "A"
+kernel = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 ctx = sp.Context()
 da = sp.DMDA(ctx, nx, nx)
 if block == "A":
@@ -16,6 +17,8 @@ else:
     Bt, B, C, Q = da.assemble_kkt()
     m = {"Bt": Bt, "B": B, "C": C}[block]
 r, c, nnz = m.size()
+if kernel >= 0:
+    m.set_spmv_kernel(kernel)
 x, y = sp.Vec(ctx, c), sp.Vec(ctx, r)
 x.set(1.0)
 for _ in range(3):
