@@ -119,6 +119,9 @@ int b200sp_mat_create_csr(b200sp_ctx ctx, int nrows, int ncols, const int *rowpt
  * (= MatSetValues(ADD_VALUES) then MatAssemblyEnd on a single rank) */
 int b200sp_mat_create_coo(b200sp_ctx ctx, int nrows, int ncols, int64_t ncoo, const int *row, const int *col, const double *val, b200sp_mat *A);
 int b200sp_mat_destroy(b200sp_mat A);
+/* MatSetDM equivalent: the M x N-node, dof-per-node DMDA a square matrix lives on (lets -pc_type mg build its
+ * hierarchy when the matrix came from b200sp_mat_create_coo/_csr instead of b200sp_assemble_stress) */
+int b200sp_mat_set_grid(b200sp_mat A, int M, int N, int dof);
 int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz);
 int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val); /* MatView / parity checks */
 /* row-length histogram (bins 0,1,2,3-4,5-8,...,1025-2048,>2048: 14 bins) and the SpMV kernel chosen from it:

@@ -72,6 +72,7 @@ _SIGS = {
     "b200sp_mat_create_csr": [_vp, C.c_int, C.c_int, c_ip, c_ip, c_dp, C.POINTER(_vp)],
     "b200sp_mat_create_coo": [_vp, C.c_int, C.c_int, C.c_int64, c_ip, c_ip, c_dp, C.POINTER(_vp)],
     "b200sp_mat_destroy": [_vp],
+    "b200sp_mat_set_grid": [_vp, C.c_int, C.c_int, C.c_int],
     "b200sp_mat_get_size": [_vp, c_ip, c_ip, C.POINTER(C.c_int64)],
     "b200sp_mat_get_csr_host": [_vp, c_ip, c_ip, c_dp],
     "b200sp_mat_get_spmv_plan": [_vp, C.POINTER(C.c_int64), c_ip, c_ip],

@@ -54,6 +54,13 @@ def build(force=False, verbose=False):
     if force or procs or _stale(OUT, objs):
         cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-ldl"]
         subprocess.check_call(cmd)
+    # PETSc API shim over the C ABI (plain C, host only): lets the unmodified reference sources link against us
+    shim_out = os.path.join(HERE, "libpetscshim.so")
+    shim_src = [os.path.join(CSRC, "petsc_shim.c"), os.path.join(CSRC, "shim_backend_b200sp.c")]
+    shim_dep = shim_src + [os.path.join(CSRC, "shim_backend.h"), os.path.join(HERE, "..", "include", "petsc_shim", "petsc.h"), OUT]
+    if force or _stale(shim_out, shim_dep):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-I", os.path.join(HERE, "..", "include", "petsc_shim"), "-o", shim_out]
+                              + shim_src + ["-L", HERE, "-lb200sp", "-Wl,-rpath,$ORIGIN", "-lm"])
     return OUT
 
 

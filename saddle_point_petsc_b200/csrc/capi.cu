@@ -379,6 +379,13 @@ int b200sp_mat_create_coo(b200sp_ctx ctx, int nrows, int ncols, int64_t ncoo, co
   API_BEGIN *A = wrap(&ctx->c, csr_from_coo_host(&ctx->c, nrows, ncols, ncoo, row, col, val)); API_END
 }
 int b200sp_mat_destroy(b200sp_mat A) { API_BEGIN if (A) { A->m.ctx->sync(); delete A; } API_END }
+int b200sp_mat_set_grid(b200sp_mat A, int M, int N, int dof) {
+  API_BEGIN
+  Csr &m = plain(A);
+  B2_REQUIRE(M >= 2 && N >= 2 && dof >= 1 && (int64_t)M * N * dof == m.nrows && m.nrows == m.ncols, "mat_set_grid: grid does not match the matrix");
+  m.grid_M = M; m.grid_N = N; m.dof_r = dof; m.dof_c = dof;
+  API_END
+}
 int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz) {
   API_BEGIN
   if (nrows) *nrows = A->m.nrows();
@@ -536,7 +543,9 @@ int b200sp_ksp_solve_host(b200sp_ksp ksp, const double *b_host, double *x_host, 
   if (!ksp->s.is_setup) ksp->s.setup();
   Ctx *c = ksp->s.ctx;
   B2_REQUIRE(n == ksp->s.outer->n, "KSPSolve(host): size mismatch");
-  DevBuf<double> b((size_t)n + 2), x((size_t)n + 2);
+  // staging vectors live with the KSP (allocated once): the call itself only copies and solves
+  DevBuf<double> &b = ksp->s.host_b, &x = ksp->s.host_x;
+  if (b.n < (size_t)n + 2) { b.alloc((size_t)n + 2); x.alloc((size_t)n + 2); }
   B2_CUDA(cudaMemcpyAsync(b.p, b_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   ksp->s.outer->solve(b.p, x.p, false);
   B2_CUDA(cudaMemcpyAsync(x_host, x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));

@@ -300,9 +300,211 @@ std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B) {
   return C;
 }
 
-std::shared_ptr<Csr> csr_transpose(const Csr &) { throw Error(B200SP_ERR_UNSUPPORTED, "csr_transpose: not available yet"); }
-std::shared_ptr<Csr> csr_from_coo_host(Ctx *, int, int, int64_t, const int *, const int *, const double *) {
-  throw Error(B200SP_ERR_UNSUPPORTED, "csr_from_coo: not available yet");
+// ---------------------------------------------------------------- COO -> CSR: stable LSD radix sort + in-order sum
+// key = (row << 32) | col, payload = position in the input (insertion order).  4-bit digits; every thread owns
+// RS_ITEMS CONSECUTIVE keys of its tile, so "lower thread, then earlier item" is the input order and the
+// scatter is stable.  After the sort equal keys are adjacent in insertion order; one thread per distinct key
+// sums its duplicates in that order starting from +0.0 == MatSetValues(ADD_VALUES) in call order.
+namespace {
+constexpr int RS_ITEMS = 8, RS_THREADS = 256, RS_TILE = RS_ITEMS * RS_THREADS, RS_BINS = 16;
+
+__global__ void __launch_bounds__(256) k_coo_keys(int64_t n, const int *__restrict__ row, const int *__restrict__ col, unsigned long long *keys, int *pay,
+                                                  int nrows, int ncols, int *bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = row[i], c = col[i];
+    if (r < 0 || r >= nrows || c < 0 || c >= ncols) *bad = 1;
+    keys[i] = ((unsigned long long)(unsigned)r << 32) | (unsigned)c;
+    pay[i] = (int)i;
+  }
+}
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(int64_t n, const unsigned long long *__restrict__ keys, int shift, int *hist, int ntiles) {
+  __shared__ int s_h[RS_BINS];
+  if (threadIdx.x < RS_BINS) s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)threadIdx.x * RS_ITEMS;
+  int cnt[RS_BINS];
+#pragma unroll
+  for (int b = 0; b < RS_BINS; ++b) cnt[b] = 0;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k)
+    if (base + k < n) {
+      const int d = (int)((keys[base + k] >> shift) & (RS_BINS - 1));
+#pragma unroll
+      for (int b = 0; b < RS_BINS; ++b) cnt[b] += (d == b);
+    }
+#pragma unroll
+  for (int b = 0; b < RS_BINS; ++b) {
+    int v = cnt[b];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_h[b], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < RS_BINS) hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_h[threadIdx.x]; // bin-major for the global scan
+}
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(int64_t n, const unsigned long long *__restrict__ keys, const int *__restrict__ pay, int shift,
+                                                           const int *__restrict__ offs, int ntiles, unsigned long long *keys_out, int *pay_out) {
+  __shared__ int s_cnt[RS_BINS][RS_THREADS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)tid * RS_ITEMS;
+  unsigned long long kk[RS_ITEMS];
+  int pp[RS_ITEMS], dd[RS_ITEMS];
+  int cnt[RS_BINS];
+#pragma unroll
+  for (int b = 0; b < RS_BINS; ++b) cnt[b] = 0;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    dd[k] = -1;
+    if (base + k < n) {
+      kk[k] = keys[base + k];
+      pp[k] = pay[base + k];
+      dd[k] = (int)((kk[k] >> shift) & (RS_BINS - 1));
+#pragma unroll
+      for (int b = 0; b < RS_BINS; ++b) cnt[b] += (dd[k] == b);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < RS_BINS; ++b) s_cnt[b][tid] = cnt[b];
+  __syncthreads();
+  // exclusive scan over the 256 threads for each bin: warp w scans bins 2w and 2w+1
+  for (int b = warp * 2; b < warp * 2 + 2; ++b) {
+    int carry = 0;
+    for (int seg = 0; seg < RS_THREADS; seg += 32) {
+      const int v = s_cnt[b][seg + lane];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+      }
+      s_cnt[b][seg + lane] = carry + incl - v;
+      carry += __shfl_sync(FULL, incl, 31);
+    }
+  }
+  __syncthreads();
+  int run[RS_BINS];
+#pragma unroll
+  for (int b = 0; b < RS_BINS; ++b) run[b] = offs[(size_t)b * ntiles + blockIdx.x] + s_cnt[b][tid];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k)
+    if (dd[k] >= 0) {
+      int dest = 0;
+#pragma unroll
+      for (int b = 0; b < RS_BINS; ++b)
+        if (dd[k] == b) dest = run[b]++;
+      keys_out[dest] = kk[k];
+      pay_out[dest] = pp[k];
+    }
+}
+__global__ void __launch_bounds__(256) k_coo_heads(int64_t n, const unsigned long long *__restrict__ keys, int *head) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// one thread per sorted entry that is a segment head: sum the run of equal keys in order, write col/val, and mark row starts
+__global__ void __launch_bounds__(256) k_coo_reduce(int64_t n, const unsigned long long *__restrict__ keys, const int *__restrict__ pay,
+                                                    const int *__restrict__ head, const int *__restrict__ upos, const double *__restrict__ val,
+                                                    int *col_out, double *val_out, int *rowcnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!head[i]) continue;
+    const unsigned long long k = keys[i];
+    double s = 0.0;
+    for (int64_t j = i; j < n && keys[j] == k; ++j) s += val[pay[j]];
+    const int u = upos[i];
+    col_out[u] = (int)(k & 0xffffffffu);
+    val_out[u] = s;
+    atomicAdd(&rowcnt[(int)(k >> 32)], 1);
+  }
+}
+int bits_for(int v) { int b = 0; while ((1LL << b) < (long long)v) ++b; return b < 1 ? 1 : b; }
+} // namespace
+
+std::shared_ptr<Csr> csr_from_coo_device(Ctx *c, int nrows, int ncols, int64_t n, const int *d_row, const int *d_col, const double *d_val) {
+  B2_REQUIRE(nrows >= 0 && ncols >= 0 && n >= 0 && n < (1LL << 31), "csr_from_coo: bad sizes");
+  DevBuf<unsigned long long> k0((size_t)n + 1), k1((size_t)n + 1);
+  DevBuf<int> p0((size_t)n + 1), p1((size_t)n + 1), bad(1);
+  bad.zero(c->stream);
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_coo_keys<<<grid_for(c, n), 256, 0, c->stream>>>(n, d_row, d_col, k0.p, p0.p, nrows, ncols, bad.p);
+    check_launch("k_coo_keys");
+  }
+  int h_bad = 0;
+  B2_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  B2_REQUIRE(!h_bad, "csr_from_coo: row or column index out of range");
+  const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  DevBuf<int> hist((size_t)RS_BINS * (ntiles > 0 ? ntiles : 1) + 1), offs((size_t)RS_BINS * (ntiles > 0 ? ntiles : 1) + 1);
+  unsigned long long *ka = k0.p, *kb = k1.p;
+  int *pa = p0.p, *pb = p1.p;
+  // LSD: the column bits first (low word), then the row bits (high word)
+  std::vector<int> shifts;
+  for (int s = 0; s < bits_for(ncols); s += 4) shifts.push_back(s);
+  for (int s = 0; s < bits_for(nrows); s += 4) shifts.push_back(32 + s);
+  for (int shift : shifts) {
+    if (!n) break;
+    {
+      LaunchScope ls(c, "setup");
+      k_rs_hist<<<ntiles, RS_THREADS, 0, c->stream>>>(n, ka, shift, hist.p, ntiles);
+      check_launch("k_rs_hist");
+    }
+    exclusive_scan_i32(c, hist.p, offs.p, (int64_t)RS_BINS * ntiles, nullptr);
+    {
+      LaunchScope ls(c, "setup");
+      k_rs_scatter<<<ntiles, RS_THREADS, 0, c->stream>>>(n, ka, pa, shift, offs.p, ntiles, kb, pb);
+      check_launch("k_rs_scatter");
+    }
+    std::swap(ka, kb);
+    std::swap(pa, pb);
+  }
+  DevBuf<int> head((size_t)n + 1), upos((size_t)n + 2);
+  int nuniq = 0;
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_coo_heads<<<grid_for(c, n), 256, 0, c->stream>>>(n, ka, head.p);
+    check_launch("k_coo_heads");
+  }
+  exclusive_scan_i32(c, head.p, upos.p, n, &nuniq);
+  auto A = csr_alloc(c, nrows, ncols, nuniq);
+  DevBuf<int> rowcnt((size_t)nrows + 1);
+  rowcnt.zero(c->stream);
+  if (n) {
+    LaunchScope ls(c, "setup");
+    k_coo_reduce<<<grid_for(c, n), 256, 0, c->stream>>>(n, ka, pa, head.p, upos.p, d_val, A->col.p, A->val.p, rowcnt.p);
+    check_launch("k_coo_reduce");
+  }
+  exclusive_scan_i32(c, rowcnt.p, A->rowptr.p, nrows, nullptr);
+  c->sync();
+  A->plan();
+  return A;
+}
+
+std::shared_ptr<Csr> csr_from_coo_host(Ctx *c, int nrows, int ncols, int64_t n, const int *row, const int *col, const double *val) {
+  DevBuf<int> d_row((size_t)n + 1), d_col((size_t)n + 1);
+  DevBuf<double> d_val((size_t)n + 1);
+  if (n) {
+    B2_CUDA(cudaMemcpyAsync(d_row.p, row, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(d_col.p, col, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(d_val.p, val, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  return csr_from_coo_device(c, nrows, ncols, n, d_row.p, d_col.p, d_val.p);
+}
+
+// explicit transpose = COO (col, row, val) through the same stable sort: rows of A^T come out with ascending
+// columns (= ascending original rows), the order MatTranspose produces
+namespace {
+__global__ void __launch_bounds__(256) k_expand_rows(int nrows, const int *__restrict__ rowptr, int *rows) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x)
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) rows[k] = r;
+}
+} // namespace
+std::shared_ptr<Csr> csr_transpose(const Csr &A) {
+  Ctx *c = A.ctx;
+  DevBuf<int> rows((size_t)A.nnz + 1);
+  if (A.nrows) {
+    LaunchScope ls(c, "setup");
+    k_expand_rows<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, rows.p);
+    check_launch("k_expand_rows");
+  }
+  return csr_from_coo_device(c, A.ncols, A.nrows, A.nnz, A.col.p, rows.p, A.val.p);
 }
 
 // ---------------------------------------------------------------- small dense inverse (coarsest MG level)

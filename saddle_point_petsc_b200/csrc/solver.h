@@ -165,6 +165,7 @@ struct Solver {
   Ksp *outer = nullptr;
   Op *outer_pc = nullptr;
   bool is_setup = false;
+  DevBuf<double> host_b, host_x; // device staging for b200sp_ksp_solve_host
   explicit Solver(Ctx *c) : ctx(c) {}
   void set_options(const char *text);
   void setup();

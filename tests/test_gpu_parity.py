@@ -320,3 +320,58 @@ def test_error_paths(ctx):
     a, b = sp.Vec(ctx, 3), sp.Vec(ctx, 4)
     with pytest.raises(sp.B200spError):
         a.axpy(1.0, b)
+
+
+# ------------------------------------------------------------------ COO -> CSR (a10), transpose, SpGEMM
+def test_coo_to_csr_sorts_and_sums_in_insertion_order(ctx):
+    rng = np.random.default_rng(11)
+    nrows, ncols, n = 300, 257, 40000
+    row = rng.integers(0, nrows, n).astype(np.int32)
+    col = rng.integers(0, ncols, n).astype(np.int32)
+    val = rng.uniform(-1, 1, n)
+    D = sp.Mat.from_coo(ctx, nrows, ncols, row, col, val)
+    dense = np.zeros(nrows * ncols)
+    np.add.at(dense, row.astype(np.int64) * ncols + col, val)      # unbuffered: sequential adds in input order
+    touched = np.zeros(nrows * ncols, dtype=bool)
+    touched[row.astype(np.int64) * ncols + col] = True
+    rp, ci, v = D.csr()
+    keys = np.repeat(np.arange(nrows), np.diff(rp)).astype(np.int64) * ncols + ci
+    assert np.all(np.diff(keys) > 0)                               # sorted by (row, col), no duplicates left
+    assert np.array_equal(keys, np.flatnonzero(touched))
+    assert same_bits(v, dense[keys])
+    # empty input and a single entry
+    E = sp.Mat.from_coo(ctx, 4, 4, [], [], [])
+    assert E.size() == (4, 4, 0)
+    S = sp.Mat.from_coo(ctx, 4, 4, [2], [3], [1.5])
+    assert S.scipy().toarray()[2, 3] == 1.5
+    with pytest.raises(sp.B200spError):
+        sp.Mat.from_coo(ctx, 4, 4, [5], [0], [1.0])
+
+
+@pytest.mark.parametrize("nx,ny", [(3, 3), (24, 17)])
+def test_reference_element_loop_through_the_coo_path(ctx, nx, ny):
+    """MatSetValuesStencil(ADD_VALUES) in the reference's element order (src/Discretization.c:146-165), shipped
+    as COO triplets and assembled by the device sort == the oracle's in-place ADD, bit for bit (values; the COO
+    path keeps only touched entries, which for this operator is the whole DMCreateMatrix pattern)."""
+    M, N = nx + 1, ny + 1
+    rows, cols, vals = [], [], []
+    for ej in range(N - 1):
+        for ei in range(M - 1):
+            ke = so.element_stress(so.element_coords(M, N, ei, ej))
+            nd = [ej * M + ei, (ej + 1) * M + ei, (ej + 1) * M + ei + 1, ej * M + ei + 1]
+            eq = np.array([2 * nd[a >> 1] + (a & 1) for a in range(8)])
+            rows.append(np.repeat(eq, 8)); cols.append(np.tile(eq, 8)); vals.append(ke)
+    D = sp.Mat.from_coo(ctx, 2 * M * N, 2 * M * N, np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))
+    orc = so.Problem(nx, ny, bc=False)
+    assert_csr_identical(D, orc.A, "A via COO")
+
+
+def test_transpose_and_matmult(ctx):
+    dev = sp.SaddlePointProblem(ctx, 20, 14, kkt=True)
+    orc = so.Problem(20, 14, kkt=True)
+    T = dev.Bt.transpose()
+    assert_csr_identical(T, orc.B, "Bt^T == B")                     # exact transpose, ascending columns
+    L = dev.B.matmult(dev.Bt)
+    assert_csr_identical(L, orc.B.matmat(orc.Bt), "L = B Bt")       # same accumulation order as the oracle
+    AA = dev.A.matmult(dev.A)
+    assert_csr_identical(AA, orc.A.matmat(orc.A), "A A")
