@@ -9,8 +9,9 @@
  *     FGMRES, MINRES, PCFIELDSPLIT/Schur, PCLSC, PCMG.
  *
  * PARITY STATUS: the element kernels and the A/f assembly + BC are PINNED
- * against the real reference code compiled from /root/reference (oracle/_ref,
- * see oracle/Makefile and tests/test_oracle_vs_ref.py).  The Krylov /
+ * bit-for-bit against the real reference code compiled from /root/reference
+ * (oracle/ref_build.sh -> oracle/_ref, golden vectors in tests/golden/,
+ * tests/test_golden.py).  The Krylov /
  * preconditioner part is "parity unpinned": PETSc is an un-vendored,
  * un-pinned dependency of the reference (CMakeLists.txt:13) that is absent
  * from this image, and the reference ships no tests or golden vectors, so
