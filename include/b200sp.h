@@ -58,6 +58,14 @@ const char *b200sp_version(void);
  * store, file, env), every rank calls b200sp_ctx_create with the same id. */
 int b200sp_nccl_unique_id(char id[128]);
 int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b200sp_ctx *ctx);
+/* In-process rank group: all `size` ranks are THREADS of this process (each with its own context and stream, on
+ * one or several GPUs).  Collectives are host barriers + peer copies, so ranks never wait on each other inside
+ * a kernel.  Used by the tests to run the whole distributed algorithm on a 1-GPU box, and usable as a
+ * single-process multi-GPU mode.  Every collective call must be made by all rank-threads. */
+typedef struct b200sp_group_s *b200sp_group;
+int b200sp_local_group_create(int size, b200sp_group *group);
+int b200sp_local_group_destroy(b200sp_group group);
+int b200sp_ctx_create_local(b200sp_group group, int rank, int device, b200sp_ctx *ctx);
 int b200sp_ctx_destroy(b200sp_ctx ctx);
 int b200sp_ctx_synchronize(b200sp_ctx ctx);
 int b200sp_ctx_get_stream(b200sp_ctx ctx, void **cuda_stream);

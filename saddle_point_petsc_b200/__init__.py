@@ -33,6 +33,9 @@ class B200spError(RuntimeError):
 _SIGS = {
     "b200sp_nccl_unique_id": [C.c_char_p],
     "b200sp_ctx_create": [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)],
+    "b200sp_local_group_create": [C.c_int, C.POINTER(_vp)],
+    "b200sp_local_group_destroy": [_vp],
+    "b200sp_ctx_create_local": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "b200sp_ctx_destroy": [_vp],
     "b200sp_ctx_synchronize": [_vp],
     "b200sp_ctx_get_stream": [_vp, C.POINTER(_vp)],
@@ -195,6 +198,15 @@ class Context:
         _chk(lib().b200sp_ctx_create(device, rank, size, nccl_id, C.byref(self.h)))
         self.rank, self.size, self.device = rank, size, device
 
+    @classmethod
+    def local(cls, group, rank, device=0):
+        """rank `rank` of an in-process LocalGroup (call from the thread that will drive this rank)"""
+        self = cls.__new__(cls)
+        self.h = _vp()
+        _chk(lib().b200sp_ctx_create_local(group.h, rank, device, C.byref(self.h)))
+        self.rank, self.size, self.device = rank, group.size, device
+        return self
+
     @staticmethod
     def nccl_unique_id():
         buf = C.create_string_buffer(128)
@@ -230,6 +242,40 @@ class Context:
         if self.h:
             _chk(lib().b200sp_ctx_destroy(self.h))
             self.h = _vp()
+
+
+class LocalGroup:
+    """All ranks as threads of this process (b200sp_local_group_create); see run_ranks()."""
+
+    def __init__(self, size):
+        self.size = size
+        self.h = _vp()
+        _chk(lib().b200sp_local_group_create(size, C.byref(self.h)))
+
+
+def run_ranks(size, fn, device=0):
+    """Run fn(ctx) SPMD-style on `size` rank-threads of one process (ctypes releases the GIL inside the library, and
+    every collective is a host barrier, so the ranks make progress together).  Returns [fn result per rank]."""
+    import threading
+    grp = LocalGroup(size)
+    out, err = [None] * size, [None] * size
+
+    def work(r):
+        try:
+            ctx = Context.local(grp, r, device)
+            out[r] = fn(ctx)
+        except BaseException as e:  # noqa: BLE001 - reported to the caller below
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(size)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 class Vec:

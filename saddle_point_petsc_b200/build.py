@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sp.so")
-SOURCES = ["kernels_vec.cu", "kernels_spmv.cu", "kernels_spmv_tma.cu", "kernels_setup.cu", "kernels_assembly.cu", "solver.cu", "capi.cu"]
-HEADERS = ["core.h", "dev.cuh", "solver.h", "nccl_dyn.h", os.path.join("..", "..", "include", "b200sp.h")]
+SOURCES = ["kernels_vec.cu", "kernels_spmv.cu", "kernels_spmv_tma.cu", "kernels_setup.cu", "kernels_assembly.cu", "dist.cu", "solver.cu", "capi.cu"]
+HEADERS = ["core.h", "dev.cuh", "solver.h", "nccl_dyn.h", "dist.h", os.path.join("..", "..", "include", "b200sp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

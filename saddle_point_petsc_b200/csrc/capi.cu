@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary of libb200sp (include/b200sp.h).  Catches every C++ exception and
 // turns it into an int error code (PetscErrorCode convention); no C++ type crosses the boundary.
 #include "solver.h"
+#include "dist.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -26,6 +27,7 @@ static thread_local std::string g_last_error;
 
 namespace b200sp {
 Ctx::~Ctx() {
+  delete dcomm;
   if (comm) nccl().CommDestroy(comm);
   if (d_partials) cudaFree(d_partials);
   if (d_ticket) cudaFree(d_ticket);
@@ -56,34 +58,6 @@ void dmda_ownership(int M, int m, int *lx) {
   for (int i = 0; i < m; ++i) lx[i] = M / m + ((M % m) > i);
 }
 } // namespace b200sp
-
-namespace {
-struct Layout {
-  int M, N, size, m, n;
-  std::vector<int> lx, ly, xoff, yoff, rstart; // rstart[r] = first global node id of rank r
-  Layout(int M_, int N_, int size_) : M(M_), N(N_), size(size_) {
-    B2_REQUIRE(M >= 2 && N >= 2 && size >= 1, "dmda: need M,N >= 2 and size >= 1");
-    dmda_proc_grid(M, N, size, &m, &n);
-    B2_REQUIRE(m * n == size, "dmda: size does not factor into a process grid");
-    B2_REQUIRE(m <= M && n <= N, "dmda: more ranks than nodes in a direction");
-    lx.resize(m); ly.resize(n);
-    dmda_ownership(M, m, lx.data());
-    dmda_ownership(N, n, ly.data());
-    xoff.assign(m + 1, 0); yoff.assign(n + 1, 0);
-    for (int i = 0; i < m; ++i) xoff[i + 1] = xoff[i] + lx[i];
-    for (int j = 0; j < n; ++j) yoff[j + 1] = yoff[j] + ly[j];
-    rstart.assign(size + 1, 0);
-    for (int r = 0; r < size; ++r) rstart[r + 1] = rstart[r] + lx[r % m] * ly[r / m];
-  }
-  int owner_x(int i) const { return (int)(std::upper_bound(xoff.begin(), xoff.end(), i) - xoff.begin()) - 1; }
-  int owner_y(int j) const { return (int)(std::upper_bound(yoff.begin(), yoff.end(), j) - yoff.begin()) - 1; }
-  int owner(int i, int j) const { return owner_y(j) * m + owner_x(i); }
-  int gnode(int i, int j) const {
-    const int pi = owner_x(i), pj = owner_y(j), r = pj * m + pi;
-    return rstart[r] + (j - yoff[pj]) * lx[pi] + (i - xoff[pi]);
-  }
-};
-} // namespace
 
 extern "C" {
 
@@ -134,9 +108,33 @@ int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b
       std::memcpy(&u, nccl_id, 128);
       if (!nccl().ok) throw Error(B200SP_ERR_NCCL, "NCCL unavailable: " + nccl().err);
       B2_NCCL(nccl().CommInitRank(&c.comm, size, u, rank));
+      c.dcomm = make_nccl_comm(c.comm, rank, size);
     }
   } catch (...) { delete h; throw; }
   *out = h;
+  API_END
+}
+// ---- in-process rank group: all ranks are threads of this process (tests on a 1-GPU box; single-process multi-GPU)
+struct b200sp_group_s { std::shared_ptr<LocalGroup> g; };
+int b200sp_local_group_create(int size, b200sp_group *out) {
+  API_BEGIN
+  B2_REQUIRE(out && size >= 1, "local_group_create: bad arguments");
+  auto *h = new b200sp_group_s();
+  h->g = std::make_shared<LocalGroup>(size);
+  *out = h;
+  API_END
+}
+int b200sp_local_group_destroy(b200sp_group g) { API_BEGIN delete g; API_END }
+int b200sp_ctx_create_local(b200sp_group group, int rank, int device, b200sp_ctx *out) {
+  API_BEGIN
+  B2_REQUIRE(group && out && rank >= 0 && rank < group->g->size, "ctx_create_local: bad arguments");
+  b200sp_ctx ctx = nullptr;
+  int rc = b200sp_ctx_create(device, 0, 1, nullptr, &ctx);
+  if (rc) throw Error(rc, g_last_error);
+  ctx->c.rank = rank;
+  ctx->c.size = group->g->size;
+  if (group->g->size > 1) ctx->c.dcomm = make_local_comm(group->g, rank, device);
+  *out = ctx;
   API_END
 }
 int b200sp_ctx_destroy(b200sp_ctx ctx) {
@@ -252,8 +250,13 @@ int b200sp_dmda_create(b200sp_ctx ctx, int M, int N, b200sp_dmda *da) {
   auto *h = new b200sp_dmda_s();
   Dmda &d = h->d;
   d.ctx = &ctx->c; d.M = M; d.N = N; d.pm = L.m; d.pn = L.n; d.lx = L.lx; d.ly = L.ly;
-  const int pi = ctx->c.rank % L.m, pj = ctx->c.rank / L.m;
-  d.xs = L.xoff[pi]; d.ys = L.yoff[pj]; d.xm = L.lx[pi]; d.ym = L.ly[pj];
+  L.box(ctx->c.rank, &d.xs, &d.ys, &d.xm, &d.ym);
+  if (ctx->c.size > 1) {
+    try {
+      d.layout = std::make_shared<Layout>(L);
+      d.halo = make_halo(&ctx->c, L, ctx->c.rank);
+    } catch (...) { delete h; throw; }
+  }
   *da = h;
   API_END
 }
@@ -326,7 +329,7 @@ int b200sp_vec_pointwise_mult(b200sp_vec w, b200sp_vec x, b200sp_vec y) {
   API_BEGIN SAME_SIZE(x, y); SAME_SIZE(x, w); vec_pointwise_mult(w->v.ctx, w->v.n, x->v.d, y->v.d, w->v.d); API_END
 }
 static void global_sum(Ctx *c, int k, double *host) {
-  if (c->size > 1) B2_NCCL(nccl().AllReduce(c->d_scalars, c->d_scalars, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->dcomm) c->dcomm->allreduce_sum(c->d_scalars, k, c->stream);
   c->fetch_scalars(c->d_scalars, k, host);
 }
 int b200sp_vec_dot(b200sp_vec x, b200sp_vec y, double *result) {
@@ -392,7 +395,7 @@ int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz) {
   if (ncols) *ncols = A->m.ncols();
   if (nnz) {
     if (A->m.nest) { *nnz = 0; for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (A->m.blk[i][j]) *nnz += A->m.blk[i][j]->nnz; }
-    else *nnz = A->m.csr->nnz;
+    else *nnz = A->m.csr->nnz + (A->m.csr->off ? A->m.csr->off->nnz : 0);
   }
   API_END
 }
@@ -400,6 +403,38 @@ int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val) {
   API_BEGIN
   Csr &M = plain(A);
   Ctx *c = M.ctx;
+  if (M.halo) {
+    // row-partitioned matrix: local rows with GLOBAL (PETSc numbering) column ids, diagonal and off-diagonal
+    // blocks merged and sorted -- what MatView / MatGetRow show for an MPIAIJ matrix
+    const Csr &O = *M.off;
+    std::vector<int> rp((size_t)M.nrows + 1), cj((size_t)M.nnz + 1), orp((size_t)O.nrows + 1), ocj((size_t)O.nnz + 1), orow((size_t)O.nrows + 1);
+    std::vector<double> va((size_t)M.nnz + 1), ova((size_t)O.nnz + 1);
+    B2_CUDA(cudaMemcpyAsync(rp.data(), M.rowptr.p, sizeof(int) * ((size_t)M.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (M.nnz) B2_CUDA(cudaMemcpyAsync(cj.data(), M.col.p, sizeof(int) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (M.nnz) B2_CUDA(cudaMemcpyAsync(va.data(), M.val.p, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(orp.data(), O.rowptr.p, sizeof(int) * ((size_t)O.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (O.nnz) B2_CUDA(cudaMemcpyAsync(ocj.data(), O.col.p, sizeof(int) * (size_t)O.nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (O.nnz) B2_CUDA(cudaMemcpyAsync(ova.data(), O.val.p, sizeof(double) * (size_t)O.nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (O.nrows) B2_CUDA(cudaMemcpyAsync(orow.data(), M.off_rows.p, sizeof(int) * (size_t)O.nrows, cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    std::vector<int> offidx((size_t)M.nrows, -1);
+    for (int k = 0; k < O.nrows; ++k) offidx[(size_t)orow[(size_t)k]] = k;
+    const int dofc = M.halo_dof;
+    int64_t p = 0;
+    std::vector<std::pair<int, double>> row;
+    for (int r = 0; r < M.nrows; ++r) {
+      if (rowptr) rowptr[r] = (int)p;
+      row.clear();
+      for (int k = rp[(size_t)r]; k < rp[(size_t)r + 1]; ++k) row.push_back({(int)(M.col_gstart + cj[(size_t)k]), va[(size_t)k]});
+      if (offidx[(size_t)r] >= 0)
+        for (int k = orp[(size_t)offidx[(size_t)r]]; k < orp[(size_t)offidx[(size_t)r] + 1]; ++k)
+          row.push_back({M.halo->ghost_gnode[(size_t)(ocj[(size_t)k] / dofc)] * dofc + ocj[(size_t)k] % dofc, ova[(size_t)k]});
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+      for (auto &e : row) { if (col) col[p] = e.first; if (val) val[p] = e.second; ++p; }
+    }
+    if (rowptr) rowptr[M.nrows] = (int)p;
+    return B200SP_OK;
+  }
   if (rowptr) B2_CUDA(cudaMemcpyAsync(rowptr, M.rowptr.p, sizeof(int) * ((size_t)M.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
   if (col && M.nnz) B2_CUDA(cudaMemcpyAsync(col, M.col.p, sizeof(int) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
   if (val && M.nnz) B2_CUDA(cudaMemcpyAsync(val, M.val.p, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));

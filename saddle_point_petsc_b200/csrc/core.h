@@ -47,6 +47,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;  // compute stream (every kernel of the library)
   cudaStream_t stream2 = nullptr; // halo / copy stream
   ncclComm_t comm = nullptr;
+  struct Comm *dcomm = nullptr;   // set when size > 1 (NCCL or in-process thread group), see dist.h
   int num_sms = 148;
   double *d_partials = nullptr; // [RED_MAX_BLOCKS][RED_MAX_OUT]
   unsigned *d_ticket = nullptr;
@@ -129,12 +130,16 @@ struct Vec {
 };
 
 // ------------------------------------------------------------------ DMDA
+struct Layout;
+struct Halo;
 struct Dmda {
-  Ctx *ctx;
-  int M, N;               // nodes
-  int pm, pn;             // process grid
-  int xs, ys, xm, ym;     // owned node box of this rank
+  Ctx *ctx = nullptr;
+  int M = 0, N = 0;                       // nodes
+  int pm = 1, pn = 1;                     // process grid
+  int xs = 0, ys = 0, xm = 0, ym = 0;     // owned node box of this rank
   std::vector<int> lx, ly;
+  std::shared_ptr<Layout> layout;         // null on a plain single-rank grid
+  std::shared_ptr<Halo> halo;             // ghost ring of this rank (null on one rank)
 };
 
 // ------------------------------------------------------------------ Mat
@@ -157,6 +162,13 @@ struct Csr {
   // grid metadata when the matrix came from DMDA assembly (for -pc_type mg); 0 = unknown
   int grid_M = 0, grid_N = 0, dof_r = 0, dof_c = 0;
   std::string tag = "spmv"; // profile class of this matrix's SpMV launches ("spmv:A", "spmv:Bt", ...)
+  // distributed (MPIAIJ-like) part: `this` holds the diagonal block (owned columns, local ids); `off` holds the
+  // entries whose column is a ghost node, rows compressed to the ranks's boundary rows
+  std::shared_ptr<Csr> off;       // nrows = number of boundary rows, ncols = ghosts * dof
+  DevBuf<int> off_rows;           // local row id of every row of `off`
+  std::shared_ptr<Halo> halo;     // column-space halo (null on one rank)
+  int halo_dof = 0;               // dof per node of the column space
+  int64_t row_gstart = 0, col_gstart = 0; // first global row / owned global column of this rank (PETSc numbering)
   void plan();           // histogram + kernel choice (device reduction)
 };
 constexpr int CSR_PAD = 8; // zero entries appended to col/val so vector loads may overrun a row tile
@@ -216,6 +228,8 @@ void assemble_rhs(const Dmda &da, int as_written, int kind, double *f);
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
 std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc);
 std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc); // = interp_q1^T, built directly
+std::shared_ptr<Csr> interp_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc);
+std::shared_ptr<Csr> restrict_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc);
 std::shared_ptr<Csr> csr_alloc_public(Ctx *c, int nrows, int ncols, int64_t nnz);
 std::vector<int> dmda_bc_ids(const Dmda &da, int dof);
 

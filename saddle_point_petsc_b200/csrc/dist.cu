@@ -1,0 +1,253 @@
+// dist.cu -- communicators (NCCL / in-process thread group), DMDA layout arithmetic, halo plan and exchange.
+#include "dist.h"
+#include <algorithm>
+#include <cmath>
+#include "dev.cuh"
+
+namespace b200sp {
+
+// ------------------------------------------------------------------ LocalGroup / LocalComm
+void LocalGroup::barrier() {
+  std::unique_lock<std::mutex> lk(mu);
+  const uint64_t gen = generation;
+  if (++arrived == size) {
+    arrived = 0;
+    ++generation;
+    cv.notify_all();
+  } else {
+    cv.wait(lk, [&] { return generation != gen; });
+  }
+}
+
+namespace {
+
+struct LocalComm : Comm {
+  std::shared_ptr<LocalGroup> g;
+  int r, dev;
+  std::vector<const std::vector<HaloMsg> *> *msg_tab; // shared table of per-rank message lists
+  LocalComm(std::shared_ptr<LocalGroup> g_, int rank, int device) : g(g_), r(rank), dev(device) { g->device[(size_t)rank] = device; }
+  int rank() const override { return r; }
+  int size() const override { return g->size; }
+  void barrier() override { g->barrier(); }
+  void allreduce_sum(double *d, int k, cudaStream_t s) override {
+    B2_REQUIRE(k <= N_SCALARS, "allreduce: too many scalars");
+    double *mine = g->host_scratch.data() + (size_t)r * N_SCALARS;
+    B2_CUDA(cudaMemcpyAsync(mine, d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    g->barrier();
+    double tot[N_SCALARS];
+    for (int j = 0; j < k; ++j) { // fixed rank order: deterministic
+      double t = 0.0;
+      for (int q = 0; q < g->size; ++q) t += g->host_scratch[(size_t)q * N_SCALARS + j];
+      tot[j] = t;
+    }
+    g->barrier(); // everyone has read before anyone overwrites host_scratch again
+    B2_CUDA(cudaMemcpyAsync(d, tot, sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s)); // tot lives on this stack frame
+  }
+  void exchange(const double *sendbuf, double *recvbuf, const std::vector<HaloMsg> &msgs, cudaStream_t s) override {
+    B2_CUDA(cudaStreamSynchronize(s)); // my packed data is complete
+    g->ptr_a[(size_t)r] = sendbuf;
+    g->ptr_b[(size_t)r] = reinterpret_cast<double *>(const_cast<std::vector<HaloMsg> *>(&msgs));
+    g->barrier();
+    for (const HaloMsg &m : msgs) {
+      if (m.recv_cnt == 0) continue;
+      // the peer's send offset for me is in the peer's message list
+      const auto *pm = reinterpret_cast<const std::vector<HaloMsg> *>(g->ptr_b[(size_t)m.peer]);
+      int64_t off = -1;
+      for (const HaloMsg &q : *pm) if (q.peer == r) { off = q.send_off; B2_REQUIRE(q.send_cnt == m.recv_cnt, "halo: asymmetric message sizes"); }
+      B2_REQUIRE(off >= 0, "halo: peer has no message for this rank");
+      B2_CUDA(cudaMemcpyPeerAsync(recvbuf + m.recv_off, dev, g->ptr_a[(size_t)m.peer] + off, g->device[(size_t)m.peer], sizeof(double) * (size_t)m.recv_cnt, s));
+    }
+    B2_CUDA(cudaStreamSynchronize(s));
+    g->barrier(); // peers may now reuse their send buffers
+  }
+  void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) override {
+    B2_CUDA(cudaStreamSynchronize(s));
+    g->ptr_a[(size_t)r] = in;
+    g->barrier();
+    for (int q = 0; q < g->size; ++q)
+      B2_CUDA(cudaMemcpyPeerAsync(out + (size_t)q * cnt, dev, g->ptr_a[(size_t)q], g->device[(size_t)q], sizeof(double) * (size_t)cnt, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    g->barrier();
+  }
+};
+
+struct NcclComm : Comm {
+  ncclComm_t c;
+  int r, n;
+  NcclComm(ncclComm_t c_, int rank, int size) : c(c_), r(rank), n(size) {}
+  int rank() const override { return r; }
+  int size() const override { return n; }
+  void barrier() override {}
+  void allreduce_sum(double *d, int k, cudaStream_t s) override { B2_NCCL(nccl().AllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c, s)); }
+  void exchange(const double *sendbuf, double *recvbuf, const std::vector<HaloMsg> &msgs, cudaStream_t s) override {
+    B2_NCCL(nccl().GroupStart());
+    for (const HaloMsg &m : msgs) {
+      if (m.send_cnt) B2_NCCL(nccl().Send(sendbuf + m.send_off, (size_t)m.send_cnt, ncclDouble, m.peer, c, s));
+      if (m.recv_cnt) B2_NCCL(nccl().Recv(recvbuf + m.recv_off, (size_t)m.recv_cnt, ncclDouble, m.peer, c, s));
+    }
+    B2_NCCL(nccl().GroupEnd());
+  }
+  void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) override {
+    // grouped send/recv (ncclAllGather is not in the dlopen table; this is the same wire pattern)
+    B2_NCCL(nccl().GroupStart());
+    for (int q = 0; q < n; ++q) {
+      B2_NCCL(nccl().Send(in, (size_t)cnt, ncclDouble, q, c, s));
+      B2_NCCL(nccl().Recv(out + (size_t)q * cnt, (size_t)cnt, ncclDouble, q, c, s));
+    }
+    B2_NCCL(nccl().GroupEnd());
+  }
+};
+
+} // namespace
+
+Comm *make_local_comm(std::shared_ptr<LocalGroup> g, int rank, int device) { return new LocalComm(g, rank, device); }
+Comm *make_nccl_comm(ncclComm_t c, int rank, int size) { return new NcclComm(c, rank, size); }
+
+// ------------------------------------------------------------------ Layout
+Layout::Layout(int M_, int N_, int size_) : M(M_), N(N_), size(size_) {
+  B2_REQUIRE(M >= 2 && N >= 2 && size >= 1, "dmda: need M,N >= 2 and size >= 1");
+  dmda_proc_grid(M, N, size, &m, &n);
+  B2_REQUIRE(m * n == size, "dmda: size does not factor into a process grid");
+  B2_REQUIRE(m <= M && n <= N, "dmda: more ranks than nodes in a direction");
+  lx.resize((size_t)m);
+  ly.resize((size_t)n);
+  dmda_ownership(M, m, lx.data());
+  dmda_ownership(N, n, ly.data());
+  finish();
+}
+Layout::Layout(int M_, int N_, int m_, int n_, const std::vector<int> &lx_, const std::vector<int> &ly_)
+    : M(M_), N(N_), size(m_ * n_), m(m_), n(n_), lx(lx_), ly(ly_) {
+  finish();
+}
+void Layout::finish() {
+  xoff.assign((size_t)m + 1, 0);
+  yoff.assign((size_t)n + 1, 0);
+  for (int i = 0; i < m; ++i) xoff[(size_t)i + 1] = xoff[(size_t)i] + lx[(size_t)i];
+  for (int j = 0; j < n; ++j) yoff[(size_t)j + 1] = yoff[(size_t)j] + ly[(size_t)j];
+  B2_REQUIRE(xoff[(size_t)m] == M && yoff[(size_t)n] == N, "dmda: ownership ranges do not sum to the grid size");
+  rstart.assign((size_t)size + 1, 0);
+  for (int r = 0; r < size; ++r) rstart[(size_t)r + 1] = rstart[(size_t)r] + lx[(size_t)(r % m)] * ly[(size_t)(r / m)];
+}
+int Layout::owner_x(int i) const { return (int)(std::upper_bound(xoff.begin(), xoff.end(), i) - xoff.begin()) - 1; }
+int Layout::owner_y(int j) const { return (int)(std::upper_bound(yoff.begin(), yoff.end(), j) - yoff.begin()) - 1; }
+int Layout::gnode(int i, int j) const {
+  const int pi = owner_x(i), pj = owner_y(j), r = pj * m + pi;
+  return rstart[(size_t)r] + (j - yoff[(size_t)pj]) * lx[(size_t)pi] + (i - xoff[(size_t)pi]);
+}
+void Layout::box(int rank, int *xs, int *ys, int *xm, int *ym) const {
+  const int pi = rank % m, pj = rank / m;
+  *xs = xoff[(size_t)pi]; *ys = yoff[(size_t)pj]; *xm = lx[(size_t)pi]; *ym = ly[(size_t)pj];
+}
+Layout Layout::coarsen() const {
+  B2_REQUIRE((M - 1) % 2 == 0 && (N - 1) % 2 == 0, "dmda: grid not coarsenable");
+  const int Mc = (M - 1) / 2 + 1, Nc = (N - 1) / 2 + 1;
+  std::vector<int> clx((size_t)m), cly((size_t)n);
+  for (int i = 0; i < m; ++i) { // coarse ic owned by the owner of fine 2*ic: ic in [ceil(xs/2), floor((xe-1)/2)]
+    const int lo = (xoff[(size_t)i] + 1) / 2, hi = (xoff[(size_t)i + 1] - 1) / 2;
+    clx[(size_t)i] = hi - lo + 1;
+  }
+  for (int j = 0; j < n; ++j) {
+    const int lo = (yoff[(size_t)j] + 1) / 2, hi = (yoff[(size_t)j + 1] - 1) / 2;
+    cly[(size_t)j] = hi - lo + 1;
+  }
+  for (int v : clx) B2_REQUIRE(v >= 2, "dmda: a rank would own fewer than 2 coarse nodes in x; use fewer distributed levels");
+  for (int v : cly) B2_REQUIRE(v >= 2, "dmda: a rank would own fewer than 2 coarse nodes in y; use fewer distributed levels");
+  return Layout(Mc, Nc, m, n, clx, cly);
+}
+
+// ------------------------------------------------------------------ Halo
+namespace {
+__global__ void __launch_bounds__(256) k_pack(int n, int dof, const int *__restrict__ lnode, const double *__restrict__ x, double *buf) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * dof; t += gridDim.x * blockDim.x) {
+    const int k = t / dof, c = t % dof;
+    buf[t] = x[(size_t)lnode[k] * dof + c];
+  }
+}
+} // namespace
+
+Halo::~Halo() {
+  if (ev_packed) cudaEventDestroy(ev_packed);
+  if (ev_arrived) cudaEventDestroy(ev_arrived);
+}
+
+std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
+  auto h = std::make_shared<Halo>();
+  h->ctx = c;
+  h->M = L.M; h->N = L.N;
+  L.box(rank, &h->xs, &h->ys, &h->xm, &h->ym);
+  const int xs = h->xs, ys = h->ys, xm = h->xm, ym = h->ym;
+  B2_REQUIRE(L.size == 1 || (xm >= 2 && ym >= 2), "dmda: every rank must own at least 2 x 2 nodes");
+  h->n_owned = xm * ym;
+  struct G { int g, owner, i, j; };
+  std::vector<G> gh;
+  for (int j = std::max(ys - 1, 0); j <= std::min(ys + ym, L.N - 1); ++j)
+    for (int i = std::max(xs - 1, 0); i <= std::min(xs + xm, L.M - 1); ++i)
+      if (i < xs || i >= xs + xm || j < ys || j >= ys + ym) gh.push_back({L.gnode(i, j), L.owner(i, j), i, j});
+  std::sort(gh.begin(), gh.end(), [](const G &a, const G &b) { return a.g < b.g; });
+  h->n_ghost = (int)gh.size();
+  std::vector<int> ring((size_t)(2 * (xm + 2) + 2 * ym), -1);
+  ColSpace cs{xs, ys, xm, ym, nullptr};
+  for (int t = 0; t < h->n_ghost; ++t) {
+    h->ghost_gnode.push_back(gh[(size_t)t].g);
+    h->ghost_i.push_back(gh[(size_t)t].i);
+    h->ghost_j.push_back(gh[(size_t)t].j);
+    ring[(size_t)cs.ring_id(gh[(size_t)t].i, gh[(size_t)t].j)] = t;
+  }
+  // messages: neighbours in ascending rank; receives are contiguous ranges of the sorted ghost list
+  std::vector<int> send_lnode;
+  for (int q = 0; q < L.size; ++q) {
+    if (q == rank) continue;
+    int qxs, qys, qxm, qym;
+    L.box(q, &qxs, &qys, &qxm, &qym);
+    const int i0 = std::max(std::max(qxs - 1, 0), xs), i1 = std::min(std::min(qxs + qxm, L.M - 1), xs + xm - 1);
+    const int j0 = std::max(std::max(qys - 1, 0), ys), j1 = std::min(std::min(qys + qym, L.N - 1), ys + ym - 1);
+    HaloMsg msg{q, (int64_t)send_lnode.size(), 0, 0, 0};
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) { send_lnode.push_back((j - ys) * xm + (i - xs)); msg.send_cnt++; }
+    int first = -1, cnt = 0;
+    for (int t = 0; t < h->n_ghost; ++t)
+      if (gh[(size_t)t].owner == q) { if (first < 0) first = t; cnt++; }
+    msg.recv_off = first < 0 ? 0 : first;
+    msg.recv_cnt = cnt;
+    if (msg.send_cnt || msg.recv_cnt) h->node_msgs.push_back(msg);
+  }
+  h->n_send = (int)send_lnode.size();
+  h->d_send_lnode.alloc((size_t)h->n_send + 1);
+  h->d_ring2ghost.alloc(ring.size() + 1);
+  if (h->n_send) B2_CUDA(cudaMemcpyAsync(h->d_send_lnode.p, send_lnode.data(), sizeof(int) * send_lnode.size(), cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaMemcpyAsync(h->d_ring2ghost.p, ring.data(), sizeof(int) * ring.size(), cudaMemcpyHostToDevice, c->stream));
+  h->sendbuf.alloc((size_t)h->n_send * 2 + 2);
+  h->ghost.alloc((size_t)h->n_ghost * 2 + 2);
+  h->ghost.zero(c->stream);
+  B2_CUDA(cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
+  c->sync();
+  return h;
+}
+
+void Halo::begin(const double *x, int dof) {
+  B2_REQUIRE(dof == 1 || dof == 2, "halo: dof must be 1 or 2");
+  Ctx *c = ctx;
+  if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
+  if (n_send) {
+    LaunchScope ls(c, "halo");
+    int grid = (n_send * dof + 255) / 256;
+    k_pack<<<grid, 256, 0, c->stream>>>(n_send, dof, d_send_lnode.p, x, sendbuf.p);
+    check_launch("k_pack");
+  }
+  B2_CUDA(cudaEventRecord(ev_packed, c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->stream2, ev_packed, 0));
+  std::vector<HaloMsg> msgs = node_msgs;
+  for (HaloMsg &m : msgs) { m.send_off *= dof; m.send_cnt *= dof; m.recv_off *= dof; m.recv_cnt *= dof; }
+  c->dcomm->exchange(sendbuf.p, ghost.p, msgs, c->stream2);
+  B2_CUDA(cudaEventRecord(ev_arrived, c->stream2));
+}
+void Halo::end() {
+  Ctx *c = ctx;
+  if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
+  B2_CUDA(cudaStreamWaitEvent(c->stream, ev_arrived, 0));
+}
+
+} // namespace b200sp

@@ -1,0 +1,97 @@
+// dist.h -- row-partitioned (DMDA) distribution: communicator, layout, halo exchange.
+// Replaces what PETSc does inside MatMult_MPIAIJ / VecScatter / MPI_Allreduce for the reference's
+// DMDACreate2d(PETSC_COMM_WORLD, ..., PETSC_DECIDE, PETSC_DECIDE, ...) partition (src/Discretization.c:17).
+#pragma once
+#include <condition_variable>
+#include <mutex>
+#include "core.h"
+
+namespace b200sp {
+
+// ---------------------------------------------------------------- communicator
+// Two transports behind one interface:
+//   NcclComm  one process per GPU (torchrun): ncclAllReduce / grouped ncclSend+ncclRecv on the compute streams
+//   LocalComm all ranks are threads of ONE process (one or several GPUs): host barrier + cudaMemcpyPeerAsync.
+//             Used by the tests (the whole distributed algorithm runs on a 1-GPU box, ranks never wait on each
+//             other inside a kernel) and usable as a single-process multi-GPU mode.
+struct HaloMsg { int peer; int64_t send_off, send_cnt, recv_off, recv_cnt; }; // in doubles
+
+struct Comm {
+  virtual ~Comm() {}
+  virtual int rank() const = 0;
+  virtual int size() const = 0;
+  // in-place global sum of k doubles on the device, ordered on `s`
+  virtual void allreduce_sum(double *d, int k, cudaStream_t s) = 0;
+  // neighbour exchange: sendbuf/recvbuf are device arrays of this rank; message list is symmetric across ranks
+  virtual void exchange(const double *sendbuf, double *recvbuf, const std::vector<HaloMsg> &msgs, cudaStream_t s) = 0;
+  // gather `cnt` doubles from every rank into out[rank*cnt...] on every rank (redundant coarse multigrid levels)
+  virtual void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) = 0;
+  virtual void barrier() = 0;
+};
+
+struct LocalGroup { // shared by the rank-threads of one process
+  int size;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t generation = 0;
+  std::vector<const double *> ptr_a;   // per rank: published device pointer (send buffer / gather input)
+  std::vector<double *> ptr_b;         // per rank: published device pointer (reduction operand)
+  std::vector<int> device;
+  std::vector<double> host_scratch;    // [size][N_SCALARS]
+  explicit LocalGroup(int n) : size(n), ptr_a((size_t)n), ptr_b((size_t)n), device((size_t)n, 0), host_scratch((size_t)n * N_SCALARS) {}
+  void barrier();
+};
+
+Comm *make_local_comm(std::shared_ptr<LocalGroup> g, int rank, int device);
+Comm *make_nccl_comm(ncclComm_t c, int rank, int size);
+
+// ---------------------------------------------------------------- layout (host index arithmetic)
+struct Layout {
+  int M = 0, N = 0, size = 1, m = 1, n = 1;
+  std::vector<int> lx, ly, xoff, yoff, rstart; // rstart[r] = first PETSc global node id of rank r
+  Layout() {}
+  Layout(int M_, int N_, int size_);                                                    // PETSC_DECIDE ownership
+  Layout(int M_, int N_, int m_, int n_, const std::vector<int> &lx_, const std::vector<int> &ly_); // explicit ownership
+  void finish();
+  int owner_x(int i) const;
+  int owner_y(int j) const;
+  int owner(int i, int j) const { return owner_y(j) * m + owner_x(i); }
+  int gnode(int i, int j) const;
+  void box(int rank, int *xs, int *ys, int *xm, int *ym) const;
+  // the layout of the next coarser DMDA: coarse node ic belongs to the owner of fine node 2*ic (DMCoarsen keeps the process grid)
+  Layout coarsen() const;
+};
+
+// ---------------------------------------------------------------- halo of one rank on one layout
+struct Halo {
+  Ctx *ctx = nullptr;
+  int xs = 0, ys = 0, xm = 0, ym = 0, M = 0, N = 0;
+  int n_owned = 0, n_ghost = 0;                   // nodes
+  std::vector<int> ghost_gnode, ghost_i, ghost_j; // sorted by PETSc global node id (MPIAIJ garray order)
+  std::vector<HaloMsg> node_msgs;                 // per neighbour, counts in NODES
+  DevBuf<int> d_send_lnode;                       // owned local node ids to pack, grouped by neighbour
+  int n_send = 0;
+  DevBuf<int> d_ring2ghost;                       // ring position -> ghost index (-1 outside the domain)
+  DevBuf<double> sendbuf, ghost;                  // sized for dof <= 2
+  cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
+  ~Halo();
+  // pack x (dof interleaved) and start the exchange on the halo stream; end() makes the compute stream wait for it
+  void begin(const double *x, int dof);
+  void end();
+};
+std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank);
+
+// device-side view of a column space (owned box + ghost ring) used by the assembly kernels to classify columns
+struct ColSpace {
+  int xs, ys, xm, ym;
+  const int *ring2ghost; // null on one rank
+  __host__ __device__ int ring_id(int i, int j) const {
+    if (j == ys - 1) return i - (xs - 1);
+    if (j == ys + ym) return (xm + 2) + i - (xs - 1);
+    if (i == xs - 1) return 2 * (xm + 2) + (j - ys);
+    return 2 * (xm + 2) + ym + (j - ys);
+  }
+};
+
+} // namespace b200sp

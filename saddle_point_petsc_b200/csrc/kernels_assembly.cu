@@ -12,6 +12,7 @@
 //      reference's element order (j outer, i inner, :146-147) starting from +0.0.
 // The reference's truncated Gauss abscissa 0.57735026919 (:52-55) is kept on purpose.
 #include "dev.cuh"
+#include "dist.h"
 #include <algorithm>
 
 namespace b200sp {
@@ -238,6 +239,170 @@ __global__ void __launch_bounds__(256) k_box_fill(GridBox g, ElemBox eb, int dof
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Distributed (row-partitioned) CSR stage.  A "row enumerator" lists the entries of one owned row in ascending
+// (column node j, column node i, column dof) order; the builder classifies every column node as owned (diagonal
+// block, local ids) or ghost (off-diagonal block, ghost ids in MPIAIJ garray order) exactly like MatMPIAIJ.
+// Values are the same sums in the same order as on one rank: the assembled matrix is partition-independent.
+struct RowBox { int xs, ys, xm, ym; };
+
+struct BoxEnum { // A, B^T, B, C, Q: box stencil on one grid
+  int M, N;
+  RowBox rb;
+  ElemBox eb;
+  int dofr, dofc, transposed;
+  const double *E;
+  __device__ int nrows() const { return rb.xm * rb.ym * dofr; }
+  template <class Emit> __device__ void enumerate(int r, Emit &emit) const {
+    const int64_t nel = (int64_t)eb.enx * eb.eny;
+    const int node = r / dofr, c = r % dofr;
+    const int i = rb.xs + node % rb.xm, j = rb.ys + node / rb.xm;
+    for (int jj = max(j - 1, 0); jj <= min(j + 1, N - 1); ++jj)
+      for (int ii = max(i - 1, 0); ii <= min(i + 1, M - 1); ++ii) {
+        const int ej0 = max(max(j, jj) - 1, 0), ej1 = min(min(j, jj), N - 2);
+        const int ei0 = max(max(i, ii) - 1, 0), ei1 = min(min(i, ii), M - 2);
+        for (int cc = 0; cc < dofc; ++cc) {
+          double acc = 0.0;
+          if (E)
+            for (int ej = ej0; ej <= ej1; ++ej)
+              for (int ei = ei0; ei <= ei1; ++ei) {
+                const int la = local_node(i, j, ei, ej) * dofr + c;
+                const int lb = local_node(ii, jj, ei, ej) * dofc + cc;
+                const int entry = transposed ? lb * (4 * dofr) + la : la * (4 * dofc) + lb;
+                const int64_t e = (int64_t)(ej - eb.ey0) * eb.enx + (ei - eb.ex0);
+                acc += E[(size_t)entry * nel + e];
+              }
+          emit(ii, jj, cc, acc);
+        }
+      }
+  }
+};
+struct InterpEnum { // P: rows = owned fine nodes, columns = coarse nodes
+  int Mc, Nc, dof, bc;
+  RowBox rb; // fine
+  __device__ int nrows() const { return rb.xm * rb.ym * dof; }
+  template <class Emit> __device__ void enumerate(int r, Emit &emit) const {
+    const int Mf = 2 * Mc - 1, Nf = 2 * Nc - 1;
+    const int node = r / dof, c = r % dof;
+    const int i = rb.xs + node % rb.xm, j = rb.ys + node / rb.xm;
+    const int fb = (i == 0 || i == Mf - 1 || j == 0 || j == Nf - 1);
+    const int ni = (i & 1) ? 2 : 1, nj = (j & 1) ? 2 : 1;
+    for (int b = 0; b < nj; ++b)
+      for (int a = 0; a < ni; ++a) {
+        const int ic = i / 2 + a, jc = j / 2 + b;
+        const int cb = (ic == 0 || ic == Mc - 1 || jc == 0 || jc == Nc - 1);
+        double w = (ni == 2 ? 0.5 : 1.0) * (nj == 2 ? 0.5 : 1.0);
+        if (bc && (fb || cb)) w = 0.0;
+        emit(ic, jc, c, w);
+      }
+  }
+};
+struct RestrictEnum { // R = P^T: rows = owned coarse nodes, columns = fine nodes
+  int Mc, Nc, dof, bc;
+  RowBox rb; // coarse
+  __device__ int nrows() const { return rb.xm * rb.ym * dof; }
+  template <class Emit> __device__ void enumerate(int r, Emit &emit) const {
+    const int Mf = 2 * Mc - 1, Nf = 2 * Nc - 1;
+    const int node = r / dof, c = r % dof;
+    const int ic = rb.xs + node % rb.xm, jc = rb.ys + node / rb.xm;
+    const int cb = (ic == 0 || ic == Mc - 1 || jc == 0 || jc == Nc - 1);
+    for (int j = max(2 * jc - 1, 0); j <= min(2 * jc + 1, Nf - 1); ++j)
+      for (int i = max(2 * ic - 1, 0); i <= min(2 * ic + 1, Mf - 1); ++i) {
+        const int fb = (i == 0 || i == Mf - 1 || j == 0 || j == Nf - 1);
+        double w = (i == 2 * ic ? 1.0 : 0.5) * (j == 2 * jc ? 1.0 : 0.5);
+        if (bc && (fb || cb)) w = 0.0;
+        emit(i, j, c, w);
+      }
+  }
+};
+
+struct CountEmit {
+  ColSpace cs;
+  int nd = 0, no = 0;
+  __device__ void operator()(int ci, int cj, int, double) {
+    if (ci >= cs.xs && ci < cs.xs + cs.xm && cj >= cs.ys && cj < cs.ys + cs.ym) ++nd; else ++no;
+  }
+};
+struct FillEmit {
+  ColSpace cs;
+  int dofc, pd, po;
+  int *col_d; double *val_d; int *col_o; double *val_o;
+  __device__ void operator()(int ci, int cj, int cc, double v) {
+    if (ci >= cs.xs && ci < cs.xs + cs.xm && cj >= cs.ys && cj < cs.ys + cs.ym) {
+      col_d[pd] = ((cj - cs.ys) * cs.xm + (ci - cs.xs)) * dofc + cc;
+      val_d[pd++] = v;
+    } else {
+      col_o[po] = cs.ring2ghost[cs.ring_id(ci, cj)] * dofc + cc;
+      val_o[po++] = v;
+    }
+  }
+};
+template <class E> __global__ void __launch_bounds__(128) k_dist_count(E e, ColSpace cs, int *len_d, int *len_o, int *has_o) {
+  const int nrows = e.nrows();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    CountEmit em{cs};
+    e.enumerate(r, em);
+    len_d[r] = em.nd; len_o[r] = em.no; has_o[r] = em.no > 0;
+  }
+}
+__global__ void __launch_bounds__(256) k_compact_off(int nrows, const int *__restrict__ has_o, const int *__restrict__ oidx, const int *__restrict__ len_o,
+                                                     int *off_rows, int *len_oc) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x)
+    if (has_o[r]) { off_rows[oidx[r]] = r; len_oc[oidx[r]] = len_o[r]; }
+}
+template <class E> __global__ void __launch_bounds__(128) k_dist_fill(E e, ColSpace cs, int dofc, const int *__restrict__ rp_d, int *col_d, double *val_d,
+                                                                      const int *__restrict__ has_o, const int *__restrict__ oidx, const int *__restrict__ rp_o,
+                                                                      int *col_o, double *val_o) {
+  const int nrows = e.nrows();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    FillEmit em{cs, dofc, rp_d[r], has_o[r] ? rp_o[oidx[r]] : 0, col_d, val_d, col_o, val_o};
+    e.enumerate(r, em);
+  }
+}
+
+template <class E>
+std::shared_ptr<Csr> build_dist(Ctx *c, const E &e, int nrows, const Halo &colh, int dofc, const char *tag) {
+  ColSpace cs{colh.xs, colh.ys, colh.xm, colh.ym, colh.d_ring2ghost.p};
+  const int ncols = colh.n_owned * dofc;
+  DevBuf<int> len_d((size_t)nrows + 1), len_o((size_t)nrows + 1), has_o((size_t)nrows + 1), rp_d((size_t)nrows + 1), oidx((size_t)nrows + 1);
+  const int grid = std::max(1, std::min((nrows + 127) / 128, c->num_sms * 16));
+  {
+    LaunchScope ls(c, "assembly");
+    k_dist_count<E><<<grid, 128, 0, c->stream>>>(e, cs, len_d.p, len_o.p, has_o.p);
+    check_launch("k_dist_count");
+  }
+  int nnz_d = 0, n_off = 0, nnz_o = 0;
+  exclusive_scan_i32(c, len_d.p, rp_d.p, nrows, &nnz_d);
+  exclusive_scan_i32(c, has_o.p, oidx.p, nrows, &n_off);
+  auto A = csr_alloc_public(c, nrows, ncols, nnz_d);
+  auto O = csr_alloc_public(c, n_off, colh.n_ghost * dofc, 0);
+  DevBuf<int> len_oc((size_t)n_off + 1);
+  A->off_rows.alloc((size_t)n_off + 1);
+  if (n_off) {
+    LaunchScope ls(c, "assembly");
+    k_compact_off<<<std::max(1, std::min((nrows + 255) / 256, c->num_sms * 16)), 256, 0, c->stream>>>(nrows, has_o.p, oidx.p, len_o.p, A->off_rows.p, len_oc.p);
+    check_launch("k_compact_off");
+  }
+  exclusive_scan_i32(c, len_oc.p, O->rowptr.p, n_off, &nnz_o);
+  O->nnz = nnz_o;
+  O->col.alloc((size_t)nnz_o + CSR_PAD);
+  O->val.alloc((size_t)nnz_o + CSR_PAD);
+  O->col.zero(c->stream);
+  O->val.zero(c->stream);
+  B2_CUDA(cudaMemcpyAsync(A->rowptr.p, rp_d.p, sizeof(int) * ((size_t)nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    LaunchScope ls(c, "assembly");
+    k_dist_fill<E><<<grid, 128, 0, c->stream>>>(e, cs, dofc, A->rowptr.p, A->col.p, A->val.p, has_o.p, oidx.p, O->rowptr.p, O->col.p, O->val.p);
+    check_launch("k_dist_fill");
+  }
+  c->sync();
+  A->tag = tag;
+  A->plan();
+  O->tag = std::string(tag) + "_off";
+  A->off = O;
+  return A;
+}
+
 // AssembleRHS_Laplace (:196-219): f[node,c] = sum of Fe over the <= 4 elements in (ej, ei) order
 __global__ void __launch_bounds__(256) k_rhs_gather(GridBox g, ElemBox eb, const double *__restrict__ Fe, double *__restrict__ f) {
   const int nrows = g.xm * g.ym * 2;
@@ -349,7 +514,17 @@ void run_elements(const Dmda &da, int as_written, int rhs_kind, int want, ElemAr
 
 std::shared_ptr<Csr> build_box_matrix(const Dmda &da, const ElemArrays &ea, int dofr, int dofc, int transposed, const double *E) {
   Ctx *c = da.ctx;
-  B2_REQUIRE(c->size == 1, "device assembly: multi-rank layout not available in this build step");
+  if (da.halo) { // row-partitioned: diagonal + off-diagonal blocks, ghost columns in MPIAIJ order
+    BoxEnum e{da.M, da.N, RowBox{da.xs, da.ys, da.xm, da.ym}, ea.eb, dofr, dofc, transposed, E};
+    auto A = build_dist(c, e, da.xm * da.ym * dofr, *da.halo, dofc, "spmv");
+    A->halo = da.halo;
+    A->halo_dof = dofc;
+    const int64_t g0 = da.layout->rstart[(size_t)c->rank];
+    A->row_gstart = g0 * dofr;
+    A->col_gstart = g0 * dofc;
+    A->grid_M = da.M; A->grid_N = da.N; A->dof_r = dofr; A->dof_c = dofc;
+    return A;
+  }
   GridBox g{da.M, da.N, da.xs, da.ys, da.xm, da.ym};
   const int nrows = da.xm * da.ym * dofr, ncols = da.xm * da.ym * dofc;
   DevBuf<int> len((size_t)nrows + 1), rp((size_t)nrows + 1);
@@ -452,6 +627,30 @@ std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc) {
   c->sync();
   R->tag = "spmv:R";
   R->plan();
+  return R;
+}
+
+// distributed P (rows: owned fine nodes of `fine`; columns: coarse nodes of `coarse`) and R = P^T
+std::shared_ptr<Csr> interp_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc) {
+  Ctx *c = fine.ctx;
+  B2_REQUIRE(fine.halo && coarse.halo && fine.M == 2 * coarse.M - 1 && fine.N == 2 * coarse.N - 1, "interp_q1_dist: grids do not nest");
+  InterpEnum e{coarse.M, coarse.N, dof, bc, RowBox{fine.xs, fine.ys, fine.xm, fine.ym}};
+  auto P = build_dist(c, e, fine.xm * fine.ym * dof, *coarse.halo, dof, "spmv:P");
+  P->halo = coarse.halo;
+  P->halo_dof = dof;
+  P->row_gstart = (int64_t)fine.layout->rstart[(size_t)c->rank] * dof;
+  P->col_gstart = (int64_t)coarse.layout->rstart[(size_t)c->rank] * dof;
+  return P;
+}
+std::shared_ptr<Csr> restrict_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc) {
+  Ctx *c = fine.ctx;
+  B2_REQUIRE(fine.halo && coarse.halo && fine.M == 2 * coarse.M - 1 && fine.N == 2 * coarse.N - 1, "restrict_q1_dist: grids do not nest");
+  RestrictEnum e{coarse.M, coarse.N, dof, bc, RowBox{coarse.xs, coarse.ys, coarse.xm, coarse.ym}};
+  auto R = build_dist(c, e, coarse.xm * coarse.ym * dof, *fine.halo, dof, "spmv:R");
+  R->halo = fine.halo;
+  R->halo_dof = dof;
+  R->row_gstart = (int64_t)coarse.layout->rstart[(size_t)c->rank] * dof;
+  R->col_gstart = (int64_t)fine.layout->rstart[(size_t)c->rank] * dof;
   return R;
 }
 

@@ -14,6 +14,7 @@
 //   SPMV_BLOCK   very long rows (dense constraint rows): one CTA per row.
 // Epilogue (fused): y = beta_z*z + alpha*(A x)  covers MatMult, MatMultAdd and the residual b - A x.
 #include "dev.cuh"
+#include "dist.h"
 #include <type_traits>
 
 namespace b200sp {
@@ -157,6 +158,28 @@ __global__ void __launch_bounds__(256) k_zero_rows_cols(int nrows, const int *__
     }
   }
 }
+// y[off_rows[k]] += alpha * (row k of the off-diagonal block) . ghost values   (the second half of MatMult_MPIAIJ)
+__global__ void __launch_bounds__(128) k_spmv_offdiag(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                                                      const int *__restrict__ off_rows, const double *__restrict__ ghost, double *y, double alpha) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int t = rowptr[k]; t < rowptr[k + 1]; ++t) s += val[t] * ghost[col[t]];
+    y[off_rows[k]] += alpha * s;
+  }
+}
+// zero the off-diagonal block: whole rows whose local row is flagged, and entries whose ghost column is flagged
+__global__ void __launch_bounds__(128) k_zero_offdiag(int n, const int *__restrict__ rowptr, const int *__restrict__ col, double *val,
+                                                      const int *__restrict__ off_rows, const unsigned char *__restrict__ rowflag,
+                                                      const double *__restrict__ ghostflag) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const bool rz = rowflag && rowflag[off_rows[k]];
+    for (int t = rowptr[k]; t < rowptr[k + 1]; ++t)
+      if (rz || (ghostflag && ghostflag[col[t]] != 0.0)) val[t] = 0.0;
+  }
+}
+__global__ void k_flag_to_double(int n, const unsigned char *flag, double *out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = flag[i] ? 1.0 : 0.0;
+}
 __global__ void k_mark(int n, const int *idx, unsigned char *flag) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flag[idx[i]] = 1;
 }
@@ -190,7 +213,27 @@ void Csr::plan() {
   lanes_per_row = mean <= 2 ? 2 : mean <= 4 ? 4 : mean <= 8 ? 8 : mean <= 16 ? 16 : 32;
 }
 
+static void csr_spmv_local(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z);
+
+// Distributed MatMult (MatMult_MPIAIJ): start the halo exchange of x, multiply the diagonal block while the
+// ghosts travel (separate stream), then add the off-diagonal block's contribution on the boundary rows.
 void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+  Ctx *c = A.ctx;
+  const bool dist = A.halo && c->dcomm;
+  if (dist) A.halo->begin(x, A.halo_dof);
+  csr_spmv_local(A, x, y, alpha, z, beta_z);
+  if (dist) {
+    A.halo->end();
+    if (A.off && A.off->nrows > 0) {
+      LaunchScope ls(c, "spmv:offdiag");
+      const int n = A.off->nrows;
+      k_spmv_offdiag<<<(n + 127) / 128, 128, 0, c->stream>>>(n, A.off->rowptr.p, A.off->col.p, A.off->val.p, A.off_rows.p, A.halo->ghost.p, y, alpha);
+      check_launch("k_spmv_offdiag");
+    }
+  }
+}
+
+static void csr_spmv_local(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
   Ctx *c = A.ctx;
   if (A.nrows <= 0) return;
   LaunchScope ls(c, A.tag.c_str());
@@ -244,11 +287,13 @@ void csr_get_diagonal(const Csr &A, double *d) {
 
 void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool do_rows, bool do_cols, bool set_diag) {
   Ctx *c = A.ctx;
-  if (n <= 0 || A.nrows <= 0) return;
-  DevBuf<int> d_idx((size_t)n);
-  B2_CUDA(cudaMemcpyAsync(d_idx.p, rows_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  const bool dist = A.halo && c->dcomm;
+  if ((n <= 0 && !dist) || A.nrows <= 0) return; // collective when distributed: ranks without ids still exchange flags
+  DevBuf<int> d_idx((size_t)n + 1);
+  if (n > 0) B2_CUDA(cudaMemcpyAsync(d_idx.p, rows_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   DevBuf<unsigned char> rowflag, colflag;
   int g = (n + 255) / 256;
+  if (g < 1) g = 1;
   if (do_rows) {
     rowflag.alloc((size_t)A.nrows);
     rowflag.zero(c->stream);
@@ -260,6 +305,23 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
     colflag.zero(c->stream);
     LaunchScope ls(c, "setup");
     k_mark<<<g, 256, 0, c->stream>>>(n, d_idx.p, colflag.p);
+  }
+  if (dist && A.off) { // ghost columns: the owners' column flags travel through the same halo as x
+    DevBuf<double> fl((size_t)A.ncols + 2);
+    const double *gf = nullptr;
+    if (do_cols) {
+      { LaunchScope ls(c, "setup"); k_flag_to_double<<<(A.ncols + 255) / 256, 256, 0, c->stream>>>(A.ncols, colflag.p, fl.p); }
+      A.halo->begin(fl.p, A.halo_dof);
+      A.halo->end();
+      gf = A.halo->ghost.p;
+    }
+    if (A.off->nrows > 0) {
+      LaunchScope ls(c, "setup");
+      k_zero_offdiag<<<(A.off->nrows + 127) / 128, 128, 0, c->stream>>>(A.off->nrows, A.off->rowptr.p, A.off->col.p, A.off->val.p, A.off_rows.p,
+                                                                         do_rows ? rowflag.p : nullptr, gf);
+      check_launch("k_zero_offdiag");
+    }
+    c->sync();
   }
   {
     LaunchScope ls(c, "setup");

@@ -3,6 +3,7 @@
 // every vector or matrix operation is one of the hand-written kernels in kernels_*.cu; the host keeps
 // the Hessenberg / Givens / Lanczos scalars exactly as PETSc does.
 #include "solver.h"
+#include "dist.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -20,7 +21,7 @@ void Ctx::fetch_scalars(const double *d, int k, double *host) {
   std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
 }
 static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
-  if (c->size > 1) B2_NCCL(nccl().AllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->dcomm) c->dcomm->allreduce_sum(d, k, c->stream);
 }
 
 // ------------------------------------------------------------------ operators

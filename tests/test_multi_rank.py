@@ -1,0 +1,125 @@
+"""Row-partitioned (DMDA) path: every rank is a thread of this process driving its own context on cuda:0
+(b200sp LocalGroup: collectives are host barriers + device copies, the ranks never wait on each other inside a
+kernel), so the whole distributed algorithm -- rank-local assembly with ghost elements, MPIAIJ-style diag/off-diag
+split, halo exchange, global reductions, distributed multigrid -- is checked on a 1-GPU box against the oracle.
+The NCCL transport used by bench.py under torchrun shares everything except the Comm object."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import sp_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def petsc_perm(M, N, size, dof):
+    nm, ow = so.dmda_natural_to_petsc(M, N, size)
+    return (np.repeat(nm.astype(np.int64) * dof, dof) + np.tile(np.arange(dof), M * N)), nm, ow
+
+
+def to_petsc_order(A, M, N, size, dofr, dofc):
+    pr, _, _ = petsc_perm(M, N, size, dofr)
+    pc, _, _ = petsc_perm(M, N, size, dofc)
+    C = A.scipy().tocoo()
+    P = sps.csr_matrix((C.data, (pr[C.row], pc[C.col])), shape=C.shape)   # explicit zeros are kept by csr_matrix((data,(i,j)))
+    P.sort_indices()
+    return P
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+
+
+@pytest.mark.parametrize("size,nx,ny", [(2, 9, 7), (4, 12, 10), (8, 21, 17), (3, 14, 5)])
+def test_distributed_assembly_and_spmv_match_the_oracle(size, nx, ny):
+    import saddle_point_petsc_b200 as sp
+    M, N = nx + 1, ny + 1
+    orc = so.Problem(nx, ny, kkt=True, rhs_kind=1)
+    blocks = {"A": (2, 2), "Bt": (2, 1), "B": (1, 2), "C": (1, 1), "Q": (1, 1)}
+    ref = {k: to_petsc_order(getattr(orc, k), M, N, size, *d) for k, d in blocks.items()}
+    pu, nm, ow = petsc_perm(M, N, size, 2)
+    pp, _, _ = petsc_perm(M, N, size, 1)
+    rng = np.random.default_rng(5)
+    xg = {1: rng.uniform(-1, 1, M * N), 2: rng.uniform(-1, 1, 2 * M * N)}      # global vectors in PETSc order
+    f_petsc = np.zeros(2 * M * N)
+    f_petsc[pu] = orc.f
+
+    def rank_fn(ctx):
+        r = ctx.rank
+        prob = sp.SaddlePointProblem(ctx, nx, ny, kkt=True, rhs_kind=1)
+        nl = prob.da.n_nodes_local
+        g0 = int(np.sum(ow < r))                     # rank-contiguous numbering: first global node of this rank
+        assert (prob.da.xs, prob.da.ys, prob.da.xm, prob.da.ym) == sp.dmda_corners(M, N, size, r)
+        out = {}
+        for name, (dr, dc) in blocks.items():
+            m = getattr(prob, name)
+            rp, col, val = m.csr()                   # local rows, GLOBAL PETSc column ids
+            R = ref[name][g0 * dr:(g0 + nl) * dr]
+            assert np.array_equal(rp, R.indptr), (name, r)
+            assert np.array_equal(col, R.indices), (name, r)
+            assert same_bits(val, R.data), (name, r)
+            # distributed MatMult: halo exchange + diagonal block + off-diagonal block
+            x = sp.Vec.from_numpy(ctx, xg[dc][g0 * dc:(g0 + nl) * dc])
+            y = sp.Vec(ctx, nl * dr)
+            m.mult(x, y)
+            yr = ref[name] @ xg[dc]
+            out[name] = np.max(np.abs(y.numpy() - yr[g0 * dr:(g0 + nl) * dr])) / max(1.0, np.max(np.abs(yr)))
+        assert same_bits(prob.rhs.numpy()[:2 * nl], f_petsc[g0 * 2:(g0 + nl) * 2])
+        # global reductions
+        v = sp.Vec.from_numpy(ctx, xg[2][g0 * 2:(g0 + nl) * 2])
+        out["norm"] = v.norm()
+        return out
+
+    res = sp.run_ranks(size, rank_fn)
+    for o in res:
+        for name in blocks:
+            assert o[name] < 1e-14, (name, o[name])
+        assert abs(o["norm"] - np.linalg.norm(xg[2])) < 1e-12 * np.linalg.norm(xg[2])
+    assert len({o["norm"] for o in res}) == 1        # every rank holds the same reduced value
+
+
+CFG_CHEB = ("-ksp_type fgmres -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type upper "
+            "-pc_fieldsplit_schur_precondition user -fieldsplit_0_ksp_type chebyshev -fieldsplit_0_ksp_max_it 6 -fieldsplit_0_pc_type jacobi "
+            "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
+CFG_MINRES = ("-ksp_type minres -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type diag "
+              "-pc_fieldsplit_schur_precondition user -fieldsplit_0_ksp_type chebyshev -fieldsplit_0_ksp_max_it 4 -fieldsplit_0_pc_type jacobi "
+              "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
+CFG_MG = ("-ksp_type fgmres -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type upper "
+          "-pc_fieldsplit_schur_precondition user -fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels 4 "
+          "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
+
+
+@pytest.mark.parametrize("size", [2, 4, 8])
+@pytest.mark.parametrize("cfg", ["cheb", "minres", "mg"])
+def test_distributed_kkt_solve_matches_single_rank_and_oracle(size, cfg):
+    import saddle_point_petsc_b200 as sp
+    nx = ny = 32 if cfg != "mg" else 48
+    opts = {"cheb": CFG_CHEB, "minres": CFG_MINRES, "mg": CFG_MG}[cfg]
+    M, N = nx + 1, ny + 1
+    orc = so.Problem(nx, ny, kkt=True, rhs_kind=1)
+    ro = so.Solver(orc, opts).solve()
+    pu, nm, ow = petsc_perm(M, N, size, 2)
+    pp, _, _ = petsc_perm(M, N, size, 1)
+    xu = np.zeros(2 * M * N); xu[pu] = ro["x"][:2 * M * N]
+    xp = np.zeros(M * N); xp[pp] = ro["x"][2 * M * N:]
+
+    def rank_fn(ctx):
+        prob = sp.SaddlePointProblem(ctx, nx, ny, kkt=True, rhs_kind=1)
+        ksp = prob.make_ksp(opts)
+        x = sp.Vec(ctx, prob.n)
+        r = ksp.solve(prob.rhs, x)
+        nl = prob.da.n_nodes_local
+        g0 = int(np.sum(ow < ctx.rank))
+        xs = x.numpy()
+        eu = np.max(np.abs(xs[:2 * nl] - xu[2 * g0:2 * (g0 + nl)]))
+        dp = xs[2 * nl:] - xp[g0:g0 + nl]
+        return r["its"], r["reason"], eu, dp
+
+    res = sp.run_ranks(size, rank_fn)
+    its = {r[0] for r in res}
+    assert len(its) == 1 and all(r[1] == 2 for r in res)
+    assert abs(res[0][0] - ro["its"]) <= 1, (res[0][0], ro["its"])
+    if res[0][0] == ro["its"]:
+        assert max(r[2] for r in res) <= 1e-8 * np.max(np.abs(xu))
+        dp = np.concatenate([r[3] for r in res])
+        assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(xp))
