@@ -168,6 +168,7 @@ struct Csr {
   DevBuf<int> off_rows;           // local row id of every row of `off`
   std::shared_ptr<Halo> halo;     // column-space halo (null on one rank)
   int halo_dof = 0;               // dof per node of the column space
+  std::shared_ptr<Layout> layout;  // node layout of a square DMDA matrix (multigrid coarsening)
   int64_t row_gstart = 0, col_gstart = 0; // first global row / owned global column of this rank (PETSc numbering)
   void plan();           // histogram + kernel choice (device reduction)
 };
@@ -197,6 +198,8 @@ void vec_pointwise_mult(Ctx *c, int64_t n, const double *x, const double *y, dou
 void vec_reciprocal_safe(Ctx *c, int64_t n, double *d); // d = 1/(d==0?1:d)   (PCJACOBI setup)
 void vec_hash(Ctx *c, int64_t n, double *v);
 void vec_scatter_set(Ctx *c, int64_t n, const int *idx, double val, double *y); // y[idx[i]] = val
+void vec_permute_scatter(Ctx *c, int64_t n, const int *map, const double *in, double *out); // out[map[i]] = in[i] where map[i] >= 0
+void vec_permute_gather(Ctx *c, int64_t n, const int *map, const double *in, double *out);  // out[i] = in[map[i]]
 // reductions: results land in device slot `out` (k doubles); fetch with ctx->fetch_scalars
 void vec_dot(Ctx *c, int64_t n, const double *x, const double *y, double *out);
 void vec_mdot(Ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ld, double *out); // out[j] = w . V_j

@@ -523,6 +523,7 @@ std::shared_ptr<Csr> build_box_matrix(const Dmda &da, const ElemArrays &ea, int 
     A->row_gstart = g0 * dofr;
     A->col_gstart = g0 * dofc;
     A->grid_M = da.M; A->grid_N = da.N; A->dof_r = dofr; A->dof_c = dofc;
+    A->layout = da.layout;
     return A;
   }
   GridBox g{da.M, da.N, da.xs, da.ys, da.xm, da.ym};

@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(256) k_scatter_set(int64_t n, const int *idx, 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[idx[i]] = val;
 }
 
+__global__ void __launch_bounds__(256) k_permute_scatter(int64_t n, const int *__restrict__ map, const double *__restrict__ in, double *out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (map[i] >= 0) out[map[i]] = in[i];
+}
+__global__ void __launch_bounds__(256) k_permute_gather(int64_t n, const int *__restrict__ map, const double *__restrict__ in, double *out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[map[i]];
+}
+
 // ---- reductions -------------------------------------------------------------------------------
 // out[j] = sum_i w[i] * V[j*ld + i], j < k <= KB.  One pass over w and the k basis vectors.
 template <int KB, bool V2>
@@ -264,6 +272,19 @@ void vec_scatter_set(Ctx *c, int64_t n, const int *idx, double val, double *y) {
   LaunchScope ls(c, "vec");
   k_scatter_set<<<stream_grid(c, n), 256, 0, c->stream>>>(n, idx, val, y);
   check_launch("k_scatter_set");
+}
+
+void vec_permute_scatter(Ctx *c, int64_t n, const int *map, const double *in, double *out) {
+  if (n <= 0) return;
+  LaunchScope ls(c, "vec");
+  k_permute_scatter<<<stream_grid(c, n), 256, 0, c->stream>>>(n, map, in, out);
+  check_launch("k_permute_scatter");
+}
+void vec_permute_gather(Ctx *c, int64_t n, const int *map, const double *in, double *out) {
+  if (n <= 0) return;
+  LaunchScope ls(c, "vec");
+  k_permute_gather<<<stream_grid(c, n), 256, 0, c->stream>>>(n, map, in, out);
+  check_launch("k_permute_gather");
 }
 
 void vec_mdot(Ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ld, double *out) {

@@ -149,13 +149,25 @@ std::string LscOp::view(int indent) const {
 // PCMG multiplicative V-cycle: smoothdown (zero guess), residual, restrict, recurse, interpolate-add, smoothup
 void MgOp::cycle(int l, const double *b, double *x) {
   Level &L = *lev[l];
-  if (l == (int)lev.size() - 1) { coarse->apply(b, x); return; }
-  Level &Lc = *lev[l + 1];
+  const bool last = l == (int)lev.size() - 1;
+  if (last && !replicated) { coarse->apply(b, x); return; }
   L.smooth->solve(b, x, false);
   csr_spmv(*L.A, x, L.r.p, -1.0, b, 1.0);          // r = b - A x
-  csr_spmv(*L.R, L.r.p, Lc.b.p);                    // restrict
-  cycle(l + 1, Lc.b.p, Lc.x.p);
-  csr_spmv(*L.P, Lc.x.p, x, 1.0, x, 1.0);           // x += P xc
+  if (!last) {
+    Level &Lc = *lev[l + 1];
+    csr_spmv(*L.R, L.r.p, Lc.b.p);                  // restrict
+    cycle(l + 1, Lc.b.p, Lc.x.p);
+    csr_spmv(*L.P, Lc.x.p, x, 1.0, x, 1.0);         // x += P xc
+  } else {
+    // bridge to the replicated coarse hierarchy: restrict into my part of the coarse vector, all-gather, reorder to
+    // the natural numbering, run the remaining levels redundantly on every rank, take my part back, interpolate
+    csr_spmv(*L.R, L.r.p, loc_b.p);
+    ctx->dcomm->allgather(loc_b.p, g_all.p, bridge_cnt, ctx->stream);
+    vec_permute_scatter(ctx, (int64_t)bridge_cnt * ctx->size, gather_map.p, g_all.p, nat_b.p);
+    replicated->apply(nat_b.p, nat_x.p);
+    vec_permute_gather(ctx, bridge_nloc, local_map.p, nat_x.p, loc_x.p);
+    csr_spmv(*L.P, loc_x.p, x, 1.0, x, 1.0);
+  }
   L.smooth->solve(b, x, true);
 }
 void MgOp::apply(const double *b, double *x) { cycle(0, b, x); } // level 0 works on the caller's vectors: no copies
@@ -469,20 +481,20 @@ std::string Ksp::view(int indent) const {
   return o.str();
 }
 
-double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits) {
+double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits, bool local_only) {
   const int64_t n = A->n_in;
   DevBuf<double> v((size_t)n + 2), t((size_t)n + 2), z((size_t)n + 2);
   vec_hash(c, n, v.p);
   double lam = 0.0, nv;
   for (int it = 0; it < nits; ++it) {
     vec_dot(c, n, v.p, v.p, c->d_scalars);
-    allreduce_sum(c, c->d_scalars, 1);
+    if (!local_only) allreduce_sum(c, c->d_scalars, 1);
     c->fetch_scalars(c->d_scalars, 1, &nv);
     vec_scale(c, n, 1.0 / std::sqrt(nv), v.p);
     A->apply(v.p, t.p);
     if (M) M->apply(t.p, z.p); else vec_copy(c, n, t.p, z.p);
     vec_dot(c, n, z.p, z.p, c->d_scalars);
-    allreduce_sum(c, c->d_scalars, 1);
+    if (!local_only) allreduce_sum(c, c->d_scalars, 1);
     c->fetch_scalars(c->d_scalars, 1, &lam);
     lam = std::sqrt(lam);
     vec_copy(c, n, z.p, v.p);
@@ -566,16 +578,36 @@ Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, 
 }
 
 // PCMG: rediscretised coarse velocity operators (the same device assembly on the coarser DMDA + the same
-// Dirichlet elimination), Q1 interpolation with Dirichlet rows/cols zeroed, R = P^T, Chebyshev/Jacobi smoothing
-Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
-  B2_REQUIRE(ctx->size == 1, "pc mg: single-GPU only in this build step");
-  B2_REQUIRE(mat->grid_M > 0 && mat->dof_r == 2 && mat->dof_c == 2, "pc mg: needs the velocity block assembled from a DMDA (b200sp_assemble_stress)");
-  const int nlev = std::stoi(opt(prefix + "pc_mg_levels", "2"));
-  B2_REQUIRE(nlev >= 2, "pc mg: need at least 2 levels");
-  MgOp *mg = add_op<MgOp>(ctx, (int64_t)mat->nrows);
-  int Ml = mat->grid_M, Nl = mat->grid_N;
-  std::shared_ptr<Csr> Al = mat;
+// Dirichlet elimination), Q1 interpolation with Dirichlet rows/cols zeroed, R = P^T, Chebyshev/Jacobi smoothing.
+// Builds levels [first .. first+nlev-1] of a single-rank (or replicated) hierarchy into mg; A0 may be null
+// (then the first level is assembled too).  local_only: the data is replicated on every rank, so the eigenvalue
+// estimates must not be all-reduced.
+static void smoother_setup(Solver *S, Ksp *k, const std::string &sp, Op *Aop, Op *jac, bool local_only,
+                           const std::map<std::string, std::string> &opts) {
+  auto opt = [&](const std::string &key, const std::string &def) { auto it = opts.find(key); return it == opts.end() ? def : it->second; };
+  k->set_operators(Aop, jac);
+  const std::string t = opt(sp + "ksp_type", "chebyshev");
+  k->type = t == "richardson" ? KSP_RICHARDSON : KSP_CHEBYSHEV;
+  B2_REQUIRE(t == "chebyshev" || t == "richardson", "mg smoother: -mg_levels_ksp_type must be chebyshev or richardson");
+  k->max_it = std::stoi(opt(sp + "ksp_max_it", "2"));
+  k->norm_none = true;
+  k->richardson_scale = std::stod(opt(sp + "ksp_richardson_scale", "1.0"));
+  const double lam = estimate_lambda_max(S->ctx, Aop, jac, 10, local_only);
+  k->emin = 0.1 * lam;
+  k->emax = 1.1 * lam;
+}
+
+void Solver::build_levels_single(MgOp *mg, std::shared_ptr<Csr> A0, int Ml, int Nl, int nlev, const std::string &prefix, bool local_only) {
   const std::string sp = prefix + "mg_levels_";
+  std::shared_ptr<Csr> Al = A0;
+  if (!Al) {
+    Dmda d0;
+    d0.ctx = ctx; d0.M = Ml; d0.N = Nl; d0.xm = Ml; d0.ym = Nl;
+    Al = assemble_stress(d0, 0);
+    std::vector<int> ids = dmda_bc_ids(d0, 2);
+    csr_zero_rows_cols(*Al, (int)ids.size(), ids.data(), 1.0, true, true, true);
+    Al->tag = "spmv:A_coarse";
+  }
   for (int l = 0; l < nlev; ++l) {
     auto L = std::make_unique<MgOp::Level>();
     L->A = Al;
@@ -588,18 +620,9 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
       L->jac = std::make_unique<JacobiOp>(*Al);
       L->Aop = std::make_unique<CsrOp>(Al);
       L->smooth = std::make_unique<Ksp>(ctx, sp);
-      Ksp *k = L->smooth.get();
-      k->set_operators(L->Aop.get(), L->jac.get());
-      k->type = ksp_type_from(opt(sp + "ksp_type", "chebyshev"));
-      k->max_it = std::stoi(opt(sp + "ksp_max_it", "2"));
-      k->norm_none = true;
-      k->richardson_scale = std::stod(opt(sp + "ksp_richardson_scale", "1.0"));
-      const double lam = estimate_lambda_max(ctx, L->Aop.get(), L->jac.get(), 10);
-      k->emin = 0.1 * lam;
-      k->emax = 1.1 * lam;
-      // next level: rediscretise
+      smoother_setup(this, L->smooth.get(), sp, L->Aop.get(), L->jac.get(), local_only, opts);
       Dmda dc;
-      dc.ctx = ctx; dc.M = Mc; dc.N = Nc; dc.pm = dc.pn = 1; dc.xs = dc.ys = 0; dc.xm = Mc; dc.ym = Nc;
+      dc.ctx = ctx; dc.M = Mc; dc.N = Nc; dc.xm = Mc; dc.ym = Nc;
       auto Ac = assemble_stress(dc, 0);
       std::vector<int> ids = dmda_bc_ids(dc, 2);
       csr_zero_rows_cols(*Ac, (int)ids.size(), ids.data(), 1.0, true, true, true);
@@ -610,6 +633,88 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
     mg->lev.push_back(std::move(L));
   }
   mg->coarse = std::make_unique<DenseInvOp>(*mg->lev.back()->A);
+}
+
+Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
+  B2_REQUIRE(mat->grid_M > 0 && mat->dof_r == 2 && mat->dof_c == 2, "pc mg: needs the velocity block assembled from a DMDA (b200sp_assemble_stress)");
+  const int nlev = std::stoi(opt(prefix + "pc_mg_levels", "2"));
+  B2_REQUIRE(nlev >= 2, "pc mg: need at least 2 levels");
+  MgOp *mg = add_op<MgOp>(ctx, (int64_t)mat->nrows);
+  if (!ctx->dcomm) {
+    build_levels_single(mg, mat, mat->grid_M, mat->grid_N, nlev, prefix, false);
+    return mg;
+  }
+  // ---- row-partitioned hierarchy: the top `nd` levels are distributed (halo exchanges), everything below is
+  // gathered and solved redundantly on every rank (no communication on the small levels; the coarse work is
+  // replicated instead of scattered across ranks that would each own a handful of nodes)
+  B2_REQUIRE(mat->layout && mat->halo, "pc mg: distributed matrix without a DMDA layout");
+  const std::string sp = prefix + "mg_levels_";
+  int nd = std::min(std::stoi(opt(prefix + "pc_mg_distributed_levels", "3")), nlev - 1);
+  B2_REQUIRE(nd >= 1, "pc mg: need at least one distributed level");
+  std::vector<std::shared_ptr<Layout>> lay{mat->layout};
+  for (int l = 1; l <= nd; ++l) {
+    try { lay.push_back(std::make_shared<Layout>(lay.back()->coarsen())); }
+    catch (const Error &) { nd = l - 1; break; }
+  }
+  B2_REQUIRE(nd >= 1, "pc mg: the grid cannot be coarsened on this process grid (every rank must own >= 2 coarse nodes per direction)");
+  std::vector<Dmda> d((size_t)nd + 1);
+  for (int l = 0; l <= nd; ++l) {
+    Dmda &q = d[(size_t)l];
+    q.ctx = ctx; q.M = lay[(size_t)l]->M; q.N = lay[(size_t)l]->N; q.pm = lay[(size_t)l]->m; q.pn = lay[(size_t)l]->n;
+    lay[(size_t)l]->box(ctx->rank, &q.xs, &q.ys, &q.xm, &q.ym);
+    q.layout = lay[(size_t)l];
+    q.halo = l == 0 ? mat->halo : make_halo(ctx, *lay[(size_t)l], ctx->rank);
+  }
+  std::shared_ptr<Csr> Al = mat;
+  for (int l = 0; l < nd; ++l) {
+    auto L = std::make_unique<MgOp::Level>();
+    L->A = Al;
+    L->b.alloc((size_t)Al->nrows + 2); L->x.alloc((size_t)Al->nrows + 2); L->r.alloc((size_t)Al->nrows + 2);
+    L->P = interp_q1_dist(d[(size_t)l], d[(size_t)l + 1], 2, 1);
+    L->R = restrict_q1_dist(d[(size_t)l], d[(size_t)l + 1], 2, 1);
+    L->jac = std::make_unique<JacobiOp>(*Al);
+    L->Aop = std::make_unique<CsrOp>(Al);
+    L->smooth = std::make_unique<Ksp>(ctx, sp);
+    smoother_setup(this, L->smooth.get(), sp, L->Aop.get(), L->jac.get(), false, opts);
+    if (l + 1 < nd) {
+      auto Ac = assemble_stress(d[(size_t)l + 1], 0);
+      std::vector<int> ids = dmda_bc_ids(d[(size_t)l + 1], 2);
+      csr_zero_rows_cols(*Ac, (int)ids.size(), ids.data(), 1.0, true, true, true);
+      Ac->tag = "spmv:A_coarse";
+      Al = Ac;
+    }
+    mg->lev.push_back(std::move(L));
+  }
+  // replicated part: levels nd .. nlev-1 on the natural-ordered global coarse grid
+  const Layout &Lc = *lay[(size_t)nd];
+  mg->replicated = std::make_unique<MgOp>(ctx, (int64_t)2 * Lc.M * Lc.N);
+  build_levels_single(mg->replicated.get(), nullptr, Lc.M, Lc.N, nlev - nd, prefix, true);
+  // bridge maps: gathered (rank-major, padded to the largest rank) -> natural ordering, and natural -> my owned part
+  int cnt_max = 0;
+  for (int q = 0; q < Lc.size; ++q) cnt_max = std::max(cnt_max, 2 * Lc.lx[(size_t)(q % Lc.m)] * Lc.ly[(size_t)(q / Lc.m)]);
+  std::vector<int> gmap((size_t)cnt_max * Lc.size, -1), lmap;
+  for (int q = 0; q < Lc.size; ++q) {
+    int xs, ys, xm, ym;
+    Lc.box(q, &xs, &ys, &xm, &ym);
+    for (int j = 0; j < ym; ++j)
+      for (int i = 0; i < xm; ++i)
+        for (int c = 0; c < 2; ++c) {
+          const int nat = ((ys + j) * Lc.M + xs + i) * 2 + c;
+          gmap[(size_t)q * cnt_max + (size_t)(j * xm + i) * 2 + c] = nat;
+          if (q == ctx->rank) lmap.push_back(nat);
+        }
+  }
+  mg->bridge_cnt = cnt_max;
+  mg->bridge_nloc = (int)lmap.size();
+  mg->gather_map.alloc(gmap.size() + 1);
+  mg->local_map.alloc(lmap.size() + 1);
+  B2_CUDA(cudaMemcpyAsync(mg->gather_map.p, gmap.data(), sizeof(int) * gmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(mg->local_map.p, lmap.data(), sizeof(int) * lmap.size(), cudaMemcpyHostToDevice, ctx->stream));
+  mg->loc_b.alloc((size_t)cnt_max + 2); mg->loc_x.alloc((size_t)cnt_max + 2);
+  mg->loc_b.zero(ctx->stream);
+  mg->g_all.alloc((size_t)cnt_max * Lc.size + 2);
+  mg->nat_b.alloc((size_t)2 * Lc.M * Lc.N + 2); mg->nat_x.alloc((size_t)2 * Lc.M * Lc.N + 2);
+  ctx->sync();
   return mg;
 }
 

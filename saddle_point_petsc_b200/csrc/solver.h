@@ -104,7 +104,12 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   };
   std::vector<std::unique_ptr<Level>> lev;
   std::unique_ptr<DenseInvOp> coarse;
-  explicit MgOp(Ctx *c, int64_t n) : Op(c, n, n) {}
+  // row-partitioned runs: `lev` holds the distributed smoothing levels; the levels below are replicated on every rank
+  std::unique_ptr<MgOp> replicated;
+  DevBuf<double> loc_b, loc_x, g_all, nat_b, nat_x;
+  DevBuf<int> gather_map, local_map;
+  int bridge_cnt = 0, bridge_nloc = 0;
+  MgOp(Ctx *c, int64_t n) : Op(c, n, n) {}
   void cycle(int l, const double *b, double *x);
   void apply(const double *b, double *x) override;
   std::string view(int indent) const override;
@@ -149,7 +154,7 @@ private:
 
 // deterministic lambda_max estimate of M^-1 A (10 power iterations from the hashed vector), same procedure as
 // the oracle's or_estimate_lambda_max; chebyshev bounds are (0.1, 1.1) x estimate (PETSc's default transform)
-double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits);
+double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits, bool local_only = false);
 
 // the object behind b200sp_ksp: options + operators + the composed solver tree
 struct Solver {
@@ -181,6 +186,11 @@ private:
   Ksp *make_ksp(const std::string &prefix, Op *A, Op *M, const char *default_type);
   Op *make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, const char *default_type);
   Op *make_mg(const std::string &prefix, std::shared_ptr<Csr> mat);
+
+public:
+  void build_levels_single(MgOp *mg, std::shared_ptr<Csr> A0, int Ml, int Nl, int nlev, const std::string &prefix, bool local_only);
+
+private:
   Op *make_fieldsplit();
 };
 
