@@ -165,10 +165,32 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)" % (args.gpus, world))
+    dist = None
+    nccl_id = None
     if world > 1:
-        raise SystemExit("bench.py: the multi-GPU path is not wired in this build yet (single-GPU only)")
+        # one process per GPU: torch.distributed (gloo, 127.0.0.1) is only the bootstrap for the NCCL unique id and
+        # the max-over-ranks of the timings; the solver's collectives are NCCL calls inside libb200sp
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("gloo", init_method="env://")
+        buf = [sp.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(buf, src=0)
+        nccl_id = buf[0]
 
-    ctx = sp.Context(device=local_rank, rank=rank, size=world)
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([float(v)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    ctx = sp.Context(device=local_rank, rank=rank, size=world, nccl_id=nccl_id)
     t0 = time.perf_counter()
     prob = sp.SaddlePointProblem(ctx, args.nx, args.nx, kkt=True, rhs_kind=1)
     ctx.synchronize()
@@ -188,15 +210,17 @@ def main():
     sampler.start()
     time.sleep(0.3)
     ctx.synchronize()
+    barrier()
     l0 = ctx.launch_count()
     ctx.timer_start()
     for _ in range(args.steps):
         res = ksp.solve(prob.rhs, x)
     ms = ctx.timer_stop()
     ctx.synchronize()
+    barrier()
     launches = ctx.launch_count() - l0
     clocks = sampler.stop()
-    t_solve = ms / 1e3 / args.steps
+    t_solve = max_over_ranks(ms) / 1e3 / args.steps   # device time, max over ranks
 
     # ---- end to end through the host-buffer C-ABI entry point, pinned host memory
     import torch
@@ -205,10 +229,11 @@ def main():
     b_np, x_np = hb.numpy(), hx.numpy()
     b_np[:] = prob.rhs.numpy()
     ksp.solve_host(b_np, x_np)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ksp.solve_host(b_np, x_np)
-    t_e2e = (time.perf_counter() - t0) / args.steps
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / args.steps)
 
     # ---- per-kernel-class device time during one solve (events around every launch; measurement pass only)
     ctx.profile(True)
@@ -233,8 +258,21 @@ def main():
     prob.K.residual(prob.rhs, x, r)
     true_rel = r.norm() / prob.rhs.norm()
 
+    if dist is not None:
+        import torch
+        t = torch.tensor([float(n)], dtype=torch.float64)
+        dist.all_reduce(t)
+        n_global = int(t[0])
+        t = torch.tensor([float(launches)], dtype=torch.float64)
+        dist.all_reduce(t)
+        launches = int(t[0])
+    else:
+        n_global = n
+    if rank != 0:
+        ctx.synchronize()
+        return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         so, oprob, osolver, t_osetup = oracle_solve_setup(args.nx, opts)
         t0 = time.perf_counter()
         orr = osolver.solve(history=False)
@@ -242,13 +280,14 @@ def main():
         cpu = {"value": t_cpu, "unit": "s", "cores": so.lib().or_get_threads(), "kind": "port",
                "sample": "full workload, one solve (oracle assembly+setup %.1fs untimed)" % t_osetup, "iterations": orr["its"]}
 
-    cfg = workload(args, n)
+    cfg = workload(args, n_global)
     cfg["solver_options"] = opts
+    cfg["dof_per_gpu"] = n
     line = {"metric": "time_to_solve_rtol1e-8", "value": t_solve, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_solve * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg, "iterations": res["its"], "converged_reason": res["reason"],
             "iterations_per_s": res["its"] / t_solve, "true_relative_residual": true_rel,
-            "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+            "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_classes_ms_per_solve": classes, "assembly_s": t_assembly, "ksp_setup_s": t_setup}
     print(json.dumps(line), flush=True)
