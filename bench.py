@@ -134,7 +134,7 @@ def run_reference(args, opts):
             "cpu_baseline": {"value": dt, "unit": "s", "cores": cores, "kind": "port",
                              "sample": "full workload: one complete solve per step (assembly %.1fs and setup untimed)" % t_setup},
             "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload(args, dof):
@@ -143,7 +143,22 @@ def workload(args, dof):
             "parallelism": "dmda_row_partition_x%d" % args.gpus}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries (NCCL's version banner, torch.distributed notices) write to fd 1; the contract is exactly one JSON
+    # line on stdout.  Everything else goes to stderr: fd 1 is pointed at fd 2 and the result is written to the
+    # saved descriptor at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -170,6 +185,10 @@ def main():
     if world > 1:
         # one process per GPU: torch.distributed (gloo, 127.0.0.1) is only the bootstrap for the NCCL unique id and
         # the max-over-ranks of the timings; the solver's collectives are NCCL calls inside libb200sp
+        # rank 0 must print exactly ONE line on stdout: keep NCCL's own banner ("NCCL version ...", printed when
+        # NCCL_DEBUG=VERSION/INFO) off stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/tmp/b200sp_nccl_%h_%p.log")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -290,7 +309,7 @@ def main():
             "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_classes_ms_per_solve": classes, "assembly_s": t_assembly, "ksp_setup_s": t_setup}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
