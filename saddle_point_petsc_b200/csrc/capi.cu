@@ -395,7 +395,7 @@ int b200sp_mat_get_size(b200sp_mat A, int *nrows, int *ncols, int64_t *nnz) {
   if (ncols) *ncols = A->m.ncols();
   if (nnz) {
     if (A->m.nest) { *nnz = 0; for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (A->m.blk[i][j]) *nnz += A->m.blk[i][j]->nnz; }
-    else *nnz = A->m.csr->nnz + (A->m.csr->off ? A->m.csr->off->nnz : 0);
+    else *nnz = A->m.csr->nnz;
   }
   API_END
 }
@@ -404,35 +404,29 @@ int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val) {
   Csr &M = plain(A);
   Ctx *c = M.ctx;
   if (M.halo) {
-    // row-partitioned matrix: local rows with GLOBAL (PETSc numbering) column ids, diagonal and off-diagonal
-    // blocks merged and sorted -- what MatView / MatGetRow show for an MPIAIJ matrix
-    const Csr &O = *M.off;
-    std::vector<int> rp((size_t)M.nrows + 1), cj((size_t)M.nnz + 1), orp((size_t)O.nrows + 1), ocj((size_t)O.nnz + 1), orow((size_t)O.nrows + 1);
-    std::vector<double> va((size_t)M.nnz + 1), ova((size_t)O.nnz + 1);
+    // row-partitioned matrix: local rows with GLOBAL (PETSc numbering) column ids, sorted -- what MatView / MatGetRow
+    // show for an MPIAIJ matrix
+    std::vector<int> rp((size_t)M.nrows + 1), cj((size_t)M.nnz + 1);
+    std::vector<double> va((size_t)M.nnz + 1);
     B2_CUDA(cudaMemcpyAsync(rp.data(), M.rowptr.p, sizeof(int) * ((size_t)M.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
     if (M.nnz) B2_CUDA(cudaMemcpyAsync(cj.data(), M.col.p, sizeof(int) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
     if (M.nnz) B2_CUDA(cudaMemcpyAsync(va.data(), M.val.p, sizeof(double) * (size_t)M.nnz, cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(orp.data(), O.rowptr.p, sizeof(int) * ((size_t)O.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
-    if (O.nnz) B2_CUDA(cudaMemcpyAsync(ocj.data(), O.col.p, sizeof(int) * (size_t)O.nnz, cudaMemcpyDeviceToHost, c->stream));
-    if (O.nnz) B2_CUDA(cudaMemcpyAsync(ova.data(), O.val.p, sizeof(double) * (size_t)O.nnz, cudaMemcpyDeviceToHost, c->stream));
-    if (O.nrows) B2_CUDA(cudaMemcpyAsync(orow.data(), M.off_rows.p, sizeof(int) * (size_t)O.nrows, cudaMemcpyDeviceToHost, c->stream));
     c->sync();
-    std::vector<int> offidx((size_t)M.nrows, -1);
-    for (int k = 0; k < O.nrows; ++k) offidx[(size_t)orow[(size_t)k]] = k;
     const int dofc = M.halo_dof;
-    int64_t p = 0;
     std::vector<std::pair<int, double>> row;
     for (int r = 0; r < M.nrows; ++r) {
-      if (rowptr) rowptr[r] = (int)p;
+      if (rowptr) rowptr[r] = rp[(size_t)r];
       row.clear();
-      for (int k = rp[(size_t)r]; k < rp[(size_t)r + 1]; ++k) row.push_back({(int)(M.col_gstart + cj[(size_t)k]), va[(size_t)k]});
-      if (offidx[(size_t)r] >= 0)
-        for (int k = orp[(size_t)offidx[(size_t)r]]; k < orp[(size_t)offidx[(size_t)r] + 1]; ++k)
-          row.push_back({M.halo->ghost_gnode[(size_t)(ocj[(size_t)k] / dofc)] * dofc + ocj[(size_t)k] % dofc, ova[(size_t)k]});
+      for (int k = rp[(size_t)r]; k < rp[(size_t)r + 1]; ++k) {
+        const int cl = cj[(size_t)k];
+        const int g = cl < M.ncols ? (int)(M.col_gstart + cl) : M.halo->ghost_gnode[(size_t)((cl - M.ncols) / dofc)] * dofc + (cl - M.ncols) % dofc;
+        row.push_back({g, va[(size_t)k]});
+      }
       std::sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+      int64_t p = rp[(size_t)r];
       for (auto &e : row) { if (col) col[p] = e.first; if (val) val[p] = e.second; ++p; }
     }
-    if (rowptr) rowptr[M.nrows] = (int)p;
+    if (rowptr) rowptr[M.nrows] = rp[(size_t)M.nrows];
     return B200SP_OK;
   }
   if (rowptr) B2_CUDA(cudaMemcpyAsync(rowptr, M.rowptr.p, sizeof(int) * ((size_t)M.nrows + 1), cudaMemcpyDeviceToHost, c->stream));

@@ -144,7 +144,9 @@ struct Dmda {
 
 // ------------------------------------------------------------------ Mat
 enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3 };
-bool csr_spmv_tma(const struct Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z);
+struct XSrc;
+struct SpmvEpi;
+bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi);
 
 struct Csr {
   Ctx *ctx = nullptr;
@@ -162,11 +164,9 @@ struct Csr {
   // grid metadata when the matrix came from DMDA assembly (for -pc_type mg); 0 = unknown
   int grid_M = 0, grid_N = 0, dof_r = 0, dof_c = 0;
   std::string tag = "spmv"; // profile class of this matrix's SpMV launches ("spmv:A", "spmv:Bt", ...)
-  // distributed (MPIAIJ-like) part: `this` holds the diagonal block (owned columns, local ids); `off` holds the
-  // entries whose column is a ghost node, rows compressed to the ranks's boundary rows
-  std::shared_ptr<Csr> off;       // nrows = number of boundary rows, ncols = ghosts * dof
-  DevBuf<int> off_rows;           // local row id of every row of `off`
-  std::shared_ptr<Halo> halo;     // column-space halo (null on one rank)
+  // row-partitioned (MPIAIJ-like) matrix: local rows; columns < ncols are owned (local ids), columns >= ncols are
+  // ghost nodes in MPIAIJ garray order, read by the kernels from the halo buffer
+  std::shared_ptr<Halo> halo;     // column-space halo (null on one rank); column ids >= ncols are ghost ids + ncols
   int halo_dof = 0;               // dof per node of the column space
   std::shared_ptr<Layout> layout;  // node layout of a square DMDA matrix (multigrid coarsening)
   int64_t row_gstart = 0, col_gstart = 0; // first global row / owned global column of this rank (PETSc numbering)
@@ -209,8 +209,41 @@ void vec_maxpy(Ctx *c, int64_t n, int k, double *w, const double *V, int64_t ld,
 // y = x * (1/sqrt(*nrm2_dev))  (normalisation without a host round trip)
 void vec_scale_inv_sqrt(Ctx *c, int64_t n, const double *nrm2_dev, const double *x, double *y);
 
-// spmv (kernels_spmv.cu):  y = beta_z * z + alpha * (A x)   (z may be null; z may alias y)
+// spmv (kernels_spmv.cu)
+// where the kernels read x from: owned columns from the caller's vector, ghost columns (>= n_owned) from the halo buffer
+struct XSrc {
+  const double *x, *ghost;
+  int n_owned;
+#ifdef __CUDACC__
+  __device__ __forceinline__ double load(int c) const { return c < n_owned ? __ldg(x + c) : __ldg(ghost + (c - n_owned)); }
+#endif
+};
+// fused epilogue of every SpMV kernel, applied to the row sum s of row r:
+//   cheb == 0:  beta_z*z[r] + alpha*s                                   (z may be null; z may alias y)
+//   cheb == 1:  ca*pm1[r] + cb*pk[r] + cc*(dinv[r]*(z[r] - s))          (z = b; dinv may be null)  -- the same
+//               operations, in the same order, as residual + PCJACOBI + VecAXPBYPCZ done separately
+struct SpmvEpi {
+  double alpha = 1.0;
+  const double *z = nullptr;
+  double beta_z = 0.0;
+  int cheb = 0;
+  const double *pm1 = nullptr, *pk = nullptr, *dinv = nullptr;
+  double ca = 0.0, cb = 0.0, cc = 0.0;
+#ifdef __CUDACC__
+  __device__ __forceinline__ double apply(double s, int r) const {
+    if (cheb) {
+      double t = z[r] - s;
+      if (dinv) t = t * dinv[r];
+      return ca * pm1[r] + cb * pk[r] + cc * t;
+    }
+    double v = alpha * s;
+    if (z) v = beta_z * z[r] + v;
+    return v;
+  }
+#endif
+};
 void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0);
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi);
 void csr_get_diagonal(const Csr &A, double *d);
 void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool do_rows, bool do_cols, bool set_diag);
 

@@ -317,45 +317,33 @@ struct RestrictEnum { // R = P^T: rows = owned coarse nodes, columns = fine node
 };
 
 struct CountEmit {
-  ColSpace cs;
-  int nd = 0, no = 0;
-  __device__ void operator()(int ci, int cj, int, double) {
-    if (ci >= cs.xs && ci < cs.xs + cs.xm && cj >= cs.ys && cj < cs.ys + cs.ym) ++nd; else ++no;
-  }
+  int n = 0;
+  __device__ void operator()(int, int, int, double) { ++n; }
 };
 struct FillEmit {
   ColSpace cs;
-  int dofc, pd, po;
-  int *col_d; double *val_d; int *col_o; double *val_o;
+  int dofc, n_owned_cols, p;
+  int *col; double *val;
   __device__ void operator()(int ci, int cj, int cc, double v) {
-    if (ci >= cs.xs && ci < cs.xs + cs.xm && cj >= cs.ys && cj < cs.ys + cs.ym) {
-      col_d[pd] = ((cj - cs.ys) * cs.xm + (ci - cs.xs)) * dofc + cc;
-      val_d[pd++] = v;
-    } else {
-      col_o[po] = cs.ring2ghost[cs.ring_id(ci, cj)] * dofc + cc;
-      val_o[po++] = v;
-    }
+    if (ci >= cs.xs && ci < cs.xs + cs.xm && cj >= cs.ys && cj < cs.ys + cs.ym)
+      col[p] = ((cj - cs.ys) * cs.xm + (ci - cs.xs)) * dofc + cc;
+    else
+      col[p] = n_owned_cols + cs.ring2ghost[cs.ring_id(ci, cj)] * dofc + cc; // ghost column
+    val[p++] = v;
   }
 };
-template <class E> __global__ void __launch_bounds__(128) k_dist_count(E e, ColSpace cs, int *len_d, int *len_o, int *has_o) {
+template <class E> __global__ void __launch_bounds__(128) k_dist_count(E e, int *len) {
   const int nrows = e.nrows();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
-    CountEmit em{cs};
+    CountEmit em;
     e.enumerate(r, em);
-    len_d[r] = em.nd; len_o[r] = em.no; has_o[r] = em.no > 0;
+    len[r] = em.n;
   }
 }
-__global__ void __launch_bounds__(256) k_compact_off(int nrows, const int *__restrict__ has_o, const int *__restrict__ oidx, const int *__restrict__ len_o,
-                                                     int *off_rows, int *len_oc) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x)
-    if (has_o[r]) { off_rows[oidx[r]] = r; len_oc[oidx[r]] = len_o[r]; }
-}
-template <class E> __global__ void __launch_bounds__(128) k_dist_fill(E e, ColSpace cs, int dofc, const int *__restrict__ rp_d, int *col_d, double *val_d,
-                                                                      const int *__restrict__ has_o, const int *__restrict__ oidx, const int *__restrict__ rp_o,
-                                                                      int *col_o, double *val_o) {
+template <class E> __global__ void __launch_bounds__(128) k_dist_fill(E e, ColSpace cs, int dofc, int n_owned_cols, const int *__restrict__ rp, int *col, double *val) {
   const int nrows = e.nrows();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
-    FillEmit em{cs, dofc, rp_d[r], has_o[r] ? rp_o[oidx[r]] : 0, col_d, val_d, col_o, val_o};
+    FillEmit em{cs, dofc, n_owned_cols, rp[r], col, val};
     e.enumerate(r, em);
   }
 }
@@ -364,42 +352,25 @@ template <class E>
 std::shared_ptr<Csr> build_dist(Ctx *c, const E &e, int nrows, const Halo &colh, int dofc, const char *tag) {
   ColSpace cs{colh.xs, colh.ys, colh.xm, colh.ym, colh.d_ring2ghost.p};
   const int ncols = colh.n_owned * dofc;
-  DevBuf<int> len_d((size_t)nrows + 1), len_o((size_t)nrows + 1), has_o((size_t)nrows + 1), rp_d((size_t)nrows + 1), oidx((size_t)nrows + 1);
+  DevBuf<int> len((size_t)nrows + 1), rp((size_t)nrows + 1);
   const int grid = std::max(1, std::min((nrows + 127) / 128, c->num_sms * 16));
   {
     LaunchScope ls(c, "assembly");
-    k_dist_count<E><<<grid, 128, 0, c->stream>>>(e, cs, len_d.p, len_o.p, has_o.p);
+    k_dist_count<E><<<grid, 128, 0, c->stream>>>(e, len.p);
     check_launch("k_dist_count");
   }
-  int nnz_d = 0, n_off = 0, nnz_o = 0;
-  exclusive_scan_i32(c, len_d.p, rp_d.p, nrows, &nnz_d);
-  exclusive_scan_i32(c, has_o.p, oidx.p, nrows, &n_off);
-  auto A = csr_alloc_public(c, nrows, ncols, nnz_d);
-  auto O = csr_alloc_public(c, n_off, colh.n_ghost * dofc, 0);
-  DevBuf<int> len_oc((size_t)n_off + 1);
-  A->off_rows.alloc((size_t)n_off + 1);
-  if (n_off) {
-    LaunchScope ls(c, "assembly");
-    k_compact_off<<<std::max(1, std::min((nrows + 255) / 256, c->num_sms * 16)), 256, 0, c->stream>>>(nrows, has_o.p, oidx.p, len_o.p, A->off_rows.p, len_oc.p);
-    check_launch("k_compact_off");
-  }
-  exclusive_scan_i32(c, len_oc.p, O->rowptr.p, n_off, &nnz_o);
-  O->nnz = nnz_o;
-  O->col.alloc((size_t)nnz_o + CSR_PAD);
-  O->val.alloc((size_t)nnz_o + CSR_PAD);
-  O->col.zero(c->stream);
-  O->val.zero(c->stream);
-  B2_CUDA(cudaMemcpyAsync(A->rowptr.p, rp_d.p, sizeof(int) * ((size_t)nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+  int nnz = 0;
+  exclusive_scan_i32(c, len.p, rp.p, nrows, &nnz);
+  auto A = csr_alloc_public(c, nrows, ncols, nnz);
+  B2_CUDA(cudaMemcpyAsync(A->rowptr.p, rp.p, sizeof(int) * ((size_t)nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
   {
     LaunchScope ls(c, "assembly");
-    k_dist_fill<E><<<grid, 128, 0, c->stream>>>(e, cs, dofc, A->rowptr.p, A->col.p, A->val.p, has_o.p, oidx.p, O->rowptr.p, O->col.p, O->val.p);
+    k_dist_fill<E><<<grid, 128, 0, c->stream>>>(e, cs, dofc, ncols, A->rowptr.p, A->col.p, A->val.p);
     check_launch("k_dist_fill");
   }
   c->sync();
   A->tag = tag;
   A->plan();
-  O->tag = std::string(tag) + "_off";
-  A->off = O;
   return A;
 }
 

@@ -1,18 +1,20 @@
-// kernels_spmv.cu -- CSR SpMV for A, B, B^T, C, P, R (replaces MatMult_SeqAIJ / MatMultAdd reached from
-// KSPSolve and PCApply; reference call site src/SaddlePointProblem.c:70).
+// kernels_spmv.cu -- CSR SpMV for A, B, B^T, C, P, R (replaces MatMult_SeqAIJ / MatMult_MPIAIJ / MatMultAdd reached
+// from KSPSolve and PCApply; reference call site src/SaddlePointProblem.c:70).
 //
 // Algorithmic bytes per launch: 12*nnz + 4*(rows+1) + 8*rows + 8*cols.
 // Kernel choice from the row-length histogram (Csr::plan):
-//   SPMV_STREAM  short rows (every 32-row group fits the per-warp shared tile): a warp owns 32 consecutive
-//                rows = ONE contiguous segment of val/col.  Phase 1 streams that segment with coalesced
-//                128-bit loads (L1 no-allocate), gathers x through L1, and parks the products in the warp's
-//                shared tile.  Phase 2: lane l sums row l's products in CSR order -> the result is
-//                bit-identical to the sequential MatMult_SeqAIJ loop (product rounded, then added).
-//                No block barrier, only __syncwarp; loads are independent of row boundaries so lanes never
-//                idle on short rows (8/12/18 nnz for A, 4/6/9 for B^T).
+//   SPMV_TMA     short rows (default): TMA-staged thread-per-row kernel, kernels_spmv_tma.cu
+//   SPMV_STREAM  short rows, no TMA: a warp owns 32 consecutive rows = ONE contiguous segment of val/col.  Phase 1
+//                streams that segment with coalesced 128-bit loads, gathers x through L1, parks the products in
+//                the warp's shared tile.  Phase 2: lane l sums row l's products in CSR order.
 //   SPMV_VECTOR  medium rows: LPR lanes per row (2..32), shuffle-tree reduction.
 //   SPMV_BLOCK   very long rows (dense constraint rows): one CTA per row.
-// Epilogue (fused): y = beta_z*z + alpha*(A x)  covers MatMult, MatMultAdd and the residual b - A x.
+// Both short-row kernels are bit-identical to the sequential MatMult_SeqAIJ loop (product rounded, then added).
+//
+// Columns >= n_owned refer to GHOST values (row-partitioned matrices): the kernels read them from the halo buffer,
+// so a distributed MatMult is ONE kernel after the halo exchange, with the same fused epilogues as on one rank:
+//   y = beta_z*z + alpha*(A x)                              MatMult / MatMultAdd / residual b - A x
+//   y = ca*pm1 + cb*pk + cc*(dinv .* (b - A pk))            one Chebyshev/Jacobi smoothing sweep in a single pass
 #include "dev.cuh"
 #include "dist.h"
 #include <type_traits>
@@ -21,18 +23,11 @@ namespace b200sp {
 
 namespace {
 
-constexpr int STREAM_WARPS = 8;           // 256 threads per CTA
+constexpr int STREAM_WARPS = 8;            // 256 threads per CTA
 constexpr int STREAM_MAX_GROUP_NNZ = 1152; // per-warp tile limit (9 KB): up to 36 nnz/row on average
 
-__device__ __forceinline__ double epilogue(double s, double alpha, const double *z, double beta_z, int r) {
-  double v = alpha * s;
-  if (z) v = beta_z * z[r] + v;
-  return v;
-}
-
 __global__ void __launch_bounds__(256) k_spmv_stream(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                     const double *__restrict__ val, const double *__restrict__ x, double *y,
-                                                     double alpha, const double *z, double beta_z, int tile_elems) {
+                                                     const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int tile_elems) {
   extern __shared__ double s_prod[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *prod = s_prod + (size_t)warp * tile_elems;
@@ -45,22 +40,20 @@ __global__ void __launch_bounds__(256) k_spmv_stream(int nrows, const int *__res
     const int s = __shfl_sync(FULL, rs, 0);
     const int e = __shfl_sync(FULL, re, 31);
     const int s_al = s & ~1; // 16-byte alignment of the val stream (col stream is then 8-byte aligned)
-    // phase 1: stream the segment [s_al, e), two entries per lane per step
 #pragma unroll 4
     for (int base = s_al + 2 * lane; base < e; base += 64) {
       const double2 v = ld_stream_f64x2(val + base);
       const int2 c = ld_stream_s32x2(col + base);
       double2 p;
-      p.x = v.x * __ldg(x + c.x);
-      p.y = v.y * __ldg(x + c.y);
+      p.x = v.x * xs.load(c.x);
+      p.y = v.y * xs.load(c.y);
       *reinterpret_cast<double2 *>(prod + (base - s_al)) = p;
     }
     __syncwarp();
-    // phase 2: one row per lane, CSR order
     if (r < nrows) {
       double sum = 0.0;
       for (int k = rs - s_al; k < re - s_al; ++k) sum += prod[k];
-      y[r] = epilogue(sum, alpha, z, beta_z, r);
+      y[r] = epi.apply(sum, r);
     }
     __syncwarp();
   }
@@ -68,8 +61,7 @@ __global__ void __launch_bounds__(256) k_spmv_stream(int nrows, const int *__res
 
 template <int LPR>
 __global__ void __launch_bounds__(256) k_spmv_vector(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                     const double *__restrict__ val, const double *__restrict__ x, double *y,
-                                                     double alpha, const double *z, double beta_z) {
+                                                     const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi) {
   constexpr int rows_per_cta = 256 / LPR;
   constexpr int rows_per_warp = 32 / LPR;
   const int sub = threadIdx.x % LPR;
@@ -80,29 +72,28 @@ __global__ void __launch_bounds__(256) k_spmv_vector(int nrows, const int *__res
     double sum = 0.0;
     if (r < nrows) {
       const int rs = rowptr[r], re = rowptr[r + 1];
-      for (int k = rs + sub; k < re; k += LPR) sum += ld_stream_f64(val + k) * __ldg(x + ld_stream_s32(col + k));
+      for (int k = rs + sub; k < re; k += LPR) sum += ld_stream_f64(val + k) * xs.load(ld_stream_s32(col + k));
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-    if (r < nrows && sub == 0) y[r] = epilogue(sum, alpha, z, beta_z, r);
+    if (r < nrows && sub == 0) y[r] = epi.apply(sum, r);
   }
 }
 
 __global__ void __launch_bounds__(256) k_spmv_block(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                                    const double *__restrict__ val, const double *__restrict__ x, double *y,
-                                                    double alpha, const double *z, double beta_z) {
+                                                    const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi) {
   __shared__ double s_w[8];
   for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
     const int rs = rowptr[r], re = rowptr[r + 1];
     double sum = 0.0;
-    for (int k = rs + threadIdx.x; k < re; k += 256) sum += ld_stream_f64(val + k) * __ldg(x + ld_stream_s32(col + k));
+    for (int k = rs + threadIdx.x; k < re; k += 256) sum += ld_stream_f64(val + k) * xs.load(ld_stream_s32(col + k));
     sum = warp_sum(sum);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < 8; ++w) t += s_w[w];
-      y[r] = epilogue(t, alpha, z, beta_z, r);
+      y[r] = epi.apply(t, r);
     }
     __syncthreads();
   }
@@ -134,47 +125,24 @@ __global__ void __launch_bounds__(256) k_row_stats(int nrows, const int *__restr
 __global__ void __launch_bounds__(256) k_get_diag(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val, double *d) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
     double v = 0.0;
-    int lo = rowptr[r], hi = rowptr[r + 1];
-    while (lo < hi) { // columns ascending: binary search
-      int mid = (lo + hi) >> 1;
-      int c = col[mid];
-      if (c < r) lo = mid + 1; else hi = mid;
-    }
-    if (lo < rowptr[r + 1] && col[lo] == r) v = val[lo];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) // rows are short; ghost columns make the row unsorted on >1 rank
+      if (col[k] == r) { v = val[k]; break; }
     d[r] = v;
   }
 }
 
-// MatZeroRowsColumns / MatZeroRows / zero columns: one thread per row, flags in a byte map
+// MatZeroRowsColumns / MatZeroRows / zero columns: one thread per row; owned columns flagged in a byte map, ghost
+// columns (>= n_owned) flagged in the halo buffer that carried the owners' flags
 __global__ void __launch_bounds__(256) k_zero_rows_cols(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col, double *val,
                                                         const unsigned char *__restrict__ rowflag, const unsigned char *__restrict__ colflag,
-                                                        double diag, int set_diag) {
+                                                        const double *__restrict__ ghostflag, int n_owned, double diag, int set_diag) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
     const bool rz = rowflag && rowflag[r];
     for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
       const int c = col[k];
       if (rz) val[k] = (set_diag && c == r) ? diag : 0.0;
-      else if (colflag && colflag[c]) val[k] = 0.0;
+      else if (c < n_owned ? (colflag && colflag[c]) : (ghostflag && ghostflag[c - n_owned] != 0.0)) val[k] = 0.0;
     }
-  }
-}
-// y[off_rows[k]] += alpha * (row k of the off-diagonal block) . ghost values   (the second half of MatMult_MPIAIJ)
-__global__ void __launch_bounds__(128) k_spmv_offdiag(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-                                                      const int *__restrict__ off_rows, const double *__restrict__ ghost, double *y, double alpha) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int t = rowptr[k]; t < rowptr[k + 1]; ++t) s += val[t] * ghost[col[t]];
-    y[off_rows[k]] += alpha * s;
-  }
-}
-// zero the off-diagonal block: whole rows whose local row is flagged, and entries whose ghost column is flagged
-__global__ void __launch_bounds__(128) k_zero_offdiag(int n, const int *__restrict__ rowptr, const int *__restrict__ col, double *val,
-                                                      const int *__restrict__ off_rows, const unsigned char *__restrict__ rowflag,
-                                                      const double *__restrict__ ghostflag) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const bool rz = rowflag && rowflag[off_rows[k]];
-    for (int t = rowptr[k]; t < rowptr[k + 1]; ++t)
-      if (rz || (ghostflag && ghostflag[col[t]] != 0.0)) val[t] = 0.0;
   }
 }
 __global__ void k_flag_to_double(int n, const unsigned char *flag, double *out) {
@@ -213,31 +181,18 @@ void Csr::plan() {
   lanes_per_row = mean <= 2 ? 2 : mean <= 4 ? 4 : mean <= 8 ? 8 : mean <= 16 ? 16 : 32;
 }
 
-static void csr_spmv_local(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z);
-
-// Distributed MatMult (MatMult_MPIAIJ): start the halo exchange of x, multiply the diagonal block while the
-// ghosts travel (separate stream), then add the off-diagonal block's contribution on the boundary rows.
-void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) {
   Ctx *c = A.ctx;
-  const bool dist = A.halo && c->dcomm;
-  if (dist) A.halo->begin(x, A.halo_dof);
-  csr_spmv_local(A, x, y, alpha, z, beta_z);
-  if (dist) {
+  XSrc xs{x, nullptr, 0x7fffffff};
+  if (A.halo && c->dcomm) { // MatMult_MPIAIJ: scatter the ghost values of x, then one kernel over owned + ghost columns
+    A.halo->begin(x, A.halo_dof);
     A.halo->end();
-    if (A.off && A.off->nrows > 0) {
-      LaunchScope ls(c, "spmv:offdiag");
-      const int n = A.off->nrows;
-      k_spmv_offdiag<<<(n + 127) / 128, 128, 0, c->stream>>>(n, A.off->rowptr.p, A.off->col.p, A.off->val.p, A.off_rows.p, A.halo->ghost.p, y, alpha);
-      check_launch("k_spmv_offdiag");
-    }
+    xs.ghost = A.halo->ghost.p;
+    xs.n_owned = A.ncols;
   }
-}
-
-static void csr_spmv_local(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
-  Ctx *c = A.ctx;
   if (A.nrows <= 0) return;
   LaunchScope ls(c, A.tag.c_str());
-  if (A.kernel == SPMV_TMA && csr_spmv_tma(A, x, y, alpha, z, beta_z)) return;
+  if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return;
   if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;
@@ -252,11 +207,11 @@ static void csr_spmv_local(const Csr &A, const double *x, double *y, double alph
     int ngroups = (A.nrows + 31) / 32;
     int grid = (ngroups + STREAM_WARPS - 1) / STREAM_WARPS;
     if (grid > c->num_sms * per_sm) grid = c->num_sms * per_sm;
-    k_spmv_stream<<<grid, 256, smem, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z, tile);
+    k_spmv_stream<<<grid, 256, smem, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, tile);
     check_launch("k_spmv_stream");
   } else if (A.kernel == SPMV_BLOCK) {
     int grid = A.nrows < c->num_sms * 8 ? A.nrows : c->num_sms * 8;
-    k_spmv_block<<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z);
+    k_spmv_block<<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, xs, y, epi);
     check_launch("k_spmv_block");
   } else {
     auto launch = [&](auto lpr_tag) {
@@ -264,7 +219,7 @@ static void csr_spmv_local(const Csr &A, const double *x, double *y, double alph
       int rows_per_cta = 256 / LPR;
       int grid = (A.nrows + rows_per_cta - 1) / rows_per_cta;
       if (grid > c->num_sms * 8) grid = c->num_sms * 8;
-      k_spmv_vector<LPR><<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z);
+      k_spmv_vector<LPR><<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, xs, y, epi);
     };
     switch (A.lanes_per_row) {
     case 2: launch(std::integral_constant<int, 2>()); break;
@@ -275,6 +230,12 @@ static void csr_spmv_local(const Csr &A, const double *x, double *y, double alph
     }
     check_launch("k_spmv_vector");
   }
+}
+
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+  SpmvEpi e;
+  e.alpha = alpha; e.z = z; e.beta_z = beta_z;
+  csr_spmv_epi(A, x, y, e);
 }
 
 void csr_get_diagonal(const Csr &A, double *d) {
@@ -292,6 +253,8 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
   DevBuf<int> d_idx((size_t)n + 1);
   if (n > 0) B2_CUDA(cudaMemcpyAsync(d_idx.p, rows_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   DevBuf<unsigned char> rowflag, colflag;
+  DevBuf<double> fl;
+  const double *ghostflag = nullptr;
   int g = (n + 255) / 256;
   if (g < 1) g = 1;
   if (do_rows) {
@@ -303,31 +266,20 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
   if (do_cols) {
     colflag.alloc((size_t)A.ncols);
     colflag.zero(c->stream);
-    LaunchScope ls(c, "setup");
-    k_mark<<<g, 256, 0, c->stream>>>(n, d_idx.p, colflag.p);
-  }
-  if (dist && A.off) { // ghost columns: the owners' column flags travel through the same halo as x
-    DevBuf<double> fl((size_t)A.ncols + 2);
-    const double *gf = nullptr;
-    if (do_cols) {
+    { LaunchScope ls(c, "setup"); k_mark<<<g, 256, 0, c->stream>>>(n, d_idx.p, colflag.p); }
+    if (dist) { // the owners' column flags travel through the same halo as x
+      fl.alloc((size_t)A.ncols + 2);
       { LaunchScope ls(c, "setup"); k_flag_to_double<<<(A.ncols + 255) / 256, 256, 0, c->stream>>>(A.ncols, colflag.p, fl.p); }
       A.halo->begin(fl.p, A.halo_dof);
       A.halo->end();
-      gf = A.halo->ghost.p;
+      ghostflag = A.halo->ghost.p;
     }
-    if (A.off->nrows > 0) {
-      LaunchScope ls(c, "setup");
-      k_zero_offdiag<<<(A.off->nrows + 127) / 128, 128, 0, c->stream>>>(A.off->nrows, A.off->rowptr.p, A.off->col.p, A.off->val.p, A.off_rows.p,
-                                                                         do_rows ? rowflag.p : nullptr, gf);
-      check_launch("k_zero_offdiag");
-    }
-    c->sync();
   }
   {
     LaunchScope ls(c, "setup");
     int grid = (A.nrows + 255) / 256;
     k_zero_rows_cols<<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, do_rows ? rowflag.p : nullptr,
-                                                   do_cols ? colflag.p : nullptr, diag, set_diag ? 1 : 0);
+                                                   do_cols ? colflag.p : nullptr, ghostflag, A.ncols, diag, set_diag ? 1 : 0);
     check_launch("k_zero_rows_cols");
   }
   c->sync(); // temporaries are freed on return

@@ -42,7 +42,7 @@ constexpr int TMA_MAX_STAGES = 4;
 // dynamic shared layout: [S stages][ val: cap doubles | col: cap ints ], then S mbarriers
 template <int UNROLL>
 __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-                           const double *__restrict__ x, double *y, double alpha, const double *z, double beta_z, int cap, int stages) {
+                           XSrc xs, double *y, SpmvEpi epi, int cap, int stages) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int R = blockDim.x;
   const size_t stage_bytes = (size_t)cap * 12;
@@ -93,14 +93,12 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr
       for (; k + UNROLL <= ke; k += UNROLL) {
         double xv[UNROLL], av[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) { av[u] = sv[k + u]; xv[u] = __ldg(x + sc[k + u]); }
+        for (int u = 0; u < UNROLL; ++u) { av[u] = sv[k + u]; xv[u] = xs.load(sc[k + u]); }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) sum += av[u] * xv[u];
       }
-      for (; k < ke; ++k) sum += sv[k] * __ldg(x + sc[k]);
-      double v = alpha * sum;
-      if (z) v = beta_z * z[r] + v;
-      y[r] = v;
+      for (; k < ke; ++k) sum += sv[k] * xs.load(sc[k]);
+      y[r] = epi.apply(sum, r);
     }
     __syncthreads(); // every consumer is done with this stage
     if (tid == 0) {
@@ -113,7 +111,7 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr
 } // namespace
 
 // returns false when the matrix does not fit the shared-memory tiling (caller falls back)
-bool csr_spmv_tma(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi) {
   Ctx *c = A.ctx;
   const size_t budget = 225 * 1024;
   int R = 0, stages = 0, cap = 0;
@@ -147,9 +145,9 @@ bool csr_spmv_tma(const Csr &A, const double *x, double *y, double alpha, const 
   const double mean = A.nrows ? (double)A.nnz / A.nrows : 0.0;
   (void)mean;
   if (env_U ? env_U == 6 : true)
-    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z, cap, stages);
+    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
   else
-    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, x, y, alpha, z, beta_z, cap, stages);
+    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
   check_launch("k_spmv_tma");
   return true;
 }

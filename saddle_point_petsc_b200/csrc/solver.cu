@@ -263,23 +263,42 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
   const bool fused = (dinv || !M) && norm_none;
   reason = 0;
   const double *res = b;
-  if (guess_nonzero) { A->residual(b, x, r); res = r; }
+  if (guess_nonzero && !fused) { A->residual(b, x, r); res = r; }
   if (fused) {
     // Smoother mode (fixed sweeps, Jacobi or no PC): no copies and no zero-fill.  The previous iterate of the
     // first update is x itself (nonzero guess) or the zero vector (coefficient 0 on a finite dummy operand);
     // iterates ping-pong between two scratch vectors and the LAST update writes straight into x.  Every
     // update is elementwise, so writing over the vector that holds p_{k-1} is safe.
+    // When the operator is a CSR matrix each sweep after the first is ONE kernel: the SpMV's epilogue forms the
+    // residual, applies Jacobi and the three-term update (SpmvEpi::cheb) -- r is never written to memory.
+    const Csr *Ac = A->csr();
+    auto sweep = [&](const double *pm1_, double ca, const double *cur_, double cb, double cc, double *out) {
+      if (Ac) {
+        SpmvEpi e;
+        e.cheb = 1; e.z = b; e.pm1 = pm1_; e.pk = cur_; e.dinv = dinv; e.ca = ca; e.cb = cb; e.cc = cc;
+        csr_spmv_epi(*Ac, cur_, out, e);
+      } else {
+        A->residual(b, cur_, r);
+        vec_cheb_update(ctx, n, ca, pm1_, cb, cur_, cc, dinv, r, out);
+      }
+    };
     const double *pm1 = guess_nonzero ? x : b; // b is only a finite dummy when the guess is zero
     double am1 = guess_nonzero ? 1.0 : 0.0;
-    double *cur = max_it == 1 ? x : w2.p;
-    vec_cheb_update(ctx, n, am1, pm1, 0.0, pm1, scale, dinv, res, cur); // p1 = x0 + scale * M^-1 r0
+    double *cur;
+    if (guess_nonzero) {
+      cur = w2.p;                                   // p1 = x0 + scale * M^-1 (b - A x0); never in place: the SpMV gathers x0
+      sweep(x, 1.0, x, 0.0, scale, cur);
+      if (max_it == 1) vec_copy(ctx, n, cur, x);
+    } else {
+      cur = max_it == 1 ? x : w2.p;
+      vec_cheb_update(ctx, n, 0.0, b, 0.0, b, scale, dinv, b, cur); // p1 = scale * M^-1 b
+    }
     its = 1;
     for (int i = 1; i < max_it; ++i) {
-      A->residual(b, cur, r);
       ckp1 = 2.0 * mu * ck - ckm1;
       omega = omegaprod * ck / ckp1;
       double *out = (i == max_it - 1) ? x : (cur == w2.p ? w3.p : w2.p);
-      vec_cheb_update(ctx, n, (1.0 - omega) * am1, pm1, omega, cur, omega * scale, dinv, r, out);
+      sweep(pm1, (1.0 - omega) * am1, cur, omega, omega * scale, out);
       pm1 = cur; am1 = 1.0; cur = out;
       ckm1 = ck; ck = ckp1;
       its = i + 1;

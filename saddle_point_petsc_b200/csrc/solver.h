@@ -20,6 +20,7 @@ struct Op {
   }
   virtual std::string view(int indent) const = 0;
   virtual const double *jacobi_dinv() const { return nullptr; } // non-null when the op is y = x .* dinv
+  virtual const Csr *csr() const { return nullptr; }            // non-null when the op is a plain CSR MatMult
 };
 
 struct CsrOp : Op { // MatMult
@@ -27,6 +28,7 @@ struct CsrOp : Op { // MatMult
   explicit CsrOp(std::shared_ptr<Csr> a) : Op(a->ctx, a->ncols, a->nrows), A(a) {}
   void apply(const double *x, double *y) override { csr_spmv(*A, x, y); }
   void residual(const double *b, const double *x, double *r) override { csr_spmv(*A, x, r, -1.0, b, 1.0); }
+  const Csr *csr() const override { return A.get(); }
   std::string view(int indent) const override;
 };
 
