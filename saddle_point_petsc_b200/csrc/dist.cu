@@ -29,6 +29,7 @@ struct LocalComm : Comm {
   int rank() const override { return r; }
   int size() const override { return g->size; }
   void barrier() override { g->barrier(); }
+  bool capturable() const override { return false; }
   void allreduce_sum(double *d, int k, cudaStream_t s) override {
     B2_REQUIRE(k <= N_SCALARS, "allreduce: too many scalars");
     double *mine = g->host_scratch.data() + (size_t)r * N_SCALARS;
@@ -80,6 +81,7 @@ struct NcclComm : Comm {
   int rank() const override { return r; }
   int size() const override { return n; }
   void barrier() override {}
+  bool capturable() const override { return true; }
   void allreduce_sum(double *d, int k, cudaStream_t s) override { B2_NCCL(nccl().AllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c, s)); }
   void exchange(const double *sendbuf, double *recvbuf, const std::vector<HaloMsg> &msgs, cudaStream_t s) override {
     B2_NCCL(nccl().GroupStart());

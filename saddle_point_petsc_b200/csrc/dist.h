@@ -27,6 +27,7 @@ struct Comm {
   // gather `cnt` doubles from every rank into out[rank*cnt...] on every rank (redundant coarse multigrid levels)
   virtual void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) = 0;
   virtual void barrier() = 0;
+  virtual bool capturable() const = 0; // may its calls be recorded into a CUDA graph (no host-side waits)?
 };
 
 struct LocalGroup { // shared by the rank-threads of one process

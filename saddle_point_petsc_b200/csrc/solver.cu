@@ -63,6 +63,16 @@ DenseInvOp::DenseInvOp(const Csr &A) : Op(A.ctx, A.nrows, A.nrows), Ainv((size_t
 std::string DenseInvOp::view(int indent) const { return pad(indent) + "PC dense inverse (coarse LU stand-in) n=" + std::to_string(n_in) + "\n"; }
 
 KspOp::KspOp(Ksp *k) : Op(k->ctx, k->n, k->n), ksp(k) {}
+bool KspOp::capturable() const { // no convergence test (no host read-back) and a capturable preconditioner
+  const bool fixed = ksp->type == KSP_PREONLY || ((ksp->type == KSP_CHEBYSHEV || ksp->type == KSP_RICHARDSON) && ksp->norm_none);
+  return fixed && (!ksp->M || ksp->M->capturable()) && ksp->A->capturable();
+}
+bool MgOp::capturable() const {
+  if (replicated && !(ctx->dcomm && ctx->dcomm->capturable() && replicated->capturable())) return false;
+  for (auto &L : lev)
+    if (L->smooth && !(L->smooth->norm_none && (L->smooth->type == KSP_CHEBYSHEV || L->smooth->type == KSP_RICHARDSON))) return false;
+  return true;
+}
 void KspOp::apply(const double *x, double *y) { ksp->solve(x, y, false); }
 std::string KspOp::view(int indent) const { return ksp->view(indent); }
 
@@ -183,8 +193,43 @@ std::string MgOp::view(int indent) const {
 }
 
 // ------------------------------------------------------------------ KSP
+Ksp::~Ksp() {
+  for (auto &kv : pc_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+}
+
+// PCApply.  For the outer KSP the whole preconditioner (fieldsplit + multigrid V-cycle: several hundred short kernels
+// and, on >1 GPU, the NCCL halo exchanges between them) is recorded once per (x, y) pair into a CUDA graph and
+// replayed: the launch-latency-bound coarse levels then cost one graph launch instead of one launch each.
 void Ksp::pc_apply(const double *x, double *y) {
-  if (M) M->apply(x, y); else vec_copy(ctx, n, x, y);
+  if (!M) { vec_copy(ctx, n, x, y); return; }
+  if (!use_pc_graph || ctx->profile) { M->apply(x, y); return; }
+  if (!pc_warmed) { M->apply(x, y); pc_warmed = true; return; } // first call runs eagerly: lazy allocations, func attributes
+  auto key = std::make_pair(x, y);
+  auto it = pc_graphs.find(key);
+  if (it == pc_graphs.end()) {
+    if (pc_graphs.size() >= 96) { M->apply(x, y); return; }
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = ctx->launches;
+    B2_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      M->apply(x, y);
+    } catch (...) {
+      cudaStreamEndCapture(ctx->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      use_pc_graph = false;
+      throw;
+    }
+    B2_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    PcGraph g;
+    g.launches = ctx->launches - l0;
+    B2_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    B2_CUDA(cudaGraphDestroy(graph));
+    it = pc_graphs.emplace(key, g).first;
+  } else {
+    ctx->launches += it->second.launches; // the recorded kernels run again
+  }
+  B2_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
 }
 double Ksp::dot(const double *x, const double *y) {
   double r;
@@ -805,6 +850,7 @@ void Solver::setup() {
   outer_pc = pc;
   outer = make_ksp("", Aop, pc, "gmres");
   outer->keep_history = true;
+  outer->use_pc_graph = pc && opt("b200sp_pc_graph", "1") != "0" && pc->capturable() && (!ctx->dcomm || ctx->dcomm->capturable());
   ctx->sync();
   is_setup = true;
 }

@@ -21,6 +21,9 @@ struct Op {
   virtual std::string view(int indent) const = 0;
   virtual const double *jacobi_dinv() const { return nullptr; } // non-null when the op is y = x .* dinv
   virtual const Csr *csr() const { return nullptr; }            // non-null when the op is a plain CSR MatMult
+  // true when apply() only enqueues work on the context's streams (no host synchronisation, no allocation after
+  // the first call), i.e. it can be recorded into a CUDA graph
+  virtual bool capturable() const { return true; }
 };
 
 struct CsrOp : Op { // MatMult
@@ -61,6 +64,7 @@ struct Ksp;
 struct KspOp : Op { // y = ksp(x), zero initial guess
   Ksp *ksp;
   explicit KspOp(Ksp *k);
+  bool capturable() const override;
   void apply(const double *x, double *y) override;
   std::string view(int indent) const override;
 };
@@ -70,6 +74,7 @@ struct SchurOp : Op { // MatSchurComplement: S x = A11 x - A10 ksp(A00) A01 x
   Op *K0;
   DevBuf<double> t0, t1;
   SchurOp(std::shared_ptr<Csr> a11, std::shared_ptr<Csr> a10, Op *k0, std::shared_ptr<Csr> a01);
+  bool capturable() const override { return K0->capturable(); }
   void apply(const double *x, double *y) override;
   std::string view(int indent) const override;
 };
@@ -81,6 +86,7 @@ struct FieldSplitOp : Op { // PCFIELDSPLIT, Schur factorisations
   Op *K0, *KS;
   DevBuf<double> t0, t1;
   FieldSplitOp(int fact_, double scale_, std::shared_ptr<Csr> a01, std::shared_ptr<Csr> a10, Op *k0, Op *ks);
+  bool capturable() const override { return K0->capturable() && KS->capturable(); }
   void apply(const double *b, double *y) override;
   std::string view(int indent) const override;
 };
@@ -92,6 +98,7 @@ struct LscOp : Op { // PCLSC
   bool scale_diag;
   DevBuf<double> p0, p1, u0, u1;
   LscOp(std::shared_ptr<Csr> a00, std::shared_ptr<Csr> a01, std::shared_ptr<Csr> a10, Op *linv, bool scale_diag_);
+  bool capturable() const override { return Linv->capturable(); }
   void apply(const double *x, double *y) override;
   std::string view(int indent) const override;
 };
@@ -112,6 +119,7 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   DevBuf<int> gather_map, local_map;
   int bridge_cnt = 0, bridge_nloc = 0;
   MgOp(Ctx *c, int64_t n) : Op(c, n, n) {}
+  bool capturable() const override;
   void cycle(int l, const double *b, double *x);
   void apply(const double *b, double *x) override;
   std::string view(int indent) const override;
@@ -137,6 +145,12 @@ struct Ksp {
   // workspace (allocated on first solve)
   DevBuf<double> V, Z, w0, w1, w2, w3, w4, w5, w6, w7, w8;
   int64_t ld = 0;
+  // CUDA-graph replay of the preconditioner application (outer KSP only): one instantiated graph per (input, output)
+  // vector pair -- the Krylov basis vectors are persistent, so the pairs repeat from solve to solve
+  struct PcGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  bool use_pc_graph = false, pc_warmed = false;
+  std::map<std::pair<const double *, double *>, PcGraph> pc_graphs;
+  ~Ksp();
 
   Ksp(Ctx *c, const std::string &pfx) : ctx(c), prefix(pfx) {}
   void set_operators(Op *a, Op *m) { A = a; M = m; n = a->n_in; }
