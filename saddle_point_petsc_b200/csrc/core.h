@@ -146,7 +146,9 @@ struct Dmda {
 enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3 };
 struct XSrc;
 struct SpmvEpi;
-bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi);
+constexpr int TMA_TILE_ROWS = 128; // rows per tile of the TMA SpMV kernel (profiles/r01_tma_tile_sweep.txt)
+int spmv_tma_tile_rows();
+bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list = nullptr, int nlist = 0);
 
 struct Csr {
   Ctx *ctx = nullptr;
@@ -167,6 +169,9 @@ struct Csr {
   // row-partitioned (MPIAIJ-like) matrix: local rows; columns < ncols are owned (local ids), columns >= ncols are
   // ghost nodes in MPIAIJ garray order, read by the kernels from the halo buffer
   std::shared_ptr<Halo> halo;     // column-space halo (null on one rank); column ids >= ncols are ghost ids + ncols
+  // TMA_TILE_ROWS-row tiles without / with ghost columns: the interior tiles are multiplied while the halo travels
+  DevBuf<int> tiles_interior, tiles_boundary;
+  int n_tiles_interior = 0, n_tiles_boundary = 0;
   int halo_dof = 0;               // dof per node of the column space
   std::shared_ptr<Layout> layout;  // node layout of a square DMDA matrix (multigrid coarsening)
   int64_t row_gstart = 0, col_gstart = 0; // first global row / owned global column of this rank (PETSc numbering)

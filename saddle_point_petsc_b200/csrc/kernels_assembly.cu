@@ -348,6 +348,14 @@ template <class E> __global__ void __launch_bounds__(128) k_dist_fill(E e, ColSp
   }
 }
 
+__global__ void __launch_bounds__(256) k_tile_has_ghost(int nrows, int n_owned_cols, const int *__restrict__ rowptr, const int *__restrict__ col, int *tile_flag) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    bool g = false;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) g |= col[k] >= n_owned_cols;
+    if (g) tile_flag[r / TMA_TILE_ROWS] = 1;
+  }
+}
+
 template <class E>
 std::shared_ptr<Csr> build_dist(Ctx *c, const E &e, int nrows, const Halo &colh, int dofc, const char *tag) {
   ColSpace cs{colh.xs, colh.ys, colh.xm, colh.ym, colh.d_ring2ghost.p};
@@ -371,6 +379,26 @@ std::shared_ptr<Csr> build_dist(Ctx *c, const E &e, int nrows, const Halo &colh,
   c->sync();
   A->tag = tag;
   A->plan();
+  // interior / boundary tile lists (TMA_TILE_ROWS rows per tile): a tile is "boundary" if any of its rows has a ghost column
+  const int ntiles = (nrows + TMA_TILE_ROWS - 1) / TMA_TILE_ROWS;
+  DevBuf<int> flag((size_t)ntiles + 1);
+  flag.zero(c->stream);
+  {
+    LaunchScope ls(c, "assembly");
+    k_tile_has_ghost<<<std::max(1, std::min((nrows + 255) / 256, c->num_sms * 16)), 256, 0, c->stream>>>(nrows, ncols, A->rowptr.p, A->col.p, flag.p);
+    check_launch("k_tile_has_ghost");
+  }
+  std::vector<int> h((size_t)ntiles + 1), ti, tb;
+  B2_CUDA(cudaMemcpyAsync(h.data(), flag.p, sizeof(int) * (size_t)ntiles, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  for (int t = 0; t < ntiles; ++t) (h[(size_t)t] ? tb : ti).push_back(t);
+  A->n_tiles_interior = (int)ti.size();
+  A->n_tiles_boundary = (int)tb.size();
+  A->tiles_interior.alloc(ti.size() + 1);
+  A->tiles_boundary.alloc(tb.size() + 1);
+  if (!ti.empty()) B2_CUDA(cudaMemcpyAsync(A->tiles_interior.p, ti.data(), sizeof(int) * ti.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!tb.empty()) B2_CUDA(cudaMemcpyAsync(A->tiles_boundary.p, tb.data(), sizeof(int) * tb.size(), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
   return A;
 }
 

@@ -184,11 +184,25 @@ void Csr::plan() {
 void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) {
   Ctx *c = A.ctx;
   XSrc xs{x, nullptr, 0x7fffffff};
-  if (A.halo && c->dcomm) { // MatMult_MPIAIJ: scatter the ghost values of x, then one kernel over owned + ghost columns
+  if (A.halo && c->dcomm) {
+    // MatMult_MPIAIJ.  The ghost values of x travel on the halo stream while the tiles that have no ghost column
+    // (the interior: ~90% of the rows) are multiplied; the boundary tiles follow once the halo has arrived.
     A.halo->begin(x, A.halo_dof);
+    const bool split = A.kernel == SPMV_TMA && A.tiles_interior.p && spmv_tma_tile_rows() == TMA_TILE_ROWS && A.nrows > 0;
+    if (split && A.n_tiles_interior > 0) {
+      LaunchScope ls(c, A.tag.c_str());
+      csr_spmv_tma(A, xs, y, epi, A.tiles_interior.p, A.n_tiles_interior);
+    }
     A.halo->end();
     xs.ghost = A.halo->ghost.p;
     xs.n_owned = A.ncols;
+    if (split) {
+      if (A.n_tiles_boundary > 0) {
+        LaunchScope ls(c, A.tag.c_str());
+        csr_spmv_tma(A, xs, y, epi, A.tiles_boundary.p, A.n_tiles_boundary);
+      }
+      return;
+    }
   }
   if (A.nrows <= 0) return;
   LaunchScope ls(c, A.tag.c_str());

@@ -41,15 +41,18 @@ constexpr int TMA_MAX_STAGES = 4;
 
 // dynamic shared layout: [S stages][ val: cap doubles | col: cap ints ], then S mbarriers
 template <int UNROLL>
-__global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-                           XSrc xs, double *y, SpmvEpi epi, int cap, int stages) {
+__global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ rowptr, const int *__restrict__ col,
+                           const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int cap, int stages) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int R = blockDim.x;
   const size_t stage_bytes = (size_t)cap * 12;
   uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + stage_bytes * stages);
   const int tid = threadIdx.x;
 
-  auto issue = [&](int tile, int stage) { // one thread
+  // ntiles counts the entries of tile_list when one is given (interior / boundary subsets of a row-partitioned
+  // matrix, so the interior can run while the halo is in flight), otherwise all tiles 0..ntiles-1
+  auto issue = [&](int idx, int stage) { // one thread
+    const int tile = tile_list ? tile_list[idx] : idx;
     const int r0 = tile * R;
     const int r1 = min(r0 + R, nrows);
     const int s0 = rowptr[r0] & ~3;
@@ -75,7 +78,8 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr
     }
   }
   int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
+    const int tile = tile_list ? tile_list[idx] : idx;
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
     const int r = tile * R + tid;
@@ -102,7 +106,7 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr
     }
     __syncthreads(); // every consumer is done with this stage
     if (tid == 0) {
-      const int t = tile + stages * gridDim.x;
+      const int t = idx + stages * gridDim.x;
       if (t < ntiles) issue(t, stage);
     }
   }
@@ -111,7 +115,12 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ rowptr
 } // namespace
 
 // returns false when the matrix does not fit the shared-memory tiling (caller falls back)
-bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi) {
+int spmv_tma_tile_rows() {
+  static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;
+  return env_R ? env_R : TMA_TILE_ROWS;
+}
+
+bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list, int nlist) {
   Ctx *c = A.ctx;
   const size_t budget = 225 * 1024;
   int R = 0, stages = 0, cap = 0;
@@ -137,7 +146,9 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi) {
     B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int ntiles = (A.nrows + R - 1) / R;
+  if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
+  const int ntiles = tile_list ? nlist : (A.nrows + R - 1) / R;
+  if (ntiles <= 0) return true;
   int per_sm = (int)(budget / smem);
   if (per_sm < 1) per_sm = 1;
   if (per_sm * R > 2048) per_sm = 2048 / R;
@@ -145,9 +156,9 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi) {
   const double mean = A.nrows ? (double)A.nnz / A.nrows : 0.0;
   (void)mean;
   if (env_U ? env_U == 6 : true)
-    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
+    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
   else
-    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
+    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
   check_launch("k_spmv_tma");
   return true;
 }
