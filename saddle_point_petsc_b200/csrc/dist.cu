@@ -243,7 +243,21 @@ void Halo::begin(const double *x, int dof) {
   B2_CUDA(cudaStreamWaitEvent(c->stream2, ev_packed, 0));
   std::vector<HaloMsg> msgs = node_msgs;
   for (HaloMsg &m : msgs) { m.send_off *= dof; m.send_cnt *= dof; m.recv_off *= dof; m.recv_cnt *= dof; }
-  c->dcomm->exchange(sendbuf.p, ghost.p, msgs, c->stream2);
+  if (c->profile) { // measurement pass: time the exchange itself on the halo stream
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream2);
+    c->dcomm->exchange(sendbuf.p, ghost.p, msgs, c->stream2);
+    cudaEventRecord(e1, c->stream2);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    auto &pe = c->prof["comm:halo_exchange"];
+    pe.ms += ms; pe.n++;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  } else {
+    c->dcomm->exchange(sendbuf.p, ghost.p, msgs, c->stream2);
+  }
   B2_CUDA(cudaEventRecord(ev_arrived, c->stream2));
 }
 void Halo::end() {

@@ -17,6 +17,7 @@
 //   y = ca*pm1 + cb*pk + cc*(dinv .* (b - A pk))            one Chebyshev/Jacobi smoothing sweep in a single pass
 #include "dev.cuh"
 #include "dist.h"
+#include <cstdlib>
 #include <type_traits>
 
 namespace b200sp {
@@ -188,7 +189,11 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) 
     // MatMult_MPIAIJ.  The ghost values of x travel on the halo stream while the tiles that have no ghost column
     // (the interior: ~90% of the rows) are multiplied; the boundary tiles follow once the halo has arrived.
     A.halo->begin(x, A.halo_dof);
-    const bool split = A.kernel == SPMV_TMA && A.tiles_interior.p && spmv_tma_tile_rows() == TMA_TILE_ROWS && A.nrows > 0;
+    // Measured (profiles/r01_scaling_notes.md): with the persistent TMA grid holding every SM the NCCL kernel cannot
+    // start until the interior kernel drains, so the two-launch split was slightly SLOWER (20.3 vs 19.9 ms at 8 GPUs).
+    // It stays available behind B200SP_SPMV_OVERLAP=1; the default is one kernel after the halo has arrived.
+    static const bool want_split = getenv("B200SP_SPMV_OVERLAP") && atoi(getenv("B200SP_SPMV_OVERLAP")) != 0;
+    const bool split = want_split && A.kernel == SPMV_TMA && A.tiles_interior.p && spmv_tma_tile_rows() == TMA_TILE_ROWS && A.nrows > 0;
     if (split && A.n_tiles_interior > 0) {
       LaunchScope ls(c, A.tag.c_str());
       csr_spmv_tma(A, xs, y, epi, A.tiles_interior.p, A.n_tiles_interior);

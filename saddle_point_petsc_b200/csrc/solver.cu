@@ -21,7 +21,19 @@ void Ctx::fetch_scalars(const double *d, int k, double *host) {
   std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
 }
 static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
-  if (c->dcomm) c->dcomm->allreduce_sum(d, k, c->stream);
+  if (!c->dcomm) return;
+  if (c->profile) {
+    cudaEventRecord(c->pev0, c->stream);
+    c->dcomm->allreduce_sum(d, k, c->stream);
+    cudaEventRecord(c->pev1, c->stream);
+    cudaEventSynchronize(c->pev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->pev0, c->pev1);
+    auto &pe = c->prof["comm:allreduce"];
+    pe.ms += ms; pe.n++;
+    return;
+  }
+  c->dcomm->allreduce_sum(d, k, c->stream);
 }
 
 // ------------------------------------------------------------------ operators
@@ -172,7 +184,16 @@ void MgOp::cycle(int l, const double *b, double *x) {
     // bridge to the replicated coarse hierarchy: restrict into my part of the coarse vector, all-gather, reorder to
     // the natural numbering, run the remaining levels redundantly on every rank, take my part back, interpolate
     csr_spmv(*L.R, L.r.p, loc_b.p);
+    if (ctx->profile) cudaEventRecord(ctx->pev0, ctx->stream);
     ctx->dcomm->allgather(loc_b.p, g_all.p, bridge_cnt, ctx->stream);
+    if (ctx->profile) {
+      cudaEventRecord(ctx->pev1, ctx->stream);
+      cudaEventSynchronize(ctx->pev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->pev0, ctx->pev1);
+      auto &pe = ctx->prof["comm:allgather"];
+      pe.ms += ms; pe.n++;
+    }
     vec_permute_scatter(ctx, (int64_t)bridge_cnt * ctx->size, gather_map.p, g_all.p, nat_b.p);
     replicated->apply(nat_b.p, nat_x.p);
     vec_permute_gather(ctx, bridge_nloc, local_map.p, nat_x.p, loc_x.p);
