@@ -33,6 +33,7 @@ Ctx::~Ctx() {
   if (d_ticket) cudaFree(d_ticket);
   if (d_scalars) cudaFree(d_scalars);
   if (h_scalars) cudaFreeHost(h_scalars);
+  if (h_err) cudaFreeHost(h_err);
   if (pev0) cudaEventDestroy(pev0);
   if (pev1) cudaEventDestroy(pev1);
   if (tev0) cudaEventDestroy(tev0);
@@ -100,6 +101,9 @@ int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b
     B2_CUDA(cudaMalloc((void **)&c.d_scalars, sizeof(double) * N_SCALARS));
     B2_CUDA(cudaMemset(c.d_scalars, 0, sizeof(double) * N_SCALARS));
     B2_CUDA(cudaMallocHost((void **)&c.h_scalars, sizeof(double) * N_SCALARS));
+    B2_CUDA(cudaHostAlloc((void **)&c.h_err, sizeof(int), cudaHostAllocMapped));
+    *c.h_err = 0;
+    B2_CUDA(cudaHostGetDevicePointer((void **)&c.d_err, c.h_err, 0));
     B2_CUDA(cudaEventCreate(&c.pev0)); B2_CUDA(cudaEventCreate(&c.pev1));
     B2_CUDA(cudaEventCreate(&c.tev0)); B2_CUDA(cudaEventCreate(&c.tev1));
     if (size > 1) {

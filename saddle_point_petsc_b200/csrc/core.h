@@ -53,6 +53,7 @@ struct Ctx {
   unsigned *d_ticket = nullptr;
   double *d_scalars = nullptr; // device result slots
   double *h_scalars = nullptr; // pinned mirror
+  int *h_err = nullptr, *d_err = nullptr; // pinned+mapped error word: device-side waits that time out report here
   int64_t launches = 0;
   bool profile = false;
   std::map<std::string, ProfEntry> prof;
@@ -219,8 +220,15 @@ void vec_scale_inv_sqrt(Ctx *c, int64_t n, const double *nrm2_dev, const double 
 struct XSrc {
   const double *x, *ghost;
   int n_owned;
+  const unsigned long long *seq = nullptr; // peer-to-peer halos: exchanges started so far; the latest one is in parity (seq-1)&1
+  long long ghost_stride = 0;
 #ifdef __CUDACC__
-  __device__ __forceinline__ double load(int c) const { return c < n_owned ? __ldg(x + c) : __ldg(ghost + (c - n_owned)); }
+  __device__ __forceinline__ double load(int c) const {
+    if (c < n_owned) return __ldg(x + c);
+    const double *g = ghost + (c - n_owned);
+    if (seq) g += ((*seq - 1ull) & 1ull) * ghost_stride;
+    return *g; // plain load: the buffer is written by a peer GPU (never through the non-coherent path)
+  }
 #endif
 };
 // fused epilogue of every SpMV kernel, applied to the row sum s of row r:

@@ -2,6 +2,8 @@
 #include "dist.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include "dev.cuh"
 
 namespace b200sp {
@@ -30,6 +32,7 @@ struct LocalComm : Comm {
   int size() const override { return g->size; }
   void barrier() override { g->barrier(); }
   bool capturable() const override { return false; }
+  bool p2p_capable() const override { return false; } // rank-threads may share one GPU: kernels must not wait on each other
   void allreduce_sum(double *d, int k, cudaStream_t s) override {
     B2_REQUIRE(k <= N_SCALARS, "allreduce: too many scalars");
     double *mine = g->host_scratch.data() + (size_t)r * N_SCALARS;
@@ -82,6 +85,7 @@ struct NcclComm : Comm {
   int size() const override { return n; }
   void barrier() override {}
   bool capturable() const override { return true; }
+  bool p2p_capable() const override { static const bool off = getenv("B200SP_NO_P2P") && atoi(getenv("B200SP_NO_P2P")); return !off; }
   void allreduce_sum(double *d, int k, cudaStream_t s) override { B2_NCCL(nccl().AllReduce(d, d, (size_t)k, ncclDouble, ncclSum, c, s)); }
   void exchange(const double *sendbuf, double *recvbuf, const std::vector<HaloMsg> &msgs, cudaStream_t s) override {
     B2_NCCL(nccl().GroupStart());
@@ -169,9 +173,114 @@ __global__ void __launch_bounds__(256) k_pack(int n, int dof, const int *__restr
 }
 } // namespace
 
+// push: every outgoing value goes straight into the neighbour's ghost buffer (parity of this exchange); the last
+// block to finish (after a system-scope fence) raises the sequence flag in every neighbour's memory.
+__global__ void __launch_bounds__(256) k_halo_push(int n_send, int dof, int nmsg, const int *__restrict__ lnode, const double *__restrict__ x,
+                                                   const Halo::P2PMsg *__restrict__ msgs, unsigned long long *seq, unsigned *ticket) {
+  __shared__ bool s_last;
+  const unsigned long long k = *seq; // exchanges completed before this one
+  const unsigned long long par = k & 1ull;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_send * dof; t += gridDim.x * blockDim.x) {
+    const int node = t / dof, c = t % dof;
+    int m = 0;
+    while (m + 1 < nmsg && node >= msgs[m].send_off + msgs[m].send_cnt) ++m;
+    const Halo::P2PMsg &g = msgs[m];
+    g.peer_ghost[par * g.peer_stride + (long long)(g.peer_recv_off + node - g.send_off) * dof + c] = x[(size_t)lnode[node] * dof + c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x < nmsg) {
+    volatile unsigned long long *f = msgs[threadIdx.x].peer_flag;
+    *f = k + 1ull;
+  }
+  if (threadIdx.x == 0) { *ticket = 0u; *seq = k + 1ull; }
+}
+// wait: one lane per incoming message polls this rank's own flag word until the neighbour's push of the current
+// exchange has landed.  Bounded: after ~2 s of polling it reports through the context's mapped error word.
+__global__ void k_halo_wait(int nmsg, const unsigned long long *seq, const unsigned long long *flags, int *err) {
+  if ((int)threadIdx.x >= nmsg) return;
+  const unsigned long long want = *seq;
+  volatile const unsigned long long *f = flags + threadIdx.x;
+  for (long long spin = 0; *f < want; ++spin) {
+    __nanosleep(200);
+    if (spin > 10000000LL) { *err = 100 + (int)threadIdx.x; __threadfence_system(); return; }
+  }
+}
+
 Halo::~Halo() {
+  for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
   if (ev_packed) cudaEventDestroy(ev_packed);
   if (ev_arrived) cudaEventDestroy(ev_arrived);
+}
+
+const double *Halo::ghost_now() {
+  if (!p2p) return ghost.p;
+  unsigned long long k = 0;
+  B2_CUDA(cudaMemcpyAsync(&k, seq.p, sizeof(k), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  return ghost.p + ((k - 1ull) & 1ull) * ghost_stride;
+}
+
+// Peer-to-peer setup: every rank publishes {IPC handle of its ghost buffer, IPC handle of its flag words, stride, and
+// for each incoming message the sender rank and the receive offset}; neighbours open the handles and remember where
+// to write.  The records travel through the communicator's all-gather (512 bytes per rank), no host side channel.
+static void setup_p2p(Halo &h, const Layout &L, int rank) {
+  Ctx *c = h.ctx;
+  constexpr int REC = 64; // doubles per record
+  struct Rec { cudaIpcMemHandle_t hg, hf; long long stride; int nmsg; int peer[8]; int recv_off[8]; };
+  static_assert(sizeof(Rec) <= REC * sizeof(double), "record too large");
+  h.n_msgs = (int)h.node_msgs.size();
+  B2_REQUIRE(h.n_msgs <= 8, "halo: more than 8 neighbours");
+  h.ghost_stride = ((int64_t)h.n_ghost * 2 + 2 + 15) & ~15LL;
+  h.ghost.alloc((size_t)h.ghost_stride * 2);
+  h.ghost.zero(c->stream);
+  h.seq.alloc(1); h.seq.zero(c->stream);
+  h.flags.alloc(8); h.flags.zero(c->stream);
+  h.ticket.alloc(1); h.ticket.zero(c->stream);
+  Rec mine;
+  std::memset(&mine, 0, sizeof(mine));
+  B2_CUDA(cudaIpcGetMemHandle(&mine.hg, h.ghost.p));
+  B2_CUDA(cudaIpcGetMemHandle(&mine.hf, h.flags.p));
+  mine.stride = h.ghost_stride;
+  mine.nmsg = h.n_msgs;
+  for (int m = 0; m < h.n_msgs; ++m) { mine.peer[m] = h.node_msgs[(size_t)m].peer; mine.recv_off[m] = (int)h.node_msgs[(size_t)m].recv_off; }
+  DevBuf<double> d_in(REC), d_all((size_t)REC * L.size);
+  std::vector<double> h_in(REC, 0.0), h_all((size_t)REC * L.size);
+  std::memcpy(h_in.data(), &mine, sizeof(mine));
+  B2_CUDA(cudaMemcpyAsync(d_in.p, h_in.data(), sizeof(double) * REC, cudaMemcpyHostToDevice, c->stream));
+  c->dcomm->allgather(d_in.p, d_all.p, REC, c->stream);
+  B2_CUDA(cudaMemcpyAsync(h_all.data(), d_all.p, sizeof(double) * h_all.size(), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  std::vector<Halo::P2PMsg> pm((size_t)h.n_msgs);
+  for (int m = 0; m < h.n_msgs; ++m) {
+    const HaloMsg &hm = h.node_msgs[(size_t)m];
+    Rec pr;
+    std::memcpy(&pr, h_all.data() + (size_t)REC * hm.peer, sizeof(pr));
+    void *pg = nullptr, *pf = nullptr;
+    B2_CUDA(cudaIpcOpenMemHandle(&pg, pr.hg, cudaIpcMemLazyEnablePeerAccess));
+    B2_CUDA(cudaIpcOpenMemHandle(&pf, pr.hf, cudaIpcMemLazyEnablePeerAccess));
+    h.ipc_opened.push_back(pg);
+    h.ipc_opened.push_back(pf);
+    int slot = -1;
+    for (int j = 0; j < pr.nmsg; ++j) if (pr.peer[j] == rank) slot = j;
+    B2_REQUIRE(slot >= 0, "halo p2p: neighbour has no message slot for this rank");
+    Halo::P2PMsg &q = pm[(size_t)m];
+    q.peer_ghost = (double *)pg;
+    q.peer_flag = (unsigned long long *)pf + slot;
+    q.peer_stride = pr.stride;
+    q.send_off = (int)hm.send_off;
+    q.send_cnt = (int)hm.send_cnt;
+    q.peer_recv_off = pr.recv_off[slot];
+    q.pad = 0;
+  }
+  h.d_p2p.alloc((size_t)h.n_msgs + 1);
+  if (h.n_msgs) B2_CUDA(cudaMemcpyAsync(h.d_p2p.p, pm.data(), sizeof(Halo::P2PMsg) * pm.size(), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  h.p2p = true;
 }
 
 std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
@@ -226,6 +335,10 @@ std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming));
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
   c->sync();
+  // every message must carry data in both directions for the flag protocol (true for a box-stencil ring)
+  bool symmetric = true;
+  for (const HaloMsg &m : h->node_msgs) symmetric = symmetric && m.send_cnt > 0 && m.recv_cnt > 0;
+  if (c->dcomm && c->dcomm->p2p_capable() && L.size > 1 && symmetric) setup_p2p(*h, L, rank);
   return h;
 }
 
@@ -233,6 +346,15 @@ void Halo::begin(const double *x, int dof) {
   B2_REQUIRE(dof == 1 || dof == 2, "halo: dof must be 1 or 2");
   Ctx *c = ctx;
   if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
+  if (p2p) { // push over NVLink + flag; the matching wait is in end()
+    LaunchScope ls(c, "halo:p2p_push");
+    int grid = (n_send * dof + 255) / 256;
+    if (grid > 64) grid = 64;
+    if (grid < 1) grid = 1;
+    k_halo_push<<<grid, 256, 0, c->stream>>>(n_send, dof, n_msgs, d_send_lnode.p, x, d_p2p.p, seq.p, ticket.p);
+    check_launch("k_halo_push");
+    return;
+  }
   if (n_send) {
     LaunchScope ls(c, "halo");
     int grid = (n_send * dof + 255) / 256;
@@ -263,6 +385,12 @@ void Halo::begin(const double *x, int dof) {
 void Halo::end() {
   Ctx *c = ctx;
   if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
+  if (p2p) {
+    LaunchScope ls(c, "halo:p2p_wait");
+    k_halo_wait<<<1, 32, 0, c->stream>>>(n_msgs, seq.p, flags.p, c->d_err);
+    check_launch("k_halo_wait");
+    return;
+  }
   B2_CUDA(cudaStreamWaitEvent(c->stream, ev_arrived, 0));
 }
 

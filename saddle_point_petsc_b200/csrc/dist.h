@@ -28,6 +28,9 @@ struct Comm {
   virtual void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) = 0;
   virtual void barrier() = 0;
   virtual bool capturable() const = 0; // may its calls be recorded into a CUDA graph (no host-side waits)?
+  // one process per GPU on distinct GPUs: halos may be pushed straight into the neighbours' memory over NVLink
+  // (CUDA IPC peer mappings + device-side flags) instead of going through send/recv
+  virtual bool p2p_capable() const = 0;
 };
 
 struct LocalGroup { // shared by the rank-threads of one process
@@ -74,8 +77,22 @@ struct Halo {
   DevBuf<int> d_send_lnode;                       // owned local node ids to pack, grouped by neighbour
   int n_send = 0;
   DevBuf<int> d_ring2ghost;                       // ring position -> ghost index (-1 outside the domain)
-  DevBuf<double> sendbuf, ghost;                  // sized for dof <= 2
+  DevBuf<double> sendbuf, ghost;                  // sized for dof <= 2 (ghost holds two parities in peer-to-peer mode)
   cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
+  // ---- peer-to-peer mode (NVLink): the "pack" kernel stores every outgoing value DIRECTLY into the neighbour's ghost
+  // buffer (CUDA IPC mapping) and then raises a sequence flag in the neighbour's memory; the receiver polls its own
+  // flags in a one-warp kernel before the SpMV.  Ghost buffers are double-buffered by exchange parity: a sender can
+  // reach exchange k+2 only after the receiver's push of exchange k+1, which is stream-ordered after the receiver's
+  // SpMV of exchange k, so parity k is free again.  No NCCL call, no second stream, ~2 tiny kernels per exchange.
+  bool p2p = false;
+  int64_t ghost_stride = 0;                       // doubles per parity
+  DevBuf<unsigned long long> seq, flags;          // exchanges started (device counter); one flag per incoming message
+  DevBuf<unsigned> ticket;
+  struct P2PMsg { double *peer_ghost; unsigned long long *peer_flag; long long peer_stride; int send_off, send_cnt, peer_recv_off, pad; };
+  DevBuf<P2PMsg> d_p2p;                           // per outgoing message
+  std::vector<void *> ipc_opened;
+  int n_msgs = 0;
+  const double *ghost_now();                      // host: synchronise and return the parity that holds the latest halo
   ~Halo();
   // pack x (dof interleaved) and start the exchange on the halo stream; end() makes the compute stream wait for it
   void begin(const double *x, int dof);

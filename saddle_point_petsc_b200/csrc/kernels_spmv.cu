@@ -201,6 +201,7 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) 
     A.halo->end();
     xs.ghost = A.halo->ghost.p;
     xs.n_owned = A.ncols;
+    if (A.halo->p2p) { xs.seq = A.halo->seq.p; xs.ghost_stride = A.halo->ghost_stride; }
     if (split) {
       if (A.n_tiles_boundary > 0) {
         LaunchScope ls(c, A.tag.c_str());
@@ -291,7 +292,7 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
       { LaunchScope ls(c, "setup"); k_flag_to_double<<<(A.ncols + 255) / 256, 256, 0, c->stream>>>(A.ncols, colflag.p, fl.p); }
       A.halo->begin(fl.p, A.halo_dof);
       A.halo->end();
-      ghostflag = A.halo->ghost.p;
+      ghostflag = A.halo->ghost_now();
     }
   }
   {

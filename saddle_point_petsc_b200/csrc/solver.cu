@@ -18,6 +18,7 @@ void Ctx::fetch_scalars(const double *d, int k, double *host) {
   B2_REQUIRE(k <= N_SCALARS, "fetch_scalars: too many scalars");
   B2_CUDA(cudaMemcpyAsync(h_scalars, d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, stream));
   B2_CUDA(cudaStreamSynchronize(stream));
+  if (h_err && *h_err) throw Error(B200SP_ERR_NCCL, "peer-to-peer halo exchange timed out waiting for a neighbour (code " + std::to_string(*h_err) + ")");
   std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
 }
 static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
