@@ -187,9 +187,13 @@ __global__ void __launch_bounds__(256) k_halo_push(int n_send, int dof, int nmsg
     const Halo::P2PMsg &g = msgs[m];
     g.peer_ghost[par * g.peer_stride + (long long)(g.peer_recv_off + node - g.send_off) * dof + c] = x[(size_t)lnode[node] * dof + c];
   }
-  __threadfence_system();
+  // one system-scope fence per block (fences are cumulative: the barrier orders the block's stores before thread 0's
+  // fence), not one per thread -- per-thread fences made this kernel ~16 us
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
@@ -348,8 +352,8 @@ void Halo::begin(const double *x, int dof) {
   if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
   if (p2p) { // push over NVLink + flag; the matching wait is in end()
     LaunchScope ls(c, "halo:p2p_push");
-    int grid = (n_send * dof + 255) / 256;
-    if (grid > 64) grid = 64;
+    int grid = (n_send * dof + 1023) / 1024; // a few elements per thread: fewer blocks, fewer fences and tickets
+    if (grid > 16) grid = 16;
     if (grid < 1) grid = 1;
     k_halo_push<<<grid, 256, 0, c->stream>>>(n_send, dof, n_msgs, d_send_lnode.p, x, d_p2p.p, seq.p, ticket.p);
     check_launch("k_halo_push");
