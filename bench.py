@@ -271,8 +271,15 @@ def main():
     # profiled solve next to the sum of its device classes so launch gaps / exposed communication are visible
     prof_total_ms = sum(v["ms"] for v in prof.values())
     total_prof = sum(v["ms"] for v in prof.values())
-    roofline = {"kernel": "k_spmv_stream on the A block (%d x %d, %d nnz)" % (rA, cA, nnzA), "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": pk, "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk, 4), "traffic": None,
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this matrix, from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")))
+        if tr["nx"] == args.nx and tr["n_gpus"] == world:
+            traffic = tr["traffic"]
+    except Exception:
+        pass
+    roofline = {"kernel": "k_spmv_tma on the A block (%d x %d, %d nnz per GPU)" % (rA, cA, nnzA), "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": pk, "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk, 4), "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_A, "avg_launch_ms": round(avg_ms, 5), "launches_per_solve": pa["launches"],
                 "share_of_solve_device_time": round(pa["ms"] / total_prof, 4) if total_prof else None}
     classes = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
