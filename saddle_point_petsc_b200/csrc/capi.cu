@@ -27,6 +27,7 @@ static thread_local std::string g_last_error;
 
 namespace b200sp {
 Ctx::~Ctx() {
+  delete reducer;
   delete dcomm;
   if (comm) nccl().CommDestroy(comm);
   if (d_partials) cudaFree(d_partials);
@@ -113,6 +114,7 @@ int b200sp_ctx_create(int device, int rank, int size, const char nccl_id[128], b
       if (!nccl().ok) throw Error(B200SP_ERR_NCCL, "NCCL unavailable: " + nccl().err);
       B2_NCCL(nccl().CommInitRank(&c.comm, size, u, rank));
       c.dcomm = make_nccl_comm(c.comm, rank, size);
+      c.reducer = make_collective(&c, 32);
     }
   } catch (...) { delete h; throw; }
   *out = h;
@@ -137,7 +139,7 @@ int b200sp_ctx_create_local(b200sp_group group, int rank, int device, b200sp_ctx
   if (rc) throw Error(rc, g_last_error);
   ctx->c.rank = rank;
   ctx->c.size = group->g->size;
-  if (group->g->size > 1) ctx->c.dcomm = make_local_comm(group->g, rank, device);
+  if (group->g->size > 1) { ctx->c.dcomm = make_local_comm(group->g, rank, device); ctx->c.reducer = make_collective(&ctx->c, 32); }
   *out = ctx;
   API_END
 }
@@ -333,7 +335,7 @@ int b200sp_vec_pointwise_mult(b200sp_vec w, b200sp_vec x, b200sp_vec y) {
   API_BEGIN SAME_SIZE(x, y); SAME_SIZE(x, w); vec_pointwise_mult(w->v.ctx, w->v.n, x->v.d, y->v.d, w->v.d); API_END
 }
 static void global_sum(Ctx *c, int k, double *host) {
-  if (c->dcomm) c->dcomm->allreduce_sum(c->d_scalars, k, c->stream);
+  if (c->reducer) c->reducer->allreduce_sum(c->d_scalars, k, c->stream);
   c->fetch_scalars(c->d_scalars, k, host);
 }
 int b200sp_vec_dot(b200sp_vec x, b200sp_vec y, double *result) {

@@ -48,6 +48,7 @@ struct Ctx {
   cudaStream_t stream2 = nullptr; // halo / copy stream
   ncclComm_t comm = nullptr;
   struct Comm *dcomm = nullptr;   // set when size > 1 (NCCL or in-process thread group), see dist.h
+  struct Collective *reducer = nullptr; // Krylov reductions (peer-to-peer kernel when the communicator allows it)
   int num_sms = 148;
   double *d_partials = nullptr; // [RED_MAX_BLOCKS][RED_MAX_OUT]
   unsigned *d_ticket = nullptr;
@@ -222,6 +223,11 @@ struct XSrc {
   int n_owned;
   const unsigned long long *seq = nullptr; // peer-to-peer halos: exchanges started so far; the latest one is in parity (seq-1)&1
   long long ghost_stride = 0;
+  // when set, the kernel itself waits for the neighbours' pushes (one lane per incoming message polls this rank's
+  // flag words) before its first ghost read, instead of a separate wait kernel
+  const unsigned long long *wait_flags = nullptr;
+  int wait_nmsg = 0;
+  int *wait_err = nullptr;
 #ifdef __CUDACC__
   __device__ __forceinline__ double load(int c) const {
     if (c < n_owned) return __ldg(x + c);
@@ -255,8 +261,9 @@ struct SpmvEpi {
   }
 #endif
 };
-void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0);
-void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi);
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0, bool reuse_halo = false);
+// reuse_halo: the ghost values of this x are already in the halo buffer (previous SpMV with the same x and halo)
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, bool reuse_halo = false);
 void csr_get_diagonal(const Csr &A, double *d);
 void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool do_rows, bool do_cols, bool set_diag);
 

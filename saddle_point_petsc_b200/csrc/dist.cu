@@ -111,6 +111,158 @@ struct NcclComm : Comm {
 Comm *make_local_comm(std::shared_ptr<LocalGroup> g, int rank, int device) { return new LocalComm(g, rank, device); }
 Comm *make_nccl_comm(ncclComm_t c, int rank, int size) { return new NcclComm(c, rank, size); }
 
+// ------------------------------------------------------------------ peer-to-peer small collectives
+namespace {
+struct SymPeer { double *rb; unsigned long long *flags; };
+
+// all-reduce of k <= 32 doubles in ONE single-block kernel: push my values into every rank's receive slot (parity of
+// this call), fence, raise my flag on every rank, poll my own flags, sum the slots in rank order.
+__global__ void __launch_bounds__(256) k_sym_allreduce(double *d, int k, int size, int rank, int64_t cap, const SymPeer *__restrict__ peers,
+                                                       double *rb, unsigned long long *flags, unsigned long long *seq, int *err) {
+  __shared__ unsigned long long s_k;
+  if (threadIdx.x == 0) s_k = *seq;
+  __syncthreads();
+  const unsigned long long kk = s_k, par = kk & 1ull;
+  for (int t = threadIdx.x; t < size * k; t += blockDim.x) {
+    const int q = t / k, j = t % k;
+    peers[q].rb[((int64_t)par * size + rank) * cap + j] = d[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < size) {
+    volatile unsigned long long *f = peers[threadIdx.x].flags + rank;
+    *f = kk + 1ull;
+    volatile const unsigned long long *mine = flags + threadIdx.x;
+    for (long long spin = 0; *mine < kk + 1ull; ++spin) {
+      __nanosleep(100);
+      if (spin > 20000000LL) { *err = 200 + (int)threadIdx.x; __threadfence_system(); break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < k) {
+    double sum = 0.0;
+    for (int r = 0; r < size; ++r) sum += ((volatile double *)rb)[((int64_t)par * size + r) * cap + threadIdx.x];
+    d[threadIdx.x] = sum;
+  }
+  if (threadIdx.x == 0) *seq = kk + 1ull;
+}
+__global__ void __launch_bounds__(256) k_sym_gather_push(const double *__restrict__ in, int64_t cnt, int size, int rank, int64_t cap,
+                                                         const SymPeer *__restrict__ peers, unsigned long long *seq, unsigned *ticket) {
+  __shared__ bool s_last;
+  const unsigned long long kk = *seq, par = kk & 1ull;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)size * cnt; t += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t / cnt);
+    const int64_t i = t % cnt;
+    peers[q].rb[((int64_t)par * size + rank) * cap + i] = in[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(ticket, 1u) == gridDim.x - 1; }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < size) { volatile unsigned long long *f = peers[threadIdx.x].flags + rank; *f = kk + 1ull; }
+  if (threadIdx.x == 0) { *ticket = 0u; *seq = kk + 1ull; }
+}
+__global__ void __launch_bounds__(256) k_sym_gather_wait_copy(double *out, int64_t cnt, int size, int64_t cap, const double *rb,
+                                                              const unsigned long long *flags, const unsigned long long *seq, int *err) {
+  const unsigned long long want = *seq, par = (want - 1ull) & 1ull;
+  if ((int)threadIdx.x < size) {
+    volatile const unsigned long long *f = flags + threadIdx.x;
+    for (long long spin = 0; *f < want; ++spin) {
+      __nanosleep(100);
+      if (spin > 20000000LL) { *err = 300 + (int)threadIdx.x; __threadfence_system(); break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)size * cnt; t += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t / cnt);
+    const int64_t i = t % cnt;
+    out[t] = ((volatile const double *)rb)[((int64_t)par * size + q) * cap + i];
+  }
+}
+
+struct FallbackCollective : Collective {
+  Ctx *c;
+  explicit FallbackCollective(Ctx *ctx) : c(ctx) {}
+  void allreduce_sum(double *d, int k, cudaStream_t s) override { c->dcomm->allreduce_sum(d, k, s); }
+  void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) override { c->dcomm->allgather(in, out, cnt, s); }
+};
+
+struct SymCollective : Collective {
+  Ctx *c;
+  int size, rank;
+  int64_t cap;
+  DevBuf<double> rb;
+  DevBuf<unsigned long long> flags, seq;
+  DevBuf<unsigned> ticket;
+  DevBuf<SymPeer> peers;
+  std::vector<void *> opened;
+  SymCollective(Ctx *ctx, int64_t cap_) : c(ctx), size(ctx->size), rank(ctx->rank), cap((cap_ + 15) & ~15LL) {
+    B2_REQUIRE(size <= 64, "p2p collective: at most 64 ranks");
+    rb.alloc((size_t)2 * size * cap);
+    rb.zero(c->stream);
+    flags.alloc((size_t)size); flags.zero(c->stream);
+    seq.alloc(1); seq.zero(c->stream);
+    ticket.alloc(1); ticket.zero(c->stream);
+    struct Rec { cudaIpcMemHandle_t hb, hf; };
+    constexpr int REC = 16; // doubles
+    static_assert(sizeof(Rec) <= REC * sizeof(double), "record too large");
+    Rec mine;
+    B2_CUDA(cudaIpcGetMemHandle(&mine.hb, rb.p));
+    B2_CUDA(cudaIpcGetMemHandle(&mine.hf, flags.p));
+    DevBuf<double> d_in(REC), d_all((size_t)REC * size);
+    std::vector<double> h_in(REC, 0.0), h_all((size_t)REC * size);
+    std::memcpy(h_in.data(), &mine, sizeof(mine));
+    B2_CUDA(cudaMemcpyAsync(d_in.p, h_in.data(), sizeof(double) * REC, cudaMemcpyHostToDevice, c->stream));
+    c->dcomm->allgather(d_in.p, d_all.p, REC, c->stream);
+    B2_CUDA(cudaMemcpyAsync(h_all.data(), d_all.p, sizeof(double) * h_all.size(), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    std::vector<SymPeer> pp((size_t)size);
+    for (int q = 0; q < size; ++q) {
+      if (q == rank) { pp[(size_t)q] = SymPeer{rb.p, flags.p}; continue; }
+      Rec pr;
+      std::memcpy(&pr, h_all.data() + (size_t)REC * q, sizeof(pr));
+      void *pb = nullptr, *pf = nullptr;
+      B2_CUDA(cudaIpcOpenMemHandle(&pb, pr.hb, cudaIpcMemLazyEnablePeerAccess));
+      B2_CUDA(cudaIpcOpenMemHandle(&pf, pr.hf, cudaIpcMemLazyEnablePeerAccess));
+      opened.push_back(pb); opened.push_back(pf);
+      pp[(size_t)q] = SymPeer{(double *)pb, (unsigned long long *)pf};
+    }
+    peers.alloc((size_t)size);
+    B2_CUDA(cudaMemcpyAsync(peers.p, pp.data(), sizeof(SymPeer) * pp.size(), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+  }
+  ~SymCollective() override { for (void *p : opened) cudaIpcCloseMemHandle(p); }
+  void allreduce_sum(double *d, int k, cudaStream_t s) override {
+    for (int j0 = 0; j0 < k; j0 += 32) { // 32 values per kernel
+      const int kk = k - j0 < 32 ? k - j0 : 32;
+      c->launches++;
+      k_sym_allreduce<<<1, 256, 0, s>>>(d + j0, kk, size, rank, cap, peers.p, rb.p, flags.p, seq.p, c->d_err);
+      check_launch("k_sym_allreduce");
+    }
+  }
+  void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) override {
+    B2_REQUIRE(cnt <= cap, "p2p allgather: message larger than the registered capacity");
+    int grid = (int)std::min<int64_t>(32, ((int64_t)size * cnt + 2047) / 2048);
+    if (grid < 1) grid = 1;
+    c->launches += 2;
+    k_sym_gather_push<<<grid, 256, 0, s>>>(in, cnt, size, rank, cap, peers.p, seq.p, ticket.p);
+    check_launch("k_sym_gather_push");
+    k_sym_gather_wait_copy<<<grid, 256, 0, s>>>(out, cnt, size, cap, rb.p, flags.p, seq.p, c->d_err);
+    check_launch("k_sym_gather_wait_copy");
+  }
+};
+} // namespace
+
+Collective *make_collective(Ctx *c, int64_t capacity_doubles) {
+  B2_REQUIRE(c->dcomm, "make_collective: context has no communicator");
+  if (c->dcomm->p2p_capable()) return new SymCollective(c, capacity_doubles < 32 ? 32 : capacity_doubles);
+  return new FallbackCollective(c);
+}
+
 // ------------------------------------------------------------------ Layout
 Layout::Layout(int M_, int N_, int size_) : M(M_), N(N_), size(size_) {
   B2_REQUIRE(M >= 2 && N >= 2 && size >= 1, "dmda: need M,N >= 2 and size >= 1");

@@ -33,6 +33,16 @@ struct Comm {
   virtual bool p2p_capable() const = 0;
 };
 
+// small-message collectives at a fixed use site (the Krylov reductions; the multigrid coarse-level bridge).  With a
+// peer-to-peer capable communicator they are single kernels over CUDA-IPC mapped buffers (push to every peer, raise a
+// flag, poll own flags, combine in RANK ORDER -> deterministic); otherwise they forward to the communicator.
+struct Collective {
+  virtual ~Collective() {}
+  virtual void allreduce_sum(double *d, int k, cudaStream_t s) = 0;                              // k <= 32
+  virtual void allgather(const double *in, double *out, int64_t cnt, cudaStream_t s) = 0;       // cnt <= capacity
+};
+Collective *make_collective(Ctx *c, int64_t capacity_doubles);
+
 struct LocalGroup { // shared by the rank-threads of one process
   int size;
   std::mutex mu;

@@ -182,13 +182,26 @@ void Csr::plan() {
   lanes_per_row = mean <= 2 ? 2 : mean <= 4 ? 4 : mean <= 8 ? 8 : mean <= 16 ? 16 : 32;
 }
 
-void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) {
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, bool reuse_halo) {
   Ctx *c = A.ctx;
   XSrc xs{x, nullptr, 0x7fffffff};
-  if (A.halo && c->dcomm) {
+  bool pending_wait = false;
+  if (A.halo && c->dcomm && A.halo->p2p) {
+    // peer-to-peer halo: push (unless the ghosts of this x are already there); the TMA kernel waits for the
+    // neighbours itself, other kernels get the separate wait kernel
+    if (!reuse_halo) A.halo->begin(x, A.halo_dof);
+    xs.ghost = A.halo->ghost.p;
+    xs.n_owned = A.ncols;
+    xs.seq = A.halo->seq.p;
+    xs.ghost_stride = A.halo->ghost_stride;
+    if (!reuse_halo) {
+      if (A.kernel == SPMV_TMA) { xs.wait_flags = A.halo->flags.p; xs.wait_nmsg = A.halo->n_msgs; xs.wait_err = c->d_err; pending_wait = true; }
+      else A.halo->end();
+    }
+  } else if (A.halo && c->dcomm) {
     // MatMult_MPIAIJ.  The ghost values of x travel on the halo stream while the tiles that have no ghost column
     // (the interior: ~90% of the rows) are multiplied; the boundary tiles follow once the halo has arrived.
-    A.halo->begin(x, A.halo_dof);
+    if (!reuse_halo) A.halo->begin(x, A.halo_dof);
     // Measured (profiles/r01_scaling_notes.md): with the persistent TMA grid holding every SM the NCCL kernel cannot
     // start until the interior kernel drains, so the two-launch split was slightly SLOWER (20.3 vs 19.9 ms at 8 GPUs).
     // It stays available behind B200SP_SPMV_OVERLAP=1; the default is one kernel after the halo has arrived.
@@ -213,6 +226,7 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) 
   if (A.nrows <= 0) return;
   LaunchScope ls(c, A.tag.c_str());
   if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return;
+  if (pending_wait) { A.halo->end(); xs.wait_flags = nullptr; } // the TMA kernel declined: wait with the separate kernel
   if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;
@@ -252,10 +266,10 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi) 
   }
 }
 
-void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z) {
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z, bool reuse_halo) {
   SpmvEpi e;
   e.alpha = alpha; e.z = z; e.beta_z = beta_z;
-  csr_spmv_epi(A, x, y, e);
+  csr_spmv_epi(A, x, y, e, reuse_halo);
 }
 
 void csr_get_diagonal(const Csr &A, double *d) {

@@ -77,6 +77,18 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
       if (t < ntiles) issue(t, s);
     }
   }
+  if (xs.wait_flags) { // peer-to-peer halo: the first tiles are already in flight while we wait for the neighbours
+    if (tid < xs.wait_nmsg) {
+      const unsigned long long want = *xs.seq;
+      volatile const unsigned long long *f = xs.wait_flags + tid;
+      for (long long spin = 0; *f < want; ++spin) {
+        __nanosleep(100);
+        if (spin > 20000000LL) { *xs.wait_err = 400 + tid; __threadfence_system(); break; }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
     const int tile = tile_list ? tile_list[idx] : idx;

@@ -25,7 +25,7 @@ static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equi
   if (!c->dcomm) return;
   if (c->profile) {
     cudaEventRecord(c->pev0, c->stream);
-    c->dcomm->allreduce_sum(d, k, c->stream);
+    c->reducer->allreduce_sum(d, k, c->stream);
     cudaEventRecord(c->pev1, c->stream);
     cudaEventSynchronize(c->pev1);
     float ms = 0;
@@ -34,7 +34,7 @@ static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equi
     pe.ms += ms; pe.n++;
     return;
   }
-  c->dcomm->allreduce_sum(d, k, c->stream);
+  c->reducer->allreduce_sum(d, k, c->stream);
 }
 
 // ------------------------------------------------------------------ operators
@@ -44,19 +44,24 @@ std::string CsrOp::view(int indent) const {
   return o.str();
 }
 
+// Row-partitioned runs: A00 and A10 read the same x0, A01 and A11 the same x1, and all four blocks share the node
+// halo, so each sub-vector is exchanged once (the second block of each pair reuses the ghosts).  The per-row
+// summation order (A00 x0 first, then += A01 x1; A10 x0 first, then += A11 x1) is unchanged.
 void NestOp::apply(const double *x, double *y) {
   const int64_t n0c = b00->ncols, n0r = b00->nrows;
+  const bool share = b00->halo && b00->halo == b10->halo && b00->halo_dof == b10->halo_dof && (!b11 || (b01->halo == b11->halo && b01->halo_dof == b11->halo_dof));
   csr_spmv(*b00, x, y);
+  csr_spmv(*b10, x, y + n0r, 1.0, nullptr, 0.0, share);
   csr_spmv(*b01, x + n0c, y, 1.0, y, 1.0);
-  csr_spmv(*b10, x, y + n0r);
-  if (b11) csr_spmv(*b11, x + n0c, y + n0r, 1.0, y + n0r, 1.0);
+  if (b11) csr_spmv(*b11, x + n0c, y + n0r, 1.0, y + n0r, 1.0, share);
 }
 void NestOp::residual(const double *b, const double *x, double *r) {
   const int64_t n0c = b00->ncols, n0r = b00->nrows;
+  const bool share = b00->halo && b00->halo == b10->halo && b00->halo_dof == b10->halo_dof && (!b11 || (b01->halo == b11->halo && b01->halo_dof == b11->halo_dof));
   csr_spmv(*b00, x, r, -1.0, b, 1.0);
+  csr_spmv(*b10, x, r + n0r, -1.0, b + n0r, 1.0, share);
   csr_spmv(*b01, x + n0c, r, -1.0, r, 1.0);
-  csr_spmv(*b10, x, r + n0r, -1.0, b + n0r, 1.0);
-  if (b11) csr_spmv(*b11, x + n0c, r + n0r, -1.0, r + n0r, 1.0);
+  if (b11) csr_spmv(*b11, x + n0c, r + n0r, -1.0, r + n0r, 1.0, share);
 }
 std::string NestOp::view(int indent) const {
   std::ostringstream o;
@@ -186,7 +191,7 @@ void MgOp::cycle(int l, const double *b, double *x) {
     // the natural numbering, run the remaining levels redundantly on every rank, take my part back, interpolate
     csr_spmv(*L.R, L.r.p, loc_b.p);
     if (ctx->profile) cudaEventRecord(ctx->pev0, ctx->stream);
-    ctx->dcomm->allgather(loc_b.p, g_all.p, bridge_cnt, ctx->stream);
+    bridge->allgather(loc_b.p, g_all.p, bridge_cnt, ctx->stream);
     if (ctx->profile) {
       cudaEventRecord(ctx->pev1, ctx->stream);
       cudaEventSynchronize(ctx->pev1);
@@ -791,6 +796,7 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
         }
   }
   mg->bridge_cnt = cnt_max;
+  mg->bridge.reset(make_collective(ctx, cnt_max));
   mg->bridge_nloc = (int)lmap.size();
   mg->gather_map.alloc(gmap.size() + 1);
   mg->local_map.alloc(lmap.size() + 1);

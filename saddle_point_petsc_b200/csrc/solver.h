@@ -3,6 +3,7 @@
 // (src/SaddlePointProblem.c:65-72); all arithmetic is in the CUDA kernels they launch.
 #pragma once
 #include "core.h"
+#include "dist.h"
 
 namespace b200sp {
 
@@ -118,6 +119,7 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   DevBuf<double> loc_b, loc_x, g_all, nat_b, nat_x;
   DevBuf<int> gather_map, local_map;
   int bridge_cnt = 0, bridge_nloc = 0;
+  std::unique_ptr<struct Collective> bridge; // all-gather of the restricted residual (peer-to-peer when possible)
   MgOp(Ctx *c, int64_t n) : Op(c, n, n) {}
   bool capturable() const override;
   void cycle(int l, const double *b, double *x);
