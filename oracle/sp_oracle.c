@@ -689,6 +689,24 @@ OrOp *or_op_lsc(const OrCsr *A00, const OrCsr *A01, const OrCsr *A10, OrOp *Linv
   return op_new(n1, n1, lsc_apply, lsc_destroy, c);
 }
 
+/* fieldsplit on a monolithic, field-interleaved vector: gather the splits (VecScatter), apply, scatter back */
+typedef struct { OrOp *inner; int n; int *map; double *xs, *ys; } PermCtx;
+static void perm_apply(OrOp *o, const double *x, double *y) {
+  PermCtx *c = (PermCtx *)o->ctx;
+  for (int i = 0; i < c->n; ++i) c->xs[i] = x[c->map[i]];
+  or_op_apply(c->inner, c->xs, c->ys);
+  for (int i = 0; i < c->n; ++i) y[c->map[i]] = c->ys[i];
+}
+static void perm_destroy(OrOp *o) { PermCtx *c = (PermCtx *)o->ctx; free(c->map); free(c->xs); free(c->ys); free(c); }
+OrOp *or_op_permuted(OrOp *inner, int n, const int *map) {
+  PermCtx *c = (PermCtx *)xmalloc(sizeof(PermCtx));
+  c->inner = inner; c->n = n;
+  c->map = (int *)xmalloc(sizeof(int) * (size_t)n);
+  memcpy(c->map, map, sizeof(int) * (size_t)n);
+  c->xs = (double *)xmalloc(sizeof(double) * (size_t)n); c->ys = (double *)xmalloc(sizeof(double) * (size_t)n);
+  return op_new(n, n, perm_apply, perm_destroy, c);
+}
+
 /* dense LU with partial pivoting (PCLU stand-in for the coarsest multigrid level) */
 typedef struct { int n; double *lu; int *piv; } LuCtx;
 static void lu_apply(OrOp *o, const double *b, double *x) {

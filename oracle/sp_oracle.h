@@ -92,6 +92,7 @@ OrOp *or_op_schur(const OrCsr *A11 /* may be NULL */, const OrCsr *A10, OrOp *K0
 OrOp *or_op_fieldsplit(int fact, const OrCsr *A01, const OrCsr *A10, OrOp *K0, OrOp *KS, double scale);
 /* PCLSC: y = Linv (A10 A00 A01) Linv x   [scale_diag: A10 D^-1 A00 D^-1 A01 with D=diag(A00)] */
 OrOp *or_op_lsc(const OrCsr *A00, const OrCsr *A01, const OrCsr *A10, OrOp *Linv, int scale_diag);
+OrOp *or_op_permuted(OrOp *inner, int n, const int *map); /* y[map[i]] = inner(x[map[.]])[i]: strided fieldsplit */
 OrOp *or_op_dense_lu(const OrCsr *A);                    /* exact solve, coarse grid */
 /* PCMG V-cycle: nlev levels, level 0 finest.  A[l] operators, P[l] (l=0..nlev-2) coarse(l+1)->fine(l),
  * pre/post smoothers S[l] (KSP-as-op with nonzero-guess support, see or_ksp_as_smoother), coarse solver. */

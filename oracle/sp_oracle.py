@@ -88,6 +88,7 @@ def lib():
     sig("or_op_schur", vp, CsrP, CsrP, vp, CsrP)
     sig("or_op_fieldsplit", vp, C.c_int, CsrP, CsrP, vp, vp, C.c_double)
     sig("or_op_lsc", vp, CsrP, CsrP, CsrP, vp, C.c_int)
+    sig("or_op_permuted", vp, vp, C.c_int, c_ip)
     sig("or_op_dense_lu", vp, CsrP)
     sig("or_op_mg", vp, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(KspP), vp)
     sig("or_ksp_create", KspP, C.c_int, vp, vp)
@@ -396,7 +397,13 @@ class Solver:
         t = self._get(prefix + "pc_type", "none")
         if t != "fieldsplit":
             return self._make_simple_pc(prefix, prob.A, grid=(prob.M, prob.N), dof=2)
-        assert prob.kkt and self._get("pc_fieldsplit_type", "schur") == "schur"
+        assert self._get("pc_fieldsplit_type", "schur") == "schur"
+        if not prob.kkt:
+            return self._make_strided_fieldsplit(prob)
+        return self._make_pc_split(prob)
+
+    def _make_pc_split(self, prob):
+        L = self.L
         fact = FACT[self._get("pc_fieldsplit_schur_fact_type", "full")]
         pre = self._get("pc_fieldsplit_schur_precondition", "a11")
         scale = float(self._get("pc_fieldsplit_schur_scale", -1.0))
@@ -455,6 +462,30 @@ class Solver:
         fs = L.or_op_fieldsplit(fact, prob.Bt.ptr, prob.B.ptr, K0, KS, scale)
         self.keep.append(fs)
         return fs
+
+    def _make_strided_fieldsplit(self, prob):
+        """PCFIELDSPLIT on the reference's own operator: KSPSetOperators(A,A) with block size 2 and no DM on the KSP
+        -> split 0 = Ux dofs, split 1 = Uy dofs (strided ISs), sub-matrices by MatCreateSubMatrix."""
+        import types
+        bs = int(self._get("pc_fieldsplit_block_size", 2))
+        assert bs == 2
+        A = prob.A.scipy()
+        n = A.shape[0]
+        i0, i1 = np.arange(0, n, 2), np.arange(1, n, 2)
+
+        def sub(r, c):
+            S = A[r][:, c].tocsr()
+            S.sort_indices()
+            return Csr.from_arrays(S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data)
+
+        sp_ = types.SimpleNamespace(A=sub(i0, i0), Bt=sub(i0, i1), B=sub(i1, i0), C=sub(i1, i1), Q=None, M=prob.M, N=prob.N, kkt=True)
+        self.keep.append(sp_)
+        inner = self._make_pc_split(sp_)
+        mp = np.concatenate([i0, i1]).astype(np.int32)
+        self.keep.append(mp)
+        op = self.L.or_op_permuted(inner, n, iptr(mp))
+        self.keep.append(op)
+        return op
 
     def solve(self, b=None, history=True):
         b = self.prob.rhs if b is None else b

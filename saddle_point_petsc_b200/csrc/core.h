@@ -273,6 +273,7 @@ std::shared_ptr<Csr> csr_from_host(Ctx *c, int nrows, int ncols, const int *rowp
 std::shared_ptr<Csr> csr_from_coo_host(Ctx *c, int nrows, int ncols, int64_t ncoo, const int *row, const int *col, const double *val);
 std::shared_ptr<Csr> csr_transpose(const Csr &A);
 std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B);
+std::shared_ptr<Csr> csr_extract_fields(const Csr &A, int bs, const std::vector<int> &split_of_field, int rs, int cs); // MatCreateSubMatrix, strided ISs
 std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d);            // A * diag(d)
 std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double a, const Csr &B);     // A + a B (same pattern required)
 void dense_inverse_from_csr(const Csr &A, double *Ainv); // n x n row-major, device

@@ -507,6 +507,65 @@ std::shared_ptr<Csr> csr_transpose(const Csr &A) {
   return csr_from_coo_device(c, A.ncols, A.nrows, A.nnz, A.col.p, rows.p, A.val.p);
 }
 
+// ---------------------------------------------------------------- MatCreateSubMatrix for strided fields (PCFIELDSPLIT
+// on a monolithic matrix with block size bs: the reference's case, KSPSetOperators(A,A) with the DMDA's bs = 2)
+namespace {
+struct FieldMap { int bs; int split[8]; int pos[8]; int nf[2]; };
+__global__ void __launch_bounds__(256) k_extract_count(int nrows_src, FieldMap fm, int rs, int cs, const int *__restrict__ rowptr, const int *__restrict__ col, int *cnt) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows_src; r += gridDim.x * blockDim.x) {
+    const int f = r % fm.bs;
+    if (fm.split[f] != rs) continue;
+    int n = 0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) n += fm.split[col[k] % fm.bs] == cs;
+    cnt[(r / fm.bs) * fm.nf[rs] + fm.pos[f]] = n;
+  }
+}
+__global__ void __launch_bounds__(256) k_extract_fill(int nrows_src, FieldMap fm, int rs, int cs, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                      const double *__restrict__ val, const int *__restrict__ rp, int *cj, double *va) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows_src; r += gridDim.x * blockDim.x) {
+    const int f = r % fm.bs;
+    if (fm.split[f] != rs) continue;
+    int p = rp[(r / fm.bs) * fm.nf[rs] + fm.pos[f]];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int c = col[k], fc = c % fm.bs;
+      if (fm.split[fc] != cs) continue;
+      cj[p] = (c / fm.bs) * fm.nf[cs] + fm.pos[fc];
+      va[p++] = val[k];
+    }
+  }
+}
+} // namespace
+
+// fields_of_split1: the fields (ascending) that form split 1; every other field goes to split 0
+std::shared_ptr<Csr> csr_extract_fields(const Csr &A, int bs, const std::vector<int> &split_of_field, int rs, int cs) {
+  Ctx *c = A.ctx;
+  B2_REQUIRE(bs >= 2 && bs <= 8 && A.nrows % bs == 0 && A.ncols % bs == 0 && (int)split_of_field.size() == bs, "extract_fields: bad block size");
+  B2_REQUIRE(!A.halo, "extract_fields: row-partitioned matrices are not supported");
+  FieldMap fm;
+  fm.bs = bs; fm.nf[0] = fm.nf[1] = 0;
+  for (int f = 0; f < bs; ++f) { fm.split[f] = split_of_field[(size_t)f]; fm.pos[f] = fm.nf[fm.split[f]]++; }
+  B2_REQUIRE(fm.nf[0] > 0 && fm.nf[1] > 0, "extract_fields: both splits need at least one field");
+  const int nr = A.nrows / bs * fm.nf[rs], nc = A.ncols / bs * fm.nf[cs];
+  DevBuf<int> cnt((size_t)nr + 1), rp((size_t)nr + 1);
+  {
+    LaunchScope ls(c, "setup");
+    k_extract_count<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, fm, rs, cs, A.rowptr.p, A.col.p, cnt.p);
+    check_launch("k_extract_count");
+  }
+  int nnz = 0;
+  exclusive_scan_i32(c, cnt.p, rp.p, nr, &nnz);
+  auto S = csr_alloc(c, nr, nc, nnz);
+  B2_CUDA(cudaMemcpyAsync(S->rowptr.p, rp.p, sizeof(int) * ((size_t)nr + 1), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    LaunchScope ls(c, "setup");
+    k_extract_fill<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, fm, rs, cs, A.rowptr.p, A.col.p, A.val.p, S->rowptr.p, S->col.p, S->val.p);
+    check_launch("k_extract_fill");
+  }
+  c->sync();
+  S->plan();
+  return S;
+}
+
 // ---------------------------------------------------------------- small dense inverse (coarsest MG level)
 namespace {
 __global__ void __launch_bounds__(256) k_csr_to_dense_aug(int n, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val, double *W /* n x 2n */) {

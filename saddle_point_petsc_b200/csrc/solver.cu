@@ -151,6 +151,17 @@ std::string FieldSplitOp::view(int indent) const {
   return o.str();
 }
 
+StridedSplitOp::StridedSplitOp(Op *in, const std::vector<int> &m) : Op(in->ctx, in->n_in, in->n_out), inner(in), map(m.size() + 1), xs(m.size() + 2), ys(m.size() + 2) {
+  B2_CUDA(cudaMemcpyAsync(map.p, m.data(), sizeof(int) * m.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+}
+void StridedSplitOp::apply(const double *x, double *y) {
+  vec_permute_gather(ctx, n_in, map.p, x, xs.p);   // VecScatter: monolithic -> [split 0; split 1]
+  inner->apply(xs.p, ys.p);
+  vec_permute_scatter(ctx, n_in, map.p, ys.p, y);  // and back
+}
+std::string StridedSplitOp::view(int indent) const { return pad(indent) + "strided fields (block size from the matrix), splits gathered/scattered\n" + inner->view(indent + 1); }
+
 LscOp::LscOp(std::shared_ptr<Csr> a00, std::shared_ptr<Csr> a01, std::shared_ptr<Csr> a10, Op *linv, bool scale_diag_)
     : Op(a10->ctx, a10->nrows, a10->nrows), A00(a00), A01(a01), A10(a10), Linv(linv), scale_diag(scale_diag_),
       p0((size_t)a10->nrows + 2), p1((size_t)a10->nrows + 2), u0((size_t)a00->nrows + 2), u1((size_t)a00->nrows + 2) {
@@ -811,9 +822,40 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
 }
 
 Op *Solver::make_fieldsplit() {
-  B2_REQUIRE(Pmat->nest, "pc fieldsplit: operator must be a 2x2 nest (b200sp_mat_create_nest)");
   B2_REQUIRE(opt("pc_fieldsplit_type", "schur") == "schur", "pc fieldsplit: only -pc_fieldsplit_type schur");
-  auto A00 = Pmat->blk[0][0], A01 = Pmat->blk[0][1], A10 = Pmat->blk[1][0], A11 = Pmat->blk[1][1];
+  std::shared_ptr<Csr> A00, A01, A10, A11;
+  std::vector<int> strided_map; // non-empty: monolithic matrix, splits defined by strided fields
+  if (Pmat->nest) {
+    A00 = Pmat->blk[0][0]; A01 = Pmat->blk[0][1]; A10 = Pmat->blk[1][0]; A11 = Pmat->blk[1][1];
+  } else {
+    // the reference's case: KSPSetOperators(A, A) on the DMDA matrix (block size 2, no DM on the KSP), so PCFIELDSPLIT
+    // defines the splits from the block size: field k -> split k, or -pc_fieldsplit_block_size / -pc_fieldsplit_1_fields
+    auto P = Pmat->csr;
+    const int bs = std::stoi(opt("pc_fieldsplit_block_size", std::to_string(P->dof_r > 0 ? P->dof_r : 2)));
+    B2_REQUIRE(bs >= 2 && bs <= 8 && P->nrows == P->ncols && P->nrows % bs == 0, "pc fieldsplit: bad -pc_fieldsplit_block_size for this matrix");
+    std::vector<int> split((size_t)bs, 0);
+    std::string f1 = opt("pc_fieldsplit_1_fields", std::to_string(bs - 1));
+    for (char &ch : f1) if (ch == ',') ch = ' ';
+    std::istringstream in(f1);
+    int f;
+    while (in >> f) { B2_REQUIRE(f >= 0 && f < bs, "pc fieldsplit: field out of range"); split[(size_t)f] = 1; }
+    if (!has("pc_fieldsplit_1_fields") && bs > 2) throw Error(B200SP_ERR_UNSUPPORTED, "pc fieldsplit: block size > 2 needs -pc_fieldsplit_1_fields");
+    A00 = csr_extract_fields(*P, bs, split, 0, 0); A01 = csr_extract_fields(*P, bs, split, 0, 1);
+    A10 = csr_extract_fields(*P, bs, split, 1, 0); A11 = csr_extract_fields(*P, bs, split, 1, 1);
+    A00->tag = "spmv:A00"; A01->tag = "spmv:A01"; A10->tag = "spmv:A10"; A11->tag = "spmv:A11";
+    mats.push_back(A00); mats.push_back(A01); mats.push_back(A10); mats.push_back(A11);
+    const int nnode = P->nrows / bs;
+    int nf0 = 0;
+    for (int k = 0; k < bs; ++k) nf0 += split[(size_t)k] == 0;
+    strided_map.resize((size_t)P->nrows);
+    for (int node = 0; node < nnode; ++node) {
+      int p0 = 0, p1 = 0;
+      for (int k = 0; k < bs; ++k) {
+        if (split[(size_t)k] == 0) strided_map[(size_t)node * nf0 + p0++] = node * bs + k;
+        else strided_map[(size_t)nnode * nf0 + (size_t)node * (bs - nf0) + p1++] = node * bs + k;
+      }
+    }
+  }
   const std::string fs = opt("pc_fieldsplit_schur_fact_type", "full");
   const int fact = fs == "diag" ? 0 : fs == "lower" ? 1 : fs == "upper" ? 2 : fs == "full" ? 3 : -1;
   B2_REQUIRE(fact >= 0, "bad -pc_fieldsplit_schur_fact_type " + fs);
@@ -861,7 +903,9 @@ Op *Solver::make_fieldsplit() {
   }
   Ksp *kS = make_ksp("fieldsplit_1_", S, pcS, "preonly");
   Op *KS = add_op<KspOp>(kS);
-  return add_op<FieldSplitOp>(fact, scale, A01, A10, K0, KS);
+  Op *fsop = add_op<FieldSplitOp>(fact, scale, A01, A10, K0, KS);
+  if (!strided_map.empty()) return add_op<StridedSplitOp>(fsop, strided_map);
+  return fsop;
 }
 
 void Solver::setup() {
@@ -870,8 +914,10 @@ void Solver::setup() {
   Op *Aop = Amat->nest ? (Op *)add_op<NestOp>(Amat->blk[0][0], Amat->blk[0][1], Amat->blk[1][0], Amat->blk[1][1]) : (Op *)add_op<CsrOp>(Amat->csr);
   const std::string pt = opt("pc_type", "none");
   Op *pc = nullptr;
-  if (pt == "fieldsplit") pc = make_fieldsplit();
-  else {
+  if (pt == "fieldsplit") {
+    B2_REQUIRE(Pmat->nest || !ctx->dcomm, "pc fieldsplit on a monolithic matrix: single GPU only (use the nest layout when row-partitioned)");
+    pc = make_fieldsplit();
+  } else {
     B2_REQUIRE(!Pmat->nest, "pc " + pt + " on a nest matrix: use -pc_type fieldsplit");
     pc = make_simple_pc("", Pmat->csr, "none");
   }

@@ -92,6 +92,16 @@ struct FieldSplitOp : Op { // PCFIELDSPLIT, Schur factorisations
   std::string view(int indent) const override;
 };
 
+struct StridedSplitOp : Op { // fieldsplit on a monolithic (field-interleaved) vector: gather the splits, apply, scatter back
+  Op *inner;
+  DevBuf<int> map;          // split-ordered position -> interleaved position
+  DevBuf<double> xs, ys;
+  StridedSplitOp(Op *in, const std::vector<int> &m);
+  bool capturable() const override { return inner->capturable(); }
+  void apply(const double *x, double *y) override;
+  std::string view(int indent) const override;
+};
+
 struct LscOp : Op { // PCLSC
   std::shared_ptr<Csr> A00, A01, A10;
   Op *Linv;

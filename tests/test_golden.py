@@ -124,6 +124,13 @@ def test_unmodified_reference_main_drives_the_cuda_backend():
         assert rc == 0 and "converged due to reason 2" in out, (opts, out, err)
         vals = [float(x) for x in out.split("type: b200sp-shim")[1].split()[:32]]
         assert np.allclose(np.array(vals)[FREE], U_FREE, rtol=1e-9), opts
+    # BASELINE config 0 as stated: the default main.c case with a fieldsplit-Schur preconditioned Krylov solve
+    rc, out, err = run_ref("saddle_point_run_b200_intended", "-ksp_type gmres -ksp_rtol 1e-12 -pc_type fieldsplit -pc_fieldsplit_type schur "
+                           "-pc_fieldsplit_schur_fact_type full -fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type jacobi "
+                           "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi -ksp_converged_reason -solution_view")
+    assert rc == 0 and "converged due to reason 2" in out, (out, err)
+    vals = [float(x) for x in out.split("type: b200sp-shim")[1].split()[:32]]
+    assert np.allclose(np.array(vals)[FREE], U_FREE, rtol=1e-9)
     rc, out, err = run_ref("saddle_point_run_b200", "-ksp_type gmres -pc_type jacobi -ksp_converged_reason")
     assert rc == 0 and "reason -9" in out, (out, err)                  # as written: NaN operator, same verdict as on the CPU
     rc, out, err = run_ref("saddle_point_run_b200_intended", "-da_grid_x 33 -da_grid_y 33 -ksp_type fgmres -pc_type mg -pc_mg_levels 3 -ksp_rtol 1e-9 -ksp_converged_reason")

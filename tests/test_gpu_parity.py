@@ -375,3 +375,26 @@ def test_transpose_and_matmult(ctx):
     assert_csr_identical(L, orc.B.matmat(orc.Bt), "L = B Bt")       # same accumulation order as the oracle
     AA = dev.A.matmult(dev.A)
     assert_csr_identical(AA, orc.A.matmat(orc.A), "A A")
+
+
+# ------------------------------------------------------------------ the reference's own use of PCFIELDSPLIT (config 0)
+FS_REF = ("-pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type {fact} -pc_fieldsplit_schur_precondition {pre} "
+          "-fieldsplit_0_ksp_type {k0} -fieldsplit_0_ksp_max_it 3 -fieldsplit_0_pc_type jacobi -fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
+
+
+@pytest.mark.parametrize("ksp,fact,pre,k0", [("gmres", "full", "a11", "preonly"), ("fgmres", "lower", "selfp", "chebyshev"),
+                                             ("gmres", "upper", "a11", "preonly"), ("minres", "diag", "a11", "preonly")])
+def test_strided_fieldsplit_on_the_reference_operator(ctx, ksp, fact, pre, k0):
+    """KSPSetOperators(A, A) on the DMDA matrix with block size 2 and no DM on the KSP (src/SaddlePointProblem.c:65-67):
+    PCFIELDSPLIT splits Ux / Uy by strided fields; sub-matrices are extracted on the device."""
+    from test_oracle import FREE, U_FREE
+    opts = "-ksp_type %s -ksp_rtol 1e-10 " % ksp + FS_REF.format(fact=fact, pre=pre, k0=k0)
+    if ksp == "minres":
+        opts += " -pc_fieldsplit_schur_scale 1.0"   # Ux/Uy Schur complement is SPD (SURVEY Appendix C): keep the PC positive
+    dev, orc, k, rd, ro, x = run_pair(ctx, 3, 3, opts, kkt=False, rhs_kind=0)
+    assert rd["reason"] == ro["reason"] == 2 and abs(rd["its"] - ro["its"]) <= 1, (rd, ro["its"])
+    assert np.allclose(x[FREE], U_FREE, rtol=1e-8)
+    dev, orc, k, rd, ro, x = run_pair(ctx, 40, 28, opts, kkt=False, rhs_kind=0)
+    assert rd["reason"] == ro["reason"] == 2 and abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    assert np.max(np.abs(x - ro["x"])) <= 1e-8 * np.max(np.abs(ro["x"]))
+    assert "strided fields" in k.view()
