@@ -316,7 +316,9 @@ def test_error_paths(ctx):
     with pytest.raises(sp.B200spError):
         dev.make_ksp("-ksp_type bogus").setup()
     with pytest.raises(sp.B200spError):
-        dev.make_ksp("-pc_type fieldsplit").setup()                             # not a nest
+        dev.make_ksp("-pc_type fieldsplit -pc_fieldsplit_type additive").setup()  # only the Schur variants exist
+    with pytest.raises(sp.B200spError):
+        dev.make_ksp("-pc_type fieldsplit -pc_fieldsplit_block_size 3").setup()   # 50 rows are not a multiple of 3
     a, b = sp.Vec(ctx, 3), sp.Vec(ctx, 4)
     with pytest.raises(sp.B200spError):
         a.axpy(1.0, b)
