@@ -868,8 +868,25 @@ static int solve_gmres(OrKsp *k, const double *b, double *x, int guess_nonzero, 
         pc_apply(k, t, vn);
       }
       double *h = H + (size_t)(m + 1) * it;
-      for (int j = 0; j <= it; ++j) h[j] = or_dot(n, vn, V + (size_t)n * j);           /* VecMDot */
-      for (int j = 0; j <= it; ++j) v_axpy(n, -h[j], V + (size_t)n * j, vn);           /* VecMAXPY */
+      if (k->orthog == 3) { /* KSPGMRESModifiedGramSchmidtOrthogonalization */
+        for (int j = 0; j <= it; ++j) { h[j] = or_dot(n, vn, V + (size_t)n * j); v_axpy(n, -h[j], V + (size_t)n * j, vn); }
+      } else {               /* KSPGMRESClassicalGramSchmidtOrthogonalization */
+        for (int j = 0; j <= it; ++j) h[j] = or_dot(n, vn, V + (size_t)n * j);         /* VecMDot */
+        for (int j = 0; j <= it; ++j) v_axpy(n, -h[j], V + (size_t)n * j, vn);         /* VecMAXPY */
+        int refine = k->orthog == 2;
+        if (k->orthog == 1) { /* refine_ifneeded */
+          double hnrm = 0.0, wn = or_dot(n, vn, vn);
+          for (int j = 0; j <= it; ++j) hnrm += h[j] * h[j];
+          refine = wn < hnrm;
+        }
+        if (refine) {
+          double *h2 = (double *)xmalloc(sizeof(double) * (size_t)(it + 1));
+          for (int j = 0; j <= it; ++j) h2[j] = or_dot(n, vn, V + (size_t)n * j);
+          for (int j = 0; j <= it; ++j) v_axpy(n, -h2[j], V + (size_t)n * j, vn);
+          for (int j = 0; j <= it; ++j) h[j] += h2[j];
+          free(h2);
+        }
+      }
       double hn = or_norm2(n, vn);
       h[it + 1] = hn;
       if (hn != 0.0) v_scale(n, 1.0 / hn, vn);

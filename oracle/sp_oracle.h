@@ -111,6 +111,7 @@ struct OrKsp {
   int norm_none;        /* 1: no convergence test, run exactly max_it iterations (smoother use) */
   double emin, emax;    /* chebyshev bounds */
   double richardson_scale;
+  int orthog;           /* gmres: 0 classical GS (PETSc default), 1 CGS refine_ifneeded, 2 CGS refine_always, 3 modified GS */
   /* results */
   int its, reason;
   double rnorm, rnorm0;

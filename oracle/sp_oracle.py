@@ -24,7 +24,7 @@ class CsrStruct(C.Structure):
 class KspStruct(C.Structure):
     _fields_ = [("type", C.c_int), ("A", C.c_void_p), ("M", C.c_void_p), ("rtol", C.c_double), ("atol", C.c_double),
                 ("dtol", C.c_double), ("max_it", C.c_int), ("restart", C.c_int), ("norm_none", C.c_int),
-                ("emin", C.c_double), ("emax", C.c_double), ("richardson_scale", C.c_double), ("its", C.c_int),
+                ("emin", C.c_double), ("emax", C.c_double), ("richardson_scale", C.c_double), ("orthog", C.c_int), ("its", C.c_int),
                 ("reason", C.c_int), ("rnorm", C.c_double), ("rnorm0", C.c_double), ("hist", c_dp),
                 ("hist_cap", C.c_int), ("hist_len", C.c_int)]
 
@@ -316,6 +316,10 @@ class Solver:
         s.max_it = int(self._get(prefix + "ksp_max_it", default_max_it))
         s.restart = int(self._get(prefix + "ksp_gmres_restart", 30))
         s.richardson_scale = float(self._get(prefix + "ksp_richardson_scale", 1.0))
+        if self._get(prefix + "ksp_gmres_modifiedgramschmidt") is not None:
+            s.orthog = 3
+        else:
+            s.orthog = {"refine_never": 0, "refine_ifneeded": 1, "refine_always": 2}[self._get(prefix + "ksp_gmres_cgs_refinement_type", "refine_never")]
         if self._get(prefix + "ksp_norm_type", "default") == "none" or (t in ("chebyshev", "richardson") and prefix and
                                                                       self._get(prefix + "ksp_norm_type") is None):
             s.norm_none = 1  # inner chebyshev/richardson are fixed-sweep smoothers unless a norm is requested

@@ -26,7 +26,6 @@ namespace {
 struct LocalComm : Comm {
   std::shared_ptr<LocalGroup> g;
   int r, dev;
-  std::vector<const std::vector<HaloMsg> *> *msg_tab; // shared table of per-rank message lists
   LocalComm(std::shared_ptr<LocalGroup> g_, int rank, int device) : g(g_), r(rank), dev(device) { g->device[(size_t)rank] = device; }
   int rank() const override { return r; }
   int size() const override { return g->size; }

@@ -128,9 +128,6 @@ namespace {
 __global__ void __launch_bounds__(256) k_scale_cols(int64_t nnz, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ d, double *out) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = val[k] * d[col[k]];
 }
-__global__ void __launch_bounds__(256) k_add_scaled_same(int64_t nnz, const double *__restrict__ a, double s, const double *__restrict__ b, double *out) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = a[k] + s * b[k];
-}
 // A + s*B on the union pattern: count, then fill (both matrices have ascending columns)
 __global__ void __launch_bounds__(256) k_union_count(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const int *__restrict__ rpb, const int *__restrict__ cb, int *cnt) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
@@ -255,9 +252,6 @@ __global__ void __launch_bounds__(128) k_spgemm_numeric(int nrows, const int *__
       }
     }
   }
-}
-__global__ void __launch_bounds__(256) k_scan64_from32(int n, const int *__restrict__ in32_excl, const int *__restrict__ carry_unused, int64_t *out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in32_excl[i];
 }
 } // namespace
 

@@ -424,7 +424,7 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
 // h never leaves the device between the three vector kernels.
 int Ksp::solve_gmres(const double *b, double *x, bool guess_nonzero, bool flexible) {
   const int m = restart;
-  B2_REQUIRE(m >= 1 && m + 2 <= N_SCALARS, "gmres: restart must be in [1,126]");
+  B2_REQUIRE(m >= 1 && 2 * m + 4 <= N_SCALARS, "gmres: restart must be in [1,62]");
   if (!V.p) {
     V.alloc((size_t)ld * (m + 1));
     if (flexible) Z.alloc((size_t)ld * m);
@@ -463,13 +463,42 @@ int Ksp::solve_gmres(const double *b, double *x, bool guess_nonzero, bool flexib
       } else {
         A->apply(vk, vn);
       }
-      vec_mdot(ctx, n, it + 1, vn, V.p, ld, d_h);                          // VecMDot
-      allreduce_sum(ctx, d_h, it + 1);
-      vec_maxpy_norm2(ctx, n, it + 1, vn, V.p, ld, d_h, d_h + it + 1);     // VecMAXPY + VecNorm fused
-      allreduce_sum(ctx, d_h + it + 1, 1);
-      vec_scale_inv_sqrt(ctx, n, d_h + it + 1, vn, vn);                    // v_{k+1} = w / ||w||
-      ctx->fetch_scalars(d_h, it + 2, hcol.data());
       double *h = H.data() + (size_t)(m + 1) * it;
+      if (orthog == ORTHOG_MGS) {
+        // KSPGMRESModifiedGramSchmidtOrthogonalization: one vector at a time (h_j on the device between the dot
+        // and the update; the norm of the last update is the Hessenberg sub-diagonal)
+        for (int j = 0; j <= it; ++j) {
+          vec_mdot(ctx, n, 1, vn, V.p + (size_t)ld * j, ld, d_h + j);
+          allreduce_sum(ctx, d_h + j, 1);
+          vec_maxpy_norm2(ctx, n, 1, vn, V.p + (size_t)ld * j, ld, d_h + j, d_h + it + 1);
+        }
+        allreduce_sum(ctx, d_h + it + 1, 1);
+        ctx->fetch_scalars(d_h, it + 2, hcol.data());
+      } else {
+        vec_mdot(ctx, n, it + 1, vn, V.p, ld, d_h);                          // VecMDot
+        allreduce_sum(ctx, d_h, it + 1);
+        vec_maxpy_norm2(ctx, n, it + 1, vn, V.p, ld, d_h, d_h + it + 1);     // VecMAXPY + VecNorm fused
+        allreduce_sum(ctx, d_h + it + 1, 1);
+        ctx->fetch_scalars(d_h, it + 2, hcol.data());
+        bool refine = orthog == ORTHOG_CGS_REFINE_ALWAYS;
+        if (orthog == ORTHOG_CGS_REFINE_IFNEEDED) { // refine when what is left of w is smaller than what was removed
+          double hnrm = 0.0;
+          for (int j = 0; j <= it; ++j) hnrm += hcol[j] * hcol[j];
+          refine = hcol[it + 1] < hnrm;
+        }
+        if (refine) { // second classical Gram-Schmidt pass; the corrections add to the Hessenberg column
+          double *d_h2 = d_h + m + 2;
+          vec_mdot(ctx, n, it + 1, vn, V.p, ld, d_h2);
+          allreduce_sum(ctx, d_h2, it + 1);
+          vec_maxpy_norm2(ctx, n, it + 1, vn, V.p, ld, d_h2, d_h + it + 1);
+          allreduce_sum(ctx, d_h + it + 1, 1);
+          std::vector<double> h2((size_t)it + 1);
+          ctx->fetch_scalars(d_h2, it + 1, h2.data());
+          ctx->fetch_scalars(d_h + it + 1, 1, &hcol[(size_t)it + 1]);
+          for (int j = 0; j <= it; ++j) hcol[j] += h2[(size_t)j];
+        }
+      }
+      vec_scale_inv_sqrt(ctx, n, d_h + it + 1, vn, vn);                    // v_{k+1} = w / ||w||
       for (int j = 0; j <= it; ++j) h[j] = hcol[j];
       const double hn = std::sqrt(hcol[it + 1]);
       h[it + 1] = hn;
@@ -651,6 +680,12 @@ Ksp *Solver::make_ksp(const std::string &prefix, Op *A, Op *M, const char *defau
   k->max_it = std::stoi(opt(prefix + "ksp_max_it", "10000"));
   k->restart = std::stoi(opt(prefix + "ksp_gmres_restart", "30"));
   k->richardson_scale = std::stod(opt(prefix + "ksp_richardson_scale", "1.0"));
+  if (has(prefix + "ksp_gmres_modifiedgramschmidt")) k->orthog = ORTHOG_MGS;
+  else {
+    const std::string rt = opt(prefix + "ksp_gmres_cgs_refinement_type", "refine_never");
+    B2_REQUIRE(rt == "refine_never" || rt == "refine_ifneeded" || rt == "refine_always", "bad -ksp_gmres_cgs_refinement_type " + rt);
+    k->orthog = rt == "refine_always" ? ORTHOG_CGS_REFINE_ALWAYS : rt == "refine_ifneeded" ? ORTHOG_CGS_REFINE_IFNEEDED : ORTHOG_CGS;
+  }
   const std::string nt = opt(prefix + "ksp_norm_type", "");
   // inner chebyshev / richardson solvers are fixed-sweep smoothers unless a norm type is requested
   if (nt == "none" || (nt.empty() && !prefix.empty() && (k->type == KSP_CHEBYSHEV || k->type == KSP_RICHARDSON))) k->norm_none = true;
@@ -738,7 +773,10 @@ void Solver::build_levels_single(MgOp *mg, std::shared_ptr<Csr> A0, int Ml, int 
 }
 
 Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
-  B2_REQUIRE(mat->grid_M > 0 && mat->dof_r == 2 && mat->dof_c == 2, "pc mg: needs the velocity block assembled from a DMDA (b200sp_assemble_stress)");
+  if (mat->grid_M == 0 && have_grid && !mat->halo && (int64_t)2 * grid_M * grid_N == mat->nrows && mat->nrows == mat->ncols) {
+    mat->grid_M = grid_M; mat->grid_N = grid_N; mat->dof_r = mat->dof_c = 2; // KSPSetDM equivalent (b200sp_ksp_set_dmda)
+  }
+  B2_REQUIRE(mat->grid_M > 0 && mat->dof_r == 2 && mat->dof_c == 2, "pc mg: needs the velocity block on a DMDA (b200sp_assemble_stress, b200sp_mat_set_grid or b200sp_ksp_set_dmda)");
   const int nlev = std::stoi(opt(prefix + "pc_mg_levels", "2"));
   B2_REQUIRE(nlev >= 2, "pc mg: need at least 2 levels");
   MgOp *mg = add_op<MgOp>(ctx, (int64_t)mat->nrows);

@@ -137,6 +137,7 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   std::string view(int indent) const override;
 };
 
+enum GmresOrthog { ORTHOG_CGS = 0, ORTHOG_CGS_REFINE_IFNEEDED = 1, ORTHOG_CGS_REFINE_ALWAYS = 2, ORTHOG_MGS = 3 };
 enum KspType { KSP_PREONLY = 0, KSP_RICHARDSON = 1, KSP_CHEBYSHEV = 2, KSP_GMRES = 3, KSP_FGMRES = 4, KSP_MINRES = 5 };
 
 struct Ksp {
@@ -150,6 +151,7 @@ struct Ksp {
   bool norm_none = false;
   double emin = 0, emax = 0, richardson_scale = 1.0;
   bool keep_history = false;
+  int orthog = ORTHOG_CGS; // -ksp_gmres_modifiedgramschmidt / -ksp_gmres_cgs_refinement_type (PETSc default: CGS, refine_never)
   // results
   int its = 0, reason = 0;
   double rnorm = 0, rnorm0 = 0;

@@ -400,3 +400,61 @@ def test_strided_fieldsplit_on_the_reference_operator(ctx, ksp, fact, pre, k0):
     assert rd["reason"] == ro["reason"] == 2 and abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
     assert np.max(np.abs(x - ro["x"])) <= 1e-8 * np.max(np.abs(ro["x"]))
     assert "strided fields" in k.view()
+
+
+@pytest.mark.parametrize("extra", ["-ksp_gmres_modifiedgramschmidt", "-ksp_gmres_cgs_refinement_type refine_always",
+                                   "-ksp_gmres_cgs_refinement_type refine_ifneeded"])
+@pytest.mark.parametrize("name", ["fgmres_lsc", "gmres_full_jacobi"])
+def test_gmres_orthogonalisation_variants(ctx, name, extra):
+    """KSPGMRES orthogonalisation options.  With a second Gram-Schmidt pass (or MGS) the basis stays orthogonal, the
+    LSC configuration is no longer rounding-chaotic and the strict tolerances hold for it too."""
+    nx = 24
+    dev, orc, ksp, rd, ro, x = run_pair(ctx, nx, nx, CONFIGS[name] + " " + extra)
+    assert rd["reason"] == ro["reason"] == 2
+    assert abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    if rd["its"] == ro["its"]:
+        assert abs(rd["rnorm"] / rd["history"][0] - ro["rnorm"] / ro["history"][0]) <= 1e-10
+        nu = dev.nu
+        assert np.max(np.abs(x[:nu] - ro["x"][:nu])) <= 1e-8 * np.max(np.abs(ro["x"][:nu]))
+    m = min(len(rd["history"]), len(ro["history"]))
+    assert np.allclose(rd["history"][:m - 1], ro["history"][:m - 1], rtol=1e-5)
+
+
+def test_full_size_properties(ctx):
+    """BASELINE's full size (nx = 2304, 15.9M DOF): size-independent properties instead of an oracle run --
+    closed-form structure counts, symmetry of K, B = (B^T)^T through x.(B^T y) == y.(B x), the constant-pressure
+    null vector, Dirichlet rows, and the headline solve reaching rtol 1e-8 with a true residual to match."""
+    nx = 2304
+    m = nx + 1
+    dev = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+    assert dev.A.size() == (2 * m * m, 2 * m * m, 4 * (3 * m - 2) ** 2)
+    assert dev.B.size()[2] == dev.Bt.size()[2] == 2 * (3 * m - 2) ** 2 and dev.C.size()[2] == (3 * m - 2) ** 2
+    plan = dev.A.spmv_plan()
+    assert plan["max_row_nnz"] == 18 and plan["hist"][5] + plan["hist"][6] == 2 * m * m          # rows of 8/12 and 18 entries
+    assert len(dev.bc) == 2 * (4 * m - 4)
+    n, nu = dev.n, dev.nu
+    rng = np.random.default_rng(0)
+    xh, yh = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    x, y = sp.Vec.from_numpy(ctx, xh), sp.Vec.from_numpy(ctx, yh)
+    kx, ky = sp.Vec(ctx, n), sp.Vec(ctx, n)
+    dev.K.mult(x, kx); dev.K.mult(y, ky)
+    a, b = y.dot(kx), x.dot(ky)
+    assert abs(a - b) <= 1e-9 * abs(a)                                                            # K symmetric
+    one = np.zeros(n); one[nu:] = 1.0
+    k1 = sp.Vec(ctx, n)
+    dev.K.mult(sp.Vec.from_numpy(ctx, one), k1)
+    assert k1.norm() <= 1e-12                                                                     # (0, 1) is the null vector
+    ex = np.zeros(n); ex[dev.bc[:50]] = 1.0                                                       # Dirichlet rows are identity rows
+    kex = sp.Vec(ctx, n)
+    dev.K.mult(sp.Vec.from_numpy(ctx, ex), kex)
+    assert np.array_equal(kex.numpy(), ex)
+    import bench
+    ksp = dev.make_ksp(bench.CONFIGS["fgmres_schur_mg"].format(levels=bench.mg_levels(nx)))
+    sol = sp.Vec(ctx, n)
+    r = ksp.solve(dev.rhs, sol)
+    assert r["reason"] == 2 and r["its"] <= 16
+    res = sp.Vec(ctx, n)
+    dev.K.residual(dev.rhs, sol, res)
+    assert res.norm() <= 1.0001e-8 * dev.rhs.norm()
+    r2 = ksp.solve(dev.rhs, sol)                                                                  # graph replay: bit-identical rerun
+    assert r2["its"] == r["its"] and r2["rnorm"] == r["rnorm"]
