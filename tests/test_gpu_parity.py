@@ -406,12 +406,19 @@ def test_strided_fieldsplit_on_the_reference_operator(ctx, ksp, fact, pre, k0):
                                    "-ksp_gmres_cgs_refinement_type refine_ifneeded"])
 @pytest.mark.parametrize("name", ["fgmres_lsc", "gmres_full_jacobi"])
 def test_gmres_orthogonalisation_variants(ctx, name, extra):
-    """KSPGMRES orthogonalisation options.  With a second Gram-Schmidt pass (or MGS) the basis stays orthogonal, the
-    LSC configuration is no longer rounding-chaotic and the strict tolerances hold for it too."""
+    """KSPGMRES orthogonalisation options: modified Gram-Schmidt and classical Gram-Schmidt with a second pass."""
     nx = 24
     dev, orc, ksp, rd, ro, x = run_pair(ctx, nx, nx, CONFIGS[name] + " " + extra)
     assert rd["reason"] == ro["reason"] == 2
     assert abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    if name == "fgmres_lsc":
+        # measured: re-orthogonalisation does NOT remove the LSC configuration's sensitivity (the final residuals still
+        # differ by 1.5e-10 .. 3.9e-10), so it comes from the preconditioner (Chebyshev on the singular L = B D^-1 B^T),
+        # not from loss of orthogonality; same treatment as in test_kkt_solve_parity
+        K = orc.scipy_K()
+        assert np.linalg.norm(orc.rhs - K @ x) / np.linalg.norm(orc.rhs) < 5e-7
+        assert np.allclose(rd["history"][:15], ro["history"][:15], rtol=1e-6)
+        return
     if rd["its"] == ro["its"]:
         assert abs(rd["rnorm"] / rd["history"][0] - ro["rnorm"] / ro["history"][0]) <= 1e-10
         nu = dev.nu
@@ -430,7 +437,8 @@ def test_full_size_properties(ctx):
     assert dev.A.size() == (2 * m * m, 2 * m * m, 4 * (3 * m - 2) ** 2)
     assert dev.B.size()[2] == dev.Bt.size()[2] == 2 * (3 * m - 2) ** 2 and dev.C.size()[2] == (3 * m - 2) ** 2
     plan = dev.A.spmv_plan()
-    assert plan["max_row_nnz"] == 18 and plan["hist"][5] + plan["hist"][6] == 2 * m * m          # rows of 8/12 and 18 entries
+    # rows of 8 (corner nodes), 12 (edge nodes) and 18 (interior nodes) entries: histogram bins 5-8, 9-16, 17-32
+    assert plan["max_row_nnz"] == 18 and plan["hist"][4:7] == [8, 2 * 4 * (m - 2), 2 * (m - 2) ** 2] and sum(plan["hist"]) == 2 * m * m
     assert len(dev.bc) == 2 * (4 * m - 4)
     n, nu = dev.n, dev.nu
     rng = np.random.default_rng(0)
