@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--config", default="fgmres_schur_mg", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    opts = CONFIGS[args.config].format(levels=mg_levels(args.nx))
+    ap_levels = int(os.environ.get("B200SP_BENCH_MG_LEVELS", "0")) or mg_levels(args.nx)
+    opts = CONFIGS[args.config].format(levels=ap_levels)
 
     if args.impl == "reference":
         run_reference(args, opts)

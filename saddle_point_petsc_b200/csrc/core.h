@@ -150,6 +150,7 @@ struct XSrc;
 struct SpmvEpi;
 constexpr int TMA_TILE_ROWS = 128; // rows per tile of the TMA SpMV kernel (profiles/r01_tma_tile_sweep.txt)
 int spmv_tma_tile_rows();
+bool csr_try_block_index(struct Csr &A, int br, int bc); // build the block-compressed column index if the pattern allows
 bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list = nullptr, int nlist = 0);
 
 struct Csr {
@@ -171,6 +172,9 @@ struct Csr {
   // row-partitioned (MPIAIJ-like) matrix: local rows; columns < ncols are owned (local ids), columns >= ncols are
   // ghost nodes in MPIAIJ garray order, read by the kernels from the halo buffer
   std::shared_ptr<Halo> halo;     // column-space halo (null on one rank); column ids >= ncols are ghost ids + ncols
+  // block-compressed column index (kernels_spmv_tma.cu): one block-column id per blk_r x blk_c node block
+  DevBuf<int> bptr, bcol;
+  int blk_r = 1, blk_c = 1;
   // TMA_TILE_ROWS-row tiles without / with ghost columns: the interior tiles are multiplied while the halo travels
   DevBuf<int> tiles_interior, tiles_boundary;
   int n_tiles_interior = 0, n_tiles_boundary = 0;

@@ -555,6 +555,7 @@ std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written) {
   run_elements(da, as_written, 0, WANT_K, ea);
   auto A = build_box_matrix(da, ea, 2, 2, 0, ea.Ke.p);
   A->tag = "spmv:A";
+  csr_try_block_index(*A, 2, 2);
   return A;
 }
 
@@ -574,8 +575,8 @@ void assemble_rhs(const Dmda &da, int as_written, int kind, double *f) {
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q) {
   ElemArrays ea;
   run_elements(da, 0, 0, WANT_KKT, ea);
-  if (Bt) { *Bt = build_box_matrix(da, ea, 2, 1, 0, ea.Ge.p); (*Bt)->tag = "spmv:Bt"; }
-  if (B) { *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p); (*B)->tag = "spmv:B"; }
+  if (Bt) { *Bt = build_box_matrix(da, ea, 2, 1, 0, ea.Ge.p); (*Bt)->tag = "spmv:Bt"; csr_try_block_index(**Bt, 2, 1); }
+  if (B) { *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p); (*B)->tag = "spmv:B"; csr_try_block_index(**B, 1, 2); }
   if (C) { *C = build_box_matrix(da, ea, 1, 1, 0, ea.Ce.p); (*C)->tag = "spmv:C"; }
   if (Q) { *Q = build_box_matrix(da, ea, 1, 1, 0, ea.Qe.p); (*Q)->tag = "spmv:Q"; }
 }
