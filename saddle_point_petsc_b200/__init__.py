@@ -79,6 +79,7 @@ _SIGS = {
     "b200sp_mat_get_size": [_vp, c_ip, c_ip, C.POINTER(C.c_int64)],
     "b200sp_mat_get_csr_host": [_vp, c_ip, c_ip, c_dp],
     "b200sp_mat_get_spmv_plan": [_vp, C.POINTER(C.c_int64), c_ip, c_ip],
+    "b200sp_mat_get_spmv_format": [_vp, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)],
     "b200sp_mat_set_spmv_kernel": [_vp, C.c_int],
     "b200sp_mat_mult": [_vp, _vp, _vp],
     "b200sp_mat_mult_add": [_vp, _vp, _vp, _vp],
@@ -416,6 +417,12 @@ class Mat:
         k, mr = C.c_int(), C.c_int()
         _chk(lib().b200sp_mat_get_spmv_plan(self.h, hist, C.byref(k), C.byref(mr)))
         return {"hist": list(hist), "kernel": k.value, "max_row_nnz": mr.value}
+
+    def spmv_format(self):
+        """What the TMA SpMV streams for this matrix (valid after the first mult)."""
+        br, bc, vd, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        _chk(lib().b200sp_mat_get_spmv_format(self.h, C.byref(br), C.byref(bc), C.byref(vd), C.byref(nb)))
+        return {"block": (br.value, bc.value), "value_dict": bool(vd.value), "matrix_bytes": nb.value}
 
     def set_spmv_kernel(self, k):
         _chk(lib().b200sp_mat_set_spmv_kernel(self.h, k))

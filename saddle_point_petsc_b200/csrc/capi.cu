@@ -449,6 +449,22 @@ int b200sp_mat_get_spmv_plan(b200sp_mat A, int64_t hist[14], int *kernel, int *m
   if (max_row_nnz) *max_row_nnz = M.max_row_nnz;
   API_END
 }
+int b200sp_mat_get_spmv_format(b200sp_mat A, int *block_r, int *block_c, int *value_dict, int64_t *matrix_bytes) {
+  API_BEGIN
+  Csr &M = plain(A);
+  const bool blk = M.bcol.p != nullptr, dict = M.dict_state == 1;
+  if (block_r) *block_r = blk ? M.blk_r : 1;
+  if (block_c) *block_c = blk ? M.blk_c : 1;
+  if (value_dict) *value_dict = dict ? 1 : 0;
+  if (matrix_bytes) {
+    const int br = blk ? M.blk_r : 1, bc = blk ? M.blk_c : 1;
+    int64_t bytes = 4 * (M.nnz / (br * bc)) + 4 * (int64_t)(M.nrows / br + 1); // (block) column index + its row pointer
+    if (dict) bytes += 2 * M.nnz + M.dict_bytes + 4 * (int64_t)((M.nrows + M.dict_rows - 1) / M.dict_rows + 1);
+    else bytes += 8 * M.nnz + (blk ? 4 * (int64_t)(M.nrows + 1) : 0); // the block-index kernel also reads rowptr
+    *matrix_bytes = bytes;
+  }
+  API_END
+}
 int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel) {
   API_BEGIN
   Csr &M = plain(A);

@@ -151,6 +151,7 @@ struct SpmvEpi;
 constexpr int TMA_TILE_ROWS = 128; // rows per tile of the TMA SpMV kernel (profiles/r01_tma_tile_sweep.txt)
 int spmv_tma_tile_rows();
 bool csr_try_block_index(struct Csr &A, int br, int bc); // build the block-compressed column index if the pattern allows
+void csr_drop_value_dict(struct Csr &A);                 // the values changed: forget the value dictionary (rebuilt lazily)
 bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list = nullptr, int nlist = 0);
 
 struct Csr {
@@ -175,6 +176,13 @@ struct Csr {
   // block-compressed column index (kernels_spmv_tma.cu): one block-column id per blk_r x blk_c node block
   DevBuf<int> bptr, bcol;
   int blk_r = 1, blk_c = 1;
+  // tile-local value dictionary (kernels_spmv_tma.cu): per TMA_TILE_ROWS-row tile the distinct values + a 16-bit code per
+  // nonzero; built lazily by the first SpMV (state 0 = not tried, 1 = in use, -1 = declined), dropped when values change
+  mutable DevBuf<double> dict;
+  mutable DevBuf<int> dptr;
+  mutable DevBuf<unsigned short> codes;
+  mutable int dict_state = 0, dict_cap = 0, dict_rows = 0; // dict_rows: rows per dictionary tile (TMA_TILE_ROWS x block rows)
+  mutable int64_t dict_bytes = 0;
   // TMA_TILE_ROWS-row tiles without / with ghost columns: the interior tiles are multiplied while the halo travels
   DevBuf<int> tiles_interior, tiles_boundary;
   int n_tiles_interior = 0, n_tiles_boundary = 0;
@@ -239,6 +247,12 @@ struct XSrc {
     if (seq) g += ((*seq - 1ull) & 1ull) * ghost_stride;
     return *g; // plain load: the buffer is written by a peer GPU (never through the non-coherent path)
   }
+  __device__ __forceinline__ double2 load2(int c) const { // columns c, c+1 of one node (c even, x 16-byte aligned)
+    if (c < n_owned) return __ldg(reinterpret_cast<const double2 *>(x + c));
+    const double *g = ghost + (c - n_owned);
+    if (seq) g += ((*seq - 1ull) & 1ull) * ghost_stride;
+    return make_double2(g[0], g[1]);
+  }
 #endif
 };
 // fused epilogue of every SpMV kernel, applied to the row sum s of row r:
@@ -252,6 +266,7 @@ struct SpmvEpi {
   int cheb = 0;
   const double *pm1 = nullptr, *pk = nullptr, *dinv = nullptr;
   double ca = 0.0, cb = 0.0, cc = 0.0;
+  int vec2 = 0; // set by the launcher of the block-row kernel, see apply2_store
 #ifdef __CUDACC__
   __device__ __forceinline__ double apply(double s, int r) const {
     if (cheb) {
@@ -262,6 +277,23 @@ struct SpmvEpi {
     double v = alpha * s;
     if (z) v = beta_z * z[r] + v;
     return v;
+  }
+  // rows r, r+1 (r even) of one node with 16-byte loads/stores; same per-element operations as apply().  Only when
+  // vec2 is set (the launcher checked that y and every operand are 16-byte aligned).
+  __device__ __forceinline__ void apply2_store(double s0, double s1, int r, double *y) const {
+    double v0, v1;
+    if (cheb) {
+      const double2 zz = *reinterpret_cast<const double2 *>(z + r);
+      double t0 = zz.x - s0, t1 = zz.y - s1;
+      if (dinv) { const double2 d = *reinterpret_cast<const double2 *>(dinv + r); t0 = t0 * d.x; t1 = t1 * d.y; }
+      const double2 a = *reinterpret_cast<const double2 *>(pm1 + r), b = *reinterpret_cast<const double2 *>(pk + r);
+      v0 = ca * a.x + cb * b.x + cc * t0;
+      v1 = ca * a.y + cb * b.y + cc * t1;
+    } else {
+      v0 = alpha * s0; v1 = alpha * s1;
+      if (z) { const double2 zz = *reinterpret_cast<const double2 *>(z + r); v0 = beta_z * zz.x + v0; v1 = beta_z * zz.y + v1; }
+    }
+    *reinterpret_cast<double2 *>(y + r) = make_double2(v0, v1);
   }
 #endif
 };

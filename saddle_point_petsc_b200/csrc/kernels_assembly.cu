@@ -576,7 +576,13 @@ void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr>
   ElemArrays ea;
   run_elements(da, 0, 0, WANT_KKT, ea);
   if (Bt) { *Bt = build_box_matrix(da, ea, 2, 1, 0, ea.Ge.p); (*Bt)->tag = "spmv:Bt"; csr_try_block_index(**Bt, 2, 1); }
-  if (B) { *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p); (*B)->tag = "spmv:B"; } // 1x2 blocks: measured no gain (0.2206 vs 0.2166 ms at 16M), plain CSR indices kept
+  if (B) {
+    *B = build_box_matrix(da, ea, 1, 2, 1, ea.Ge.p); (*B)->tag = "spmv:B";
+    // 1x2 blocks: no gain for the plain value stream (0.2206 vs 0.2166 ms at 16M), but the value-dictionary kernel
+    // loads both x entries of a block with one 16-byte load
+    static const bool bblk = !(getenv("B200SP_B_BLOCK_INDEX") && atoi(getenv("B200SP_B_BLOCK_INDEX")) == 0);
+    if (bblk) csr_try_block_index(**B, 1, 2);
+  }
   if (C) { *C = build_box_matrix(da, ea, 1, 1, 0, ea.Ce.p); (*C)->tag = "spmv:C"; }
   if (Q) { *Q = build_box_matrix(da, ea, 1, 1, 0, ea.Qe.p); (*Q)->tag = "spmv:Q"; }
 }

@@ -317,6 +317,7 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
     check_launch("k_zero_rows_cols");
   }
   c->sync(); // temporaries are freed on return
+  csr_drop_value_dict(A); // values changed
 }
 
 } // namespace b200sp

@@ -114,7 +114,15 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) sum += av[u] * xv[u];
       }
-      for (; k < ke; ++k) sum += sv[k] * xs.load(sc[k]);
+      if (k < ke) { // tail: the remaining (< UNROLL) entries are loaded together under predicates, not one by one
+        double xv[UNROLL - 1], av[UNROLL - 1];
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (k + u < ke) { av[u] = sv[k + u]; xv[u] = xs.load(sc[k + u]); }
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (k + u < ke) sum += av[u] * xv[u];
+      }
       y[r] = epi.apply(sum, r);
     }
     __syncthreads(); // every consumer is done with this stage
@@ -200,7 +208,15 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) sum += av[u] * xv[u];
       }
-      for (; k < len; ++k) sum += sv[k] * xs.load(sb[k / BC] * BC + (k % BC));
+      if (k < len) { // tail under predicates (k is a multiple of BC here)
+        double xv[UNROLL - 1], av[UNROLL - 1];
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (k + u < len) { av[u] = sv[k + u]; xv[u] = xs.load(sb[(k + u) / BC] * BC + (u % BC)); }
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (k + u < len) sum += av[u] * xv[u];
+      }
       y[r] = epi.apply(sum, r);
     }
     __syncthreads();
@@ -209,6 +225,211 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
       if (t < ntiles) issue(t, stage);
     }
   }
+}
+
+// ---- tile-local value dictionary (CSR-VI style value indexing, per tile) ------------------------------------------
+// Finite-element matrices on structured grids repeat a small set of element-matrix sums: a 128-row tile of the A block
+// holds ~2300 values but only ~300 DISTINCT bit patterns.  Each tile therefore stores its distinct values once (8 B
+// each, in order of first occurrence) and one 16-bit code per nonzero; the kernel streams dictionary + codes + column
+// index (A: ~3.7 B/nnz instead of 9) and looks the value up in shared memory.  The value fed to the multiply is the
+// identical double, in the identical CSR order, so the result is bit-for-bit the same as every other SpMV kernel.
+// Matrices whose tiles do not compress (unstructured values) keep the plain value stream.
+constexpr int DICT_T = 8192;             // hash slots per tile in the build kernel
+constexpr int DICT_MAX_TILE_NNZ = 6144;  // larger tiles: no dictionary
+constexpr int DICT_MAX_ENTRIES = 2048;   // per tile (8 KB of shared memory per stage at most)
+constexpr unsigned long long DICT_EMPTY = ~0ull;
+
+// One thread per BLOCK ROW (node): the BR rows of a node share their block columns, so one x load (16 bytes when
+// BC = 2) and one index load serve BR x BC nonzeros -- the kernel is bound by L1/shared-memory wavefronts once the
+// stream is this small, not by HBM.  Each row still accumulates its own entries in CSR order.  A tile is blockDim.x
+// block rows (BR * 128 rows); rowptr is not needed: row I*BR + rr starts at (bptr[I] * BR + rr * nb) * BC.
+// BR = BC = 1 is plain CSR (bptr = rowptr, bcol = col).
+template <int BR, int BC, int UB>
+__global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ bptr, const int *__restrict__ bcol,
+                                const int *__restrict__ dptr, const double *__restrict__ dict, const unsigned short *__restrict__ codes, XSrc xs,
+                                double *y, SpmvEpi epi, int capc, int capb, int dcap, int stages) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const int NB = blockDim.x;
+  const size_t off_codes = (size_t)dcap * 8, off_bcol = off_codes + (size_t)capc * 2; // capc is a multiple of 8
+  const size_t stage_bytes = off_bcol + (size_t)capb * 4;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + stage_bytes * stages);
+  const int tid = threadIdx.x;
+  auto issue = [&](int idx, int stage) { // one thread
+    const int tile = tile_list ? tile_list[idx] : idx;
+    const int I0 = tile * NB;
+    const int I1 = min(I0 + NB, nbrows);
+    const int g0 = bptr[I0], g1 = bptr[I1];
+    const int s0 = (g0 * (BR * BC)) & ~7;
+    const int cnt = (g1 * (BR * BC) - s0 + 7) & ~7;
+    const int b0 = g0 & ~3;
+    const int bcnt = (g1 - b0 + 3) & ~3;
+    const int d0 = dptr[tile], dcnt = dptr[tile + 1] - d0;
+    unsigned char *base = s_raw + stage_bytes * stage;
+    mbar_expect_tx(&full[stage], (unsigned)dcnt * 8u + (unsigned)cnt * 2u + (unsigned)bcnt * 4u);
+    if (dcnt > 0) bulk_g2s(base, dict + d0, (unsigned)dcnt * 8u, &full[stage]);
+    if (cnt > 0) bulk_g2s(base + off_codes, codes + s0, (unsigned)cnt * 2u, &full[stage]);
+    if (bcnt > 0) bulk_g2s(base + off_bcol, bcol + b0, (unsigned)bcnt * 4u, &full[stage]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+  if (xs.wait_flags) {
+    if (tid < xs.wait_nmsg) {
+      const unsigned long long want = *xs.seq;
+      volatile const unsigned long long *f = xs.wait_flags + tid;
+      for (long long spin = 0; *f < want; ++spin) {
+        __nanosleep(100);
+        if (spin > 20000000LL) { *xs.wait_err = 400 + tid; __threadfence_system(); break; }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+  // values of block b of this thread's rows and the x entries they multiply
+  auto fetch = [&](const double *sd, const unsigned short *sc, const int *sb, int L, int b, double (&av)[BR][BC], double (&xv)[BC]) {
+    const int c0 = sb[b] * BC;
+    if (BC == 2) {
+      const double2 x2 = xs.load2(c0);
+      xv[0] = x2.x; xv[BC - 1] = x2.y;
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr) { // (row start + rr*L + 2b) is even: both codes in one 32-bit load
+        const unsigned pr = *reinterpret_cast<const unsigned *>(sc + rr * L + b * 2);
+        av[rr][0] = sd[pr & 0xffffu]; av[rr][BC - 1] = sd[pr >> 16];
+      }
+    } else {
+      xv[0] = xs.load(c0);
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr) av[rr][0] = sd[sc[rr * L + b]];
+    }
+  };
+  int it = 0;
+  for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
+    const int tile = tile_list ? tile_list[idx] : idx;
+    const int stage = it % stages;
+    const unsigned parity = (unsigned)(it / stages) & 1u;
+    const int I = tile * NB + tid;
+    const int g_al = bptr[tile * NB];
+    const int bs = bptr[I < nbrows ? I : nbrows];
+    const int be = bptr[I + 1 < nbrows ? I + 1 : nbrows];
+    mbar_wait(&full[stage], parity);
+    const unsigned char *base = s_raw + stage_bytes * stage;
+    const double *sd = reinterpret_cast<const double *>(base);
+    const unsigned short *sc = reinterpret_cast<const unsigned short *>(base + off_codes) + (bs * (BR * BC) - ((g_al * (BR * BC)) & ~7));
+    const int *sb = reinterpret_cast<const int *>(base + off_bcol) + (bs - (g_al & ~3));
+    if (I < nbrows) {
+      double sum[BR];
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr) sum[rr] = 0.0;
+      const int nb = be - bs, L = nb * BC;
+      int b = 0;
+      for (; b + UB <= nb; b += UB) {
+        double av[UB][BR][BC], xv[UB][BC];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) fetch(sd, sc, sb, L, b + u, av[u], xv[u]);
+#pragma unroll
+        for (int u = 0; u < UB; ++u)
+#pragma unroll
+          for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) sum[rr] += av[u][rr][cc] * xv[u][cc];
+      }
+      if (b < nb) { // tail under predicates
+        double av[UB - 1][BR][BC], xv[UB - 1][BC];
+#pragma unroll
+        for (int u = 0; u < UB - 1; ++u)
+          if (b + u < nb) fetch(sd, sc, sb, L, b + u, av[u], xv[u]);
+#pragma unroll
+        for (int u = 0; u < UB - 1; ++u)
+          if (b + u < nb) {
+#pragma unroll
+            for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+              for (int cc = 0; cc < BC; ++cc) sum[rr] += av[u][rr][cc] * xv[u][cc];
+          }
+      }
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr)
+        if (!(BR == 2 && epi.vec2)) y[I * BR + rr] = epi.apply(sum[rr], I * BR + rr);
+      if (BR == 2 && epi.vec2) epi.apply2_store(sum[0], sum[BR - 1], I * BR, y);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int t = idx + stages * gridDim.x;
+      if (t < ntiles) issue(t, stage);
+    }
+  }
+}
+
+// one CTA per tile: distinct bit patterns through a shared-memory hash set; codes are ranks in order of FIRST
+// OCCURRENCE (atomicMin of the position per key + a block scan), so the format is deterministic.  Run twice: the
+// count pass sizes the dictionaries, the write pass fills dictionaries and codes.
+__global__ void __launch_bounds__(256) k_dict_build(int nrows, int R, const int *__restrict__ rowptr, const double *__restrict__ val, int write,
+                                                    int *dcnt, const int *__restrict__ dptr, double *dict, unsigned short *codes, int *stat) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
+  int *minpos = reinterpret_cast<int *>(keys + DICT_T);
+  unsigned short *rank = reinterpret_cast<unsigned short *>(minpos + DICT_T);
+  unsigned short *slot = rank + DICT_T;
+  __shared__ int s_scan[256];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  const int r0 = tile * R, r1 = min(r0 + R, nrows);
+  const int j0 = rowptr[r0], n = rowptr[r1] - j0;
+  if (n > DICT_MAX_TILE_NNZ) {
+    if (tid == 0) { stat[0] = 1; if (!write) dcnt[tile] = 0; }
+    return;
+  }
+  for (int h = tid; h < DICT_T; h += 256) { keys[h] = DICT_EMPTY; minpos[h] = 0x7fffffff; }
+  __syncthreads();
+  for (int j = tid; j < n; j += 256) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(val[j0 + j]);
+    if (bits == DICT_EMPTY) { stat[0] = 1; slot[j] = 0; continue; } // the one pattern the set cannot hold: no dictionary
+    unsigned h = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 51) & (DICT_T - 1);
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&keys[h], DICT_EMPTY, bits);
+      if (prev == DICT_EMPTY || prev == bits) break;
+      h = (h + 1) & (DICT_T - 1);
+    }
+    atomicMin(&minpos[h], j);
+    slot[j] = (unsigned short)h;
+  }
+  __syncthreads();
+  const int C = (n + 255) / 256;
+  const int b = min(tid * C, n), e = min(b + C, n);
+  int cnt = 0;
+  for (int j = b; j < e; ++j) cnt += minpos[slot[j]] == j;
+  s_scan[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int t = 0; t < 256; ++t) { const int v = s_scan[t]; s_scan[t] = acc; acc += v; }
+    s_total = acc;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (!write) {
+    if (tid == 0) {
+      dcnt[tile] = (total + 1) & ~1; // 16-byte granules for the bulk copy
+      atomicMax(&stat[1], total);
+      if (total > DICT_MAX_ENTRIES) stat[0] = 1;
+    }
+    return;
+  }
+  int at = s_scan[tid];
+  const int d0 = dptr[tile];
+  for (int j = b; j < e; ++j)
+    if (minpos[slot[j]] == j) { rank[slot[j]] = (unsigned short)at; dict[d0 + at] = val[j0 + j]; ++at; }
+  if (tid == 0 && (total & 1)) dict[d0 + total] = 0.0;
+  __syncthreads();
+  for (int j = tid; j < n; j += 256) codes[j0 + j] = rank[slot[j]];
 }
 
 // verify the block structure of block row I and count its blocks
@@ -271,6 +492,50 @@ bool csr_try_block_index(Csr &A, int br, int bc) {
   return false;
 }
 
+// build (or decline) the tile-local value dictionary of A; called lazily from the first un-captured TMA SpMV
+static void build_value_dict(const Csr &A) {
+  static const bool off = getenv("B200SP_NO_VALUE_DICT") && atoi(getenv("B200SP_NO_VALUE_DICT"));
+  Ctx *c = A.ctx;
+  A.dict_state = -1;
+  if (off || A.nrows == 0 || A.nnz < 4096 || spmv_tma_tile_rows() != TMA_TILE_ROWS) return;
+  const int R = TMA_TILE_ROWS * (A.bcol.p ? A.blk_r : 1), ntiles = (A.nrows + R - 1) / R; // one thread per block row
+  A.dict_rows = R;
+  DevBuf<int> cnt((size_t)ntiles + 1), stat(2);
+  stat.zero(c->stream);
+  const size_t smem = (size_t)DICT_T * 14 + (size_t)DICT_MAX_TILE_NNZ * 2;
+  static bool attr = false;
+  if (!attr) { B2_CUDA(cudaFuncSetAttribute(k_dict_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  { LaunchScope ls(c, "setup"); k_dict_build<<<ntiles, 256, smem, c->stream>>>(A.nrows, R, A.rowptr.p, A.val.p, 0, cnt.p, nullptr, nullptr, nullptr, stat.p); check_launch("k_dict_build"); }
+  int h_stat[2] = {0, 0};
+  B2_CUDA(cudaMemcpyAsync(h_stat, stat.p, sizeof(h_stat), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  if (h_stat[0]) return;
+  A.dptr.alloc((size_t)ntiles + 1);
+  int total = 0;
+  exclusive_scan_i32(c, cnt.p, A.dptr.p, ntiles, &total);
+  // worth it only if dictionary + codes are clearly smaller than the 8 B/nnz value stream
+  if ((double)total * 8.0 + (double)A.nnz * 2.0 > 0.75 * 8.0 * (double)A.nnz) { A.dptr.release(); return; }
+  A.dict.alloc((size_t)total + 16);
+  A.codes.alloc((size_t)A.nnz + 32);
+  A.codes.zero(c->stream);
+  { LaunchScope ls(c, "setup"); k_dict_build<<<ntiles, 256, smem, c->stream>>>(A.nrows, R, A.rowptr.p, A.val.p, 1, nullptr, A.dptr.p, A.dict.p, A.codes.p, stat.p); check_launch("k_dict_build"); }
+  c->sync();
+  // Measured (profiles/r01_value_dict_sweep.txt): the dictionary wins whenever the block-row kernel applies (A 2x2,
+  // B^T 2x1, B 1x2: 1.7-1.9x over the plain value stream), for long scalar rows, and for tiny dictionaries (R: the
+  // lookup is a shared-memory broadcast); for scalar matrices with 9 nnz/row and a few hundred distinct values per
+  // tile (C, Q) the extra dependent shared-memory lookup costs more than the smaller stream saves.
+  static const int force = getenv("B200SP_VALUE_DICT") ? atoi(getenv("B200SP_VALUE_DICT")) : 0;
+  if (force < 2 && !A.bcol.p && (double)A.nnz / A.nrows < 12.0 && h_stat[1] > 32) { A.dptr.release(); A.dict.release(); A.codes.release(); return; }
+  A.dict_cap = (h_stat[1] + 1) & ~1;
+  if (A.dict_cap < 2) A.dict_cap = 2;
+  A.dict_bytes = (int64_t)total * 8;
+  A.dict_state = 1;
+}
+void csr_drop_value_dict(Csr &A) {
+  A.dict.release(); A.dptr.release(); A.codes.release();
+  A.dict_state = 0; A.dict_cap = 0; A.dict_rows = 0; A.dict_bytes = 0;
+}
+
 // returns false when the matrix does not fit the shared-memory tiling (caller falls back)
 int spmv_tma_tile_rows() {
   static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;
@@ -312,7 +577,51 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
   const double mean = A.nrows ? (double)A.nnz / A.nrows : 0.0;
   (void)mean;
-  if (A.bcol.p && R == TMA_TILE_ROWS) { // block-compressed column index: 8 + 4/(BR*BC) bytes per nonzero
+  if (A.dict_state == 0) { // lazily, never while a CUDA graph is being recorded
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    B2_CUDA(cudaStreamIsCapturing(c->stream, &st));
+    if (st == cudaStreamCaptureStatusNone) build_value_dict(A);
+  }
+  const int dbr = A.bcol.p ? A.blk_r : 1, dbc = A.bcol.p ? A.blk_c : 1;
+  if (A.dict_state == 1 && R == TMA_TILE_ROWS && !tile_list && A.dict_rows == TMA_TILE_ROWS * dbr &&
+      (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // tile-local value dictionary, one thread per block row
+    const int capt = cap * dbr;                       // nonzeros per tile of 128 block rows
+    const int capc = (capt + 16) & ~7;
+    const int capb = ((capt / (dbr * dbc) + 8) + 3) & ~3;
+    const size_t smem_d = ((size_t)A.dict_cap * 8 + (size_t)capc * 2 + (size_t)capb * 4) * stages + 8 * TMA_MAX_STAGES;
+    if (smem_d <= budget) {
+      static bool attr_d = false;
+      if (!attr_d) {
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_d = true;
+      }
+      int psm = (int)(budget / smem_d);
+      if (psm < 1) psm = 1;
+      if (psm * R > 2048) psm = 2048 / R;
+      static const int env_psm = getenv("B200SP_TMA_CTAS") ? atoi(getenv("B200SP_TMA_CTAS")) : 0;
+      if (env_psm && env_psm < psm) psm = env_psm;
+      const int nbrows = A.nrows / dbr;
+      const int ntd = (nbrows + R - 1) / R;
+      const int gridd = ntd < c->num_sms * psm ? ntd : c->num_sms * psm;
+      const int *bp = A.bcol.p ? A.bptr.p : A.rowptr.p, *bc = A.bcol.p ? A.bcol.p : A.col.p;
+      auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+      SpmvEpi e2 = epi;
+      e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
+#define B200SP_DICT_LAUNCH(BR_, BC_, UB_) \
+  k_spmv_tma_dict<BR_, BC_, UB_><<<gridd, R, smem_d, c->stream>>>(nbrows, ntd, nullptr, bp, bc, A.dptr.p, A.dict.p, A.codes.p, xs, y, e2, capc, capb, A.dict_cap, stages)
+      if (dbr == 2 && dbc == 2) B200SP_DICT_LAUNCH(2, 2, 3);
+      else if (dbr == 2 && dbc == 1) B200SP_DICT_LAUNCH(2, 1, 3);
+      else if (dbr == 1 && dbc == 2) B200SP_DICT_LAUNCH(1, 2, 3);
+      else B200SP_DICT_LAUNCH(1, 1, 6);
+#undef B200SP_DICT_LAUNCH
+      check_launch("k_spmv_tma_dict");
+      return true;
+    }
+  }
+  if (A.bcol.p) { // block-compressed column index: 8 + 4/(BR*BC) bytes per nonzero (R is a multiple of BR)
     const int capb = ((cap / (A.blk_r * A.blk_c) + 8) + 3) & ~3;
     const size_t smem_b = ((size_t)cap * 8 + (size_t)capb * 4) * stages + 8 * TMA_MAX_STAGES;
     static bool attr_b = false;

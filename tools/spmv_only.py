@@ -13,6 +13,14 @@ ctx = sp.Context()
 da = sp.DMDA(ctx, nx, nx)
 if block == "A":
     m = da.assemble_stress()
+elif block in ("P", "R"):
+    import ctypes as C
+    h = sp._vp()
+    Mc = nx // 2 + 1
+    sp._chk(sp.lib().b200sp_interp_q1(ctx.h, Mc, Mc, 2, 1, C.byref(h)))
+    m = sp.Mat(ctx, h)
+    if block == "R":
+        m = m.transpose()
 else:
     Bt, B, C, Q = da.assemble_kkt()
     m = {"Bt": Bt, "B": B, "C": C}[block]
@@ -28,4 +36,7 @@ for _ in range(reps):
     m.mult(x, y)
 ms = ctx.timer_stop() / reps
 byts = 12 * nnz + 4 * (r + 1) + 8 * r + 8 * c
-print("block %s nx %d: %.4f ms  %.1f GB/s (algorithmic)" % (block, nx, ms, byts / ms / 1e6))
+fmt = m.spmv_format()
+stream = fmt["matrix_bytes"] + 8 * r + 8 * c
+print("block %s nx %d: %.4f ms  %.1f GB/s (algorithmic CSR bytes)  %.1f GB/s (bytes of the stored format: block %s, value_dict %s, %.2f B/nnz)"
+      % (block, nx, ms, byts / ms / 1e6, stream / ms / 1e6, fmt["block"], fmt["value_dict"], fmt["matrix_bytes"] / nnz))
