@@ -183,6 +183,9 @@ struct Csr {
   mutable DevBuf<unsigned short> codes;
   mutable int dict_state = 0, dict_cap = 0, dict_rows = 0; // dict_rows: rows per dictionary tile (TMA_TILE_ROWS x block rows)
   mutable int64_t dict_bytes = 0;
+  // tile order for kernels that wait for the halo themselves: tiles (of wait_order_rows rows) without ghost columns first
+  mutable DevBuf<int> wait_order;
+  mutable int wait_order_rows = 0, wait_n_nowait = 0;
   // TMA_TILE_ROWS-row tiles without / with ghost columns: the interior tiles are multiplied while the halo travels
   DevBuf<int> tiles_interior, tiles_boundary;
   int n_tiles_interior = 0, n_tiles_boundary = 0;
@@ -255,6 +258,67 @@ struct XSrc {
   }
 #endif
 };
+// ---- halo push fused into the producing SpMV (peer-to-peer halos) ----------------------------------------------
+// When the caller knows that the vector an SpMV writes is the next one to be multiplied by a row-partitioned matrix,
+// the kernel itself stores the values its neighbours need straight into their ghost buffers (NVLink) as it produces
+// them, and the last CTA to finish raises the neighbours' sequence flags -- the separate push kernel, its launch and
+// its dependency on the whole producer disappear.  Protocol (parity, flags, sequence counter) as in dist.h.
+struct HaloP2PMsg { double *peer_ghost; unsigned long long *peer_flag; long long peer_stride; int send_off, send_cnt, peer_recv_off, pad; };
+struct PushOut {
+  const unsigned char *grp = nullptr; // per 64 owned nodes: does any of them go to a neighbour?  (null: no push)
+  const int *node_ent = nullptr;      // per owned node: (first entry << 2) | number of entries (<= 3), 0 = none
+  const int2 *ents = nullptr;         // {message, position of the node inside that message}
+  const HaloP2PMsg *msgs = nullptr;
+  unsigned long long *seq = nullptr;
+  unsigned *ticket = nullptr;
+  int nmsg = 0, dof = 1;
+#ifdef __CUDACC__
+  __device__ __forceinline__ void row(int r, double v) const { // row r of the produced vector has the value v
+    const int node = dof == 2 ? r >> 1 : r, c = dof == 2 ? r & 1 : 0;
+    if (!grp[node >> 6]) return;
+    const int e = node_ent[node];
+    if (!e) return;
+    const unsigned long long par = *seq & 1ull;
+    for (int k = 0; k < (e & 3); ++k) {
+      const int2 t = ents[(e >> 2) + k];
+      const HaloP2PMsg &g = msgs[t.x];
+      g.peer_ghost[par * g.peer_stride + (long long)(g.peer_recv_off + t.y) * dof + c] = v;
+    }
+  }
+  __device__ __forceinline__ void node2(int node, double v0, double v1) const { // both dofs of a node (dof == 2)
+    if (!grp[node >> 6]) return;
+    const int e = node_ent[node];
+    if (!e) return;
+    const unsigned long long par = *seq & 1ull;
+    for (int k = 0; k < (e & 3); ++k) {
+      const int2 t = ents[(e >> 2) + k];
+      const HaloP2PMsg &g = msgs[t.x];
+      *reinterpret_cast<double2 *>(g.peer_ghost + par * g.peer_stride + (long long)(g.peer_recv_off + t.y) * 2) = make_double2(v0, v1);
+    }
+  }
+  // called by EVERY thread of EVERY CTA once, after its last row: one system-scope fence per CTA, a ticket, and the
+  // last CTA raises the flags in the neighbours' memory and advances the sequence counter
+  __device__ __forceinline__ void finish() const {
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    const unsigned long long k = *seq;
+    __syncthreads(); // everyone has read seq before thread 0 advances it
+    if ((int)threadIdx.x < nmsg) {
+      volatile unsigned long long *f = msgs[threadIdx.x].peer_flag;
+      *f = k + 1ull;
+    }
+    if (threadIdx.x == 0) { *ticket = 0u; *seq = k + 1ull; }
+  }
+#endif
+};
+
 // fused epilogue of every SpMV kernel, applied to the row sum s of row r:
 //   cheb == 0:  beta_z*z[r] + alpha*s                                   (z may be null; z may alias y)
 //   cheb == 1:  ca*pm1[r] + cb*pk[r] + cc*(dinv[r]*(z[r] - s))          (z = b; dinv may be null)  -- the same
@@ -267,6 +331,7 @@ struct SpmvEpi {
   const double *pm1 = nullptr, *pk = nullptr, *dinv = nullptr;
   double ca = 0.0, cb = 0.0, cc = 0.0;
   int vec2 = 0; // set by the launcher of the block-row kernel, see apply2_store
+  PushOut push; // fused halo push of the produced vector (grp == null: none)
 #ifdef __CUDACC__
   __device__ __forceinline__ double apply(double s, int r) const {
     if (cheb) {
@@ -280,8 +345,7 @@ struct SpmvEpi {
   }
   // rows r, r+1 (r even) of one node with 16-byte loads/stores; same per-element operations as apply().  Only when
   // vec2 is set (the launcher checked that y and every operand are 16-byte aligned).
-  __device__ __forceinline__ void apply2_store(double s0, double s1, int r, double *y) const {
-    double v0, v1;
+  __device__ __forceinline__ void apply2_store(double s0, double s1, int r, double *y, double &v0, double &v1) const {
     if (cheb) {
       const double2 zz = *reinterpret_cast<const double2 *>(z + r);
       double t0 = zz.x - s0, t1 = zz.y - s1;
@@ -297,9 +361,12 @@ struct SpmvEpi {
   }
 #endif
 };
-void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0, bool reuse_halo = false);
+// push_to: the produced vector y is the next one multiplied by a matrix whose column halo is *push_to (dof values per
+// node): push its boundary values to the neighbours now (fused into the kernel when possible); the consumer then only waits
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha = 1.0, const double *z = nullptr, double beta_z = 0.0, bool reuse_halo = false,
+              Halo *push_to = nullptr, int push_dof = 0);
 // reuse_halo: the ghost values of this x are already in the halo buffer (previous SpMV with the same x and halo)
-void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, bool reuse_halo = false);
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, bool reuse_halo = false, Halo *push_to = nullptr, int push_dof = 0);
 void csr_get_diagonal(const Csr &A, double *d);
 void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool do_rows, bool do_cols, bool set_diag);
 

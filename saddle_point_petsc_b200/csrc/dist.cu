@@ -372,6 +372,13 @@ Halo::~Halo() {
   if (ev_arrived) cudaEventDestroy(ev_arrived);
 }
 
+PushOut Halo::push_out(int dof) const {
+  PushOut o;
+  o.grp = d_push_grp.p; o.node_ent = d_push_node_ent.p; o.ents = d_push_ents.p; o.msgs = d_p2p.p;
+  o.seq = seq.p; o.ticket = ticket.p; o.nmsg = n_msgs; o.dof = dof;
+  return o;
+}
+
 const double *Halo::ghost_now() {
   if (!p2p) return ghost.p;
   unsigned long long k = 0;
@@ -432,6 +439,31 @@ static void setup_p2p(Halo &h, const Layout &L, int rank) {
     q.peer_recv_off = pr.recv_off[slot];
     q.pad = 0;
   }
+  { // node-keyed send tables for pushes fused into producing kernels
+    const int ngrp = (h.n_owned + 63) / 64 + 1;
+    std::vector<unsigned char> grp((size_t)ngrp, 0);
+    std::vector<int> cnt((size_t)h.n_owned + 1, 0), first((size_t)h.n_owned + 1, 0), ent((size_t)h.n_owned + 1, 0);
+    for (int m = 0; m < h.n_msgs; ++m)
+      for (int64_t k = 0; k < h.node_msgs[(size_t)m].send_cnt; ++k) cnt[(size_t)h.h_send_lnode[(size_t)(h.node_msgs[(size_t)m].send_off + k)]]++;
+    int total = 1; // entry 0 is never used so that "0" can mean "none"
+    for (int v = 0; v < h.n_owned; ++v) { B2_REQUIRE(cnt[(size_t)v] <= 3, "halo: a node goes to more than 3 neighbours"); first[(size_t)v] = total; total += cnt[(size_t)v]; }
+    std::vector<int2> ents((size_t)total + 1, make_int2(0, 0));
+    std::vector<int> fill((size_t)h.n_owned + 1, 0);
+    for (int m = 0; m < h.n_msgs; ++m)
+      for (int64_t k = 0; k < h.node_msgs[(size_t)m].send_cnt; ++k) {
+        const int v = h.h_send_lnode[(size_t)(h.node_msgs[(size_t)m].send_off + k)];
+        ents[(size_t)(first[(size_t)v] + fill[(size_t)v]++)] = make_int2(m, (int)k);
+      }
+    for (int v = 0; v < h.n_owned; ++v)
+      if (cnt[(size_t)v]) { ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; grp[(size_t)(v >> 6)] = 1; }
+    h.d_push_grp.alloc(grp.size());
+    h.d_push_node_ent.alloc(ent.size());
+    h.d_push_ents.alloc(ents.size());
+    B2_CUDA(cudaMemcpyAsync(h.d_push_grp.p, grp.data(), grp.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(h.d_push_node_ent.p, ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(h.d_push_ents.p, ents.data(), sizeof(int2) * ents.size(), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+  }
   h.d_p2p.alloc((size_t)h.n_msgs + 1);
   if (h.n_msgs) B2_CUDA(cudaMemcpyAsync(h.d_p2p.p, pm.data(), sizeof(Halo::P2PMsg) * pm.size(), cudaMemcpyHostToDevice, c->stream));
   c->sync();
@@ -480,6 +512,7 @@ std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
     if (msg.send_cnt || msg.recv_cnt) h->node_msgs.push_back(msg);
   }
   h->n_send = (int)send_lnode.size();
+  h->h_send_lnode = send_lnode;
   h->d_send_lnode.alloc((size_t)h->n_send + 1);
   h->d_ring2ghost.alloc(ring.size() + 1);
   if (h->n_send) B2_CUDA(cudaMemcpyAsync(h->d_send_lnode.p, send_lnode.data(), sizeof(int) * send_lnode.size(), cudaMemcpyHostToDevice, c->stream));
@@ -501,6 +534,11 @@ void Halo::begin(const double *x, int dof) {
   B2_REQUIRE(dof == 1 || dof == 2, "halo: dof must be 1 or 2");
   Ctx *c = ctx;
   if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
+  if (p2p && pushed_vec) { // the kernel that produced x already pushed it (csr_spmv_epi push_to)
+    B2_REQUIRE(pushed_vec == x, "halo: the vector pushed ahead is not the one being multiplied");
+    pushed_vec = nullptr;
+    return;
+  }
   if (p2p) { // push over NVLink + flag; the matching wait is in end()
     LaunchScope ls(c, "halo:p2p_push");
     int grid = (n_send * dof + 1023) / 1024; // a few elements per thread: fewer blocks, fewer fences and tickets

@@ -98,9 +98,16 @@ struct Halo {
   int64_t ghost_stride = 0;                       // doubles per parity
   DevBuf<unsigned long long> seq, flags;          // exchanges started (device counter); one flag per incoming message
   DevBuf<unsigned> ticket;
-  struct P2PMsg { double *peer_ghost; unsigned long long *peer_flag; long long peer_stride; int send_off, send_cnt, peer_recv_off, pad; };
+  using P2PMsg = HaloP2PMsg;
   DevBuf<P2PMsg> d_p2p;                           // per outgoing message
   std::vector<void *> ipc_opened;
+  // fused push (PushOut in core.h): which owned nodes go where, keyed by node
+  std::vector<int> h_send_lnode;
+  DevBuf<unsigned char> d_push_grp;
+  DevBuf<int> d_push_node_ent;
+  DevBuf<int2> d_push_ents;
+  const double *pushed_vec = nullptr;             // a producer already pushed this vector for the next exchange
+  PushOut push_out(int dof) const;                // descriptor for a producing kernel
   int n_msgs = 0;
   const double *ghost_now();                      // host: synchronise and return the parity that holds the latest halo
   ~Halo();

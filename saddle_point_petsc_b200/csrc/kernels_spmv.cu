@@ -182,7 +182,25 @@ void Csr::plan() {
   lanes_per_row = mean <= 2 ? 2 : mean <= 4 ? 4 : mean <= 8 ? 8 : mean <= 16 ? 16 : 32;
 }
 
-void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, bool reuse_halo) {
+static bool csr_spmv_launch(const Csr &A, const double *x, double *y, SpmvEpi &epi, bool reuse_halo);
+void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi_in, bool reuse_halo, Halo *push_to, int push_dof) {
+  Ctx *c = A.ctx;
+  SpmvEpi epi = epi_in;
+  // the produced vector is multiplied next by a matrix with the halo *push_to: push its boundary values now.  Only for
+  // peer-to-peer halos; fused into the TMA kernels, otherwise the ordinary push kernel right after this SpMV.
+  static const bool no_fused_push = getenv("B200SP_NO_FUSED_PUSH") && atoi(getenv("B200SP_NO_FUSED_PUSH"));
+  if (push_to && !(c->dcomm && push_to->p2p && A.nrows > 0) ) push_to = nullptr;
+  if (push_to && no_fused_push) push_to = nullptr;
+  if (push_to && A.kernel == SPMV_TMA) epi.push = push_to->push_out(push_dof);
+  const bool fused = csr_spmv_launch(A, x, y, epi, reuse_halo);
+  if (push_to) {
+    if (!fused) push_to->begin(y, push_dof); // the kernel that ran cannot push: ordinary push kernel, still ahead of the consumer
+    push_to->pushed_vec = y;
+  }
+}
+
+// returns true when the kernel that ran also pushed the produced vector (epi.push)
+static bool csr_spmv_launch(const Csr &A, const double *x, double *y, SpmvEpi &epi, bool reuse_halo) {
   Ctx *c = A.ctx;
   XSrc xs{x, nullptr, 0x7fffffff};
   bool pending_wait = false;
@@ -201,6 +219,7 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, 
   } else if (A.halo && c->dcomm) {
     // MatMult_MPIAIJ.  The ghost values of x travel on the halo stream while the tiles that have no ghost column
     // (the interior: ~90% of the rows) are multiplied; the boundary tiles follow once the halo has arrived.
+    epi.push = PushOut(); // send/recv halos: no fused push (push_to is peer-to-peer only, so it is null here anyway)
     if (!reuse_halo) A.halo->begin(x, A.halo_dof);
     // Measured (profiles/r01_scaling_notes.md): with the persistent TMA grid holding every SM the NCCL kernel cannot
     // start until the interior kernel drains, so the two-launch split was slightly SLOWER (20.3 vs 19.9 ms at 8 GPUs).
@@ -220,12 +239,13 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, 
         LaunchScope ls(c, A.tag.c_str());
         csr_spmv_tma(A, xs, y, epi, A.tiles_boundary.p, A.n_tiles_boundary);
       }
-      return;
+      return false;
     }
   }
-  if (A.nrows <= 0) return;
+  if (A.nrows <= 0) return false;
   LaunchScope ls(c, A.tag.c_str());
-  if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return;
+  if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return epi.push.grp != nullptr;
+  epi.push = PushOut(); // the kernels below do not push
   if (pending_wait) { A.halo->end(); xs.wait_flags = nullptr; } // the TMA kernel declined: wait with the separate kernel
   if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
@@ -264,12 +284,13 @@ void csr_spmv_epi(const Csr &A, const double *x, double *y, const SpmvEpi &epi, 
     }
     check_launch("k_spmv_vector");
   }
+  return false;
 }
 
-void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z, bool reuse_halo) {
+void csr_spmv(const Csr &A, const double *x, double *y, double alpha, const double *z, double beta_z, bool reuse_halo, Halo *push_to, int push_dof) {
   SpmvEpi e;
   e.alpha = alpha; e.z = z; e.beta_z = beta_z;
-  csr_spmv_epi(A, x, y, e, reuse_halo);
+  csr_spmv_epi(A, x, y, e, reuse_halo, push_to, push_dof);
 }
 
 void csr_get_diagonal(const Csr &A, double *d) {

@@ -40,10 +40,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 constexpr int TMA_MAX_STAGES = 4;
 
+// peer-to-peer halo: one lane per incoming message polls this rank's flag words until the neighbours' pushes of the
+// current exchange have landed (bounded; reports through the mapped error word).  Called by the whole CTA.
+__device__ __forceinline__ void halo_wait_cta(const XSrc &xs) {
+  if ((int)threadIdx.x < xs.wait_nmsg) {
+    const unsigned long long want = *xs.seq;
+    volatile const unsigned long long *f = xs.wait_flags + threadIdx.x;
+    for (long long spin = 0; *f < want; ++spin) {
+      __nanosleep(100);
+      if (spin > 20000000LL) { *xs.wait_err = 400 + (int)threadIdx.x; __threadfence_system(); break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 // dynamic shared layout: [S stages][ val: cap doubles | col: cap ints ], then S mbarriers
 template <int UNROLL>
 __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ rowptr, const int *__restrict__ col,
-                           const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int cap, int stages) {
+                           const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int cap, int stages, int n_nowait) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int R = blockDim.x;
   const size_t stage_bytes = (size_t)cap * 12;
@@ -78,21 +93,11 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
       if (t < ntiles) issue(t, s);
     }
   }
-  if (xs.wait_flags) { // peer-to-peer halo: the first tiles are already in flight while we wait for the neighbours
-    if (tid < xs.wait_nmsg) {
-      const unsigned long long want = *xs.seq;
-      volatile const unsigned long long *f = xs.wait_flags + tid;
-      for (long long spin = 0; *f < want; ++spin) {
-        __nanosleep(100);
-        if (spin > 20000000LL) { *xs.wait_err = 400 + tid; __threadfence_system(); break; }
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-  }
+  bool waited = xs.wait_flags == nullptr; // tiles before n_nowait read no ghost column: the wait is deferred until the first one that does
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
     const int tile = tile_list ? tile_list[idx] : idx;
+    if (!waited && idx >= n_nowait) { halo_wait_cta(xs); waited = true; }
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
     const int r = tile * R + tid;
@@ -123,7 +128,9 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
         for (int u = 0; u < UNROLL - 1; ++u)
           if (k + u < ke) sum += av[u] * xv[u];
       }
-      y[r] = epi.apply(sum, r);
+      const double v = epi.apply(sum, r);
+      y[r] = v;
+      if (epi.push.grp) epi.push.row(r, v);
     }
     __syncthreads(); // every consumer is done with this stage
     if (tid == 0) {
@@ -131,6 +138,7 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
       if (t < ntiles) issue(t, stage);
     }
   }
+  if (epi.push.grp) epi.push.finish(); // fused halo push: fence, ticket, last CTA raises the neighbours' flags
 }
 
 // ---- block-compressed column index (BCSR-style indices, CSR values) ---------------------------------------------
@@ -141,7 +149,7 @@ __global__ void k_spmv_tma(int nrows, int ntiles, const int *__restrict__ tile_l
 // The CSR col array is kept for MatView/export and for the other kernels.
 template <int BR, int BC, int UNROLL>
 __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ rowptr, const int *__restrict__ bptr,
-                               const int *__restrict__ bcol, const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int cap, int capb, int stages) {
+                               const int *__restrict__ bcol, const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi, int cap, int capb, int stages, int n_nowait) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int R = blockDim.x;
   const size_t stage_bytes = (size_t)cap * 8 + (size_t)capb * 4;
@@ -171,21 +179,11 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
       if (t < ntiles) issue(t, s);
     }
   }
-  if (xs.wait_flags) {
-    if (tid < xs.wait_nmsg) {
-      const unsigned long long want = *xs.seq;
-      volatile const unsigned long long *f = xs.wait_flags + tid;
-      for (long long spin = 0; *f < want; ++spin) {
-        __nanosleep(100);
-        if (spin > 20000000LL) { *xs.wait_err = 400 + tid; __threadfence_system(); break; }
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-  }
+  bool waited = xs.wait_flags == nullptr; // tiles before n_nowait read no ghost column: the wait is deferred until the first one that does
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
     const int tile = tile_list ? tile_list[idx] : idx;
+    if (!waited && idx >= n_nowait) { halo_wait_cta(xs); waited = true; }
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
     const int r = tile * R + tid;
@@ -217,7 +215,9 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
         for (int u = 0; u < UNROLL - 1; ++u)
           if (k + u < len) sum += av[u] * xv[u];
       }
-      y[r] = epi.apply(sum, r);
+      const double v = epi.apply(sum, r);
+      y[r] = v;
+      if (epi.push.grp) epi.push.row(r, v);
     }
     __syncthreads();
     if (tid == 0) {
@@ -225,6 +225,7 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
       if (t < ntiles) issue(t, stage);
     }
   }
+  if (epi.push.grp) epi.push.finish(); // fused halo push: fence, ticket, last CTA raises the neighbours' flags
 }
 
 // ---- tile-local value dictionary (CSR-VI style value indexing, per tile) ------------------------------------------
@@ -247,7 +248,7 @@ constexpr unsigned long long DICT_EMPTY = ~0ull;
 template <int BR, int BC, int UB>
 __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ bptr, const int *__restrict__ bcol,
                                 const int *__restrict__ dptr, const double *__restrict__ dict, const unsigned short *__restrict__ codes, XSrc xs,
-                                double *y, SpmvEpi epi, int capc, int capb, int dcap, int stages) {
+                                double *y, SpmvEpi epi, int capc, int capb, int dcap, int stages, int n_nowait) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int NB = blockDim.x;
   const size_t off_codes = (size_t)dcap * 8, off_bcol = off_codes + (size_t)capc * 2; // capc is a multiple of 8
@@ -281,18 +282,7 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
       if (t < ntiles) issue(t, s);
     }
   }
-  if (xs.wait_flags) {
-    if (tid < xs.wait_nmsg) {
-      const unsigned long long want = *xs.seq;
-      volatile const unsigned long long *f = xs.wait_flags + tid;
-      for (long long spin = 0; *f < want; ++spin) {
-        __nanosleep(100);
-        if (spin > 20000000LL) { *xs.wait_err = 400 + tid; __threadfence_system(); break; }
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-  }
+  bool waited = xs.wait_flags == nullptr; // tiles before n_nowait read no ghost column: the wait is deferred until the first one that does
   // values of block b of this thread's rows and the x entries they multiply
   auto fetch = [&](const double *sd, const unsigned short *sc, const int *sb, int L, int b, double (&av)[BR][BC], double (&xv)[BC]) {
     const int c0 = sb[b] * BC;
@@ -313,6 +303,7 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
     const int tile = tile_list ? tile_list[idx] : idx;
+    if (!waited && idx >= n_nowait) { halo_wait_cta(xs); waited = true; }
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
     const int I = tile * NB + tid;
@@ -355,10 +346,21 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
               for (int cc = 0; cc < BC; ++cc) sum[rr] += av[u][rr][cc] * xv[u][cc];
           }
       }
+      if (BR == 2 && epi.vec2) {
+        double v0, v1;
+        epi.apply2_store(sum[0], sum[BR - 1], I * BR, y, v0, v1);
+        if (epi.push.grp) {
+          if (epi.push.dof == 2) epi.push.node2(I, v0, v1);
+          else { epi.push.row(I * BR, v0); epi.push.row(I * BR + 1, v1); }
+        }
+      } else {
 #pragma unroll
-      for (int rr = 0; rr < BR; ++rr)
-        if (!(BR == 2 && epi.vec2)) y[I * BR + rr] = epi.apply(sum[rr], I * BR + rr);
-      if (BR == 2 && epi.vec2) epi.apply2_store(sum[0], sum[BR - 1], I * BR, y);
+        for (int rr = 0; rr < BR; ++rr) {
+          const double v = epi.apply(sum[rr], I * BR + rr);
+          y[I * BR + rr] = v;
+          if (epi.push.grp) epi.push.row(I * BR + rr, v);
+        }
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -366,6 +368,7 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
       if (t < ntiles) issue(t, stage);
     }
   }
+  if (epi.push.grp) epi.push.finish(); // fused halo push: fence, ticket, last CTA raises the neighbours' flags
 }
 
 // one CTA per tile: distinct bit patterns through a shared-memory hash set; codes are ranks in order of FIRST
@@ -492,6 +495,43 @@ bool csr_try_block_index(Csr &A, int br, int bc) {
   return false;
 }
 
+// tiles of T rows that read no ghost column come first: a kernel that waits for the neighbours' halo itself does so
+// only when it reaches the first tile that needs it, so the wait hides behind the interior tiles
+__global__ void __launch_bounds__(256) k_tile_ghost_flag(int nrows, int T, int ncols, const int *__restrict__ rowptr, const int *__restrict__ col, int *flag) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    bool g = false;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) g = g || col[k] >= ncols;
+    if (g) flag[r / T] = 1;
+  }
+}
+static void ensure_wait_order(const Csr &A, int T) {
+  static const bool off = getenv("B200SP_NO_DEFER_WAIT") && atoi(getenv("B200SP_NO_DEFER_WAIT"));
+  if (off || A.wait_order_rows == T || A.nrows <= 0) return;
+  Ctx *c = A.ctx;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  B2_CUDA(cudaStreamIsCapturing(c->stream, &st));
+  if (st != cudaStreamCaptureStatusNone) return;
+  const int ntiles = (A.nrows + T - 1) / T;
+  DevBuf<int> flag((size_t)ntiles + 1);
+  flag.zero(c->stream);
+  {
+    LaunchScope ls(c, "setup");
+    k_tile_ghost_flag<<<std::max(1, std::min((A.nrows + 255) / 256, c->num_sms * 16)), 256, 0, c->stream>>>(A.nrows, T, A.ncols, A.rowptr.p, A.col.p, flag.p);
+    check_launch("k_tile_ghost_flag");
+  }
+  std::vector<int> hf((size_t)ntiles), order;
+  B2_CUDA(cudaMemcpyAsync(hf.data(), flag.p, sizeof(int) * (size_t)ntiles, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  order.reserve((size_t)ntiles);
+  for (int t = 0; t < ntiles; ++t) if (!hf[(size_t)t]) order.push_back(t);
+  A.wait_n_nowait = (int)order.size();
+  for (int t = 0; t < ntiles; ++t) if (hf[(size_t)t]) order.push_back(t);
+  A.wait_order.alloc((size_t)ntiles + 1);
+  B2_CUDA(cudaMemcpyAsync(A.wait_order.p, order.data(), sizeof(int) * (size_t)ntiles, cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  A.wait_order_rows = T;
+}
+
 // build (or decline) the tile-local value dictionary of A; called lazily from the first un-captured TMA SpMV
 static void build_value_dict(const Csr &A) {
   static const bool off = getenv("B200SP_NO_VALUE_DICT") && atoi(getenv("B200SP_NO_VALUE_DICT"));
@@ -564,8 +604,8 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   const size_t smem = (size_t)cap * 12 * stages + 8 * TMA_MAX_STAGES;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
@@ -592,10 +632,10 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     if (smem_d <= budget) {
       static bool attr_d = false;
       if (!attr_d) {
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_d = true;
       }
       int psm = (int)(budget / smem_d);
@@ -607,11 +647,14 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
       const int ntd = (nbrows + R - 1) / R;
       const int gridd = ntd < c->num_sms * psm ? ntd : c->num_sms * psm;
       const int *bp = A.bcol.p ? A.bptr.p : A.rowptr.p, *bc = A.bcol.p ? A.bcol.p : A.col.p;
+      const int *order = nullptr;
+      int n_nowait = 0;
+      if (xs.wait_flags) { ensure_wait_order(A, R * dbr); if (A.wait_order_rows == R * dbr) { order = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
       auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
       SpmvEpi e2 = epi;
       e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
 #define B200SP_DICT_LAUNCH(BR_, BC_, UB_) \
-  k_spmv_tma_dict<BR_, BC_, UB_><<<gridd, R, smem_d, c->stream>>>(nbrows, ntd, nullptr, bp, bc, A.dptr.p, A.dict.p, A.codes.p, xs, y, e2, capc, capb, A.dict_cap, stages)
+  k_spmv_tma_dict<BR_, BC_, UB_><<<gridd, R, smem_d, c->stream>>>(nbrows, ntd, order, bp, bc, A.dptr.p, A.dict.p, A.codes.p, xs, y, e2, capc, capb, A.dict_cap, stages, n_nowait)
       if (dbr == 2 && dbc == 2) B200SP_DICT_LAUNCH(2, 2, 3);
       else if (dbr == 2 && dbc == 1) B200SP_DICT_LAUNCH(2, 1, 3);
       else if (dbr == 1 && dbc == 2) B200SP_DICT_LAUNCH(1, 2, 3);
@@ -621,14 +664,16 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
       return true;
     }
   }
+  int n_nowait = 0;
+  if (xs.wait_flags && !tile_list) { ensure_wait_order(A, R); if (A.wait_order_rows == R) { tile_list = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
   if (A.bcol.p) { // block-compressed column index: 8 + 4/(BR*BC) bytes per nonzero (R is a multiple of BR)
     const int capb = ((cap / (A.blk_r * A.blk_c) + 8) + 3) & ~3;
     const size_t smem_b = ((size_t)cap * 8 + (size_t)capb * 4) * stages + 8 * TMA_MAX_STAGES;
     static bool attr_b = false;
     if (!attr_b) {
-      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<1, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<1, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_b = true;
     }
     int psm = (int)(budget / smem_b);
@@ -636,18 +681,18 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     if (psm * R > 2048) psm = 2048 / R;
     const int gridb = ntiles < c->num_sms * psm ? ntiles : c->num_sms * psm;
     if (A.blk_r == 2 && A.blk_c == 2)
-      k_spmv_tma_blk<2, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages);
+      k_spmv_tma_blk<2, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages, n_nowait);
     else if (A.blk_r == 1 && A.blk_c == 2)
-      k_spmv_tma_blk<1, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages);
+      k_spmv_tma_blk<1, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages, n_nowait);
     else
-      k_spmv_tma_blk<2, 1, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages);
+      k_spmv_tma_blk<2, 1, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages, n_nowait);
     check_launch("k_spmv_tma_blk");
     return true;
   }
   if (env_U ? env_U == 6 : true)
-    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
+    k_spmv_tma<6><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages, n_nowait);
   else
-    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages);
+    k_spmv_tma<3><<<grid, R, smem, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, cap, stages, n_nowait);
   check_launch("k_spmv_tma");
   return true;
 }

@@ -190,13 +190,18 @@ void MgOp::cycle(int l, const double *b, double *x) {
   Level &L = *lev[l];
   const bool last = l == (int)lev.size() - 1;
   if (last && !replicated) { coarse->apply(b, x); return; }
+  // Row-partitioned levels: every vector below is consumed by a known matrix, so its producer pushes the halo
+  // (smoother -> A for the residual, residual -> R, interpolation -> A for the post-smoother, post-smoother -> the
+  // finer level's P); without peer-to-peer halos the hints are ignored.
+  Halo *hA = L.A->halo.get(), *hR = L.R ? L.R->halo.get() : nullptr;
+  L.smooth->push_after = hA; L.smooth->push_after_dof = L.A->halo_dof;
   L.smooth->solve(b, x, false);
-  csr_spmv(*L.A, x, L.r.p, -1.0, b, 1.0);          // r = b - A x
+  csr_spmv(*L.A, x, L.r.p, -1.0, b, 1.0, false, hR, hR ? L.R->halo_dof : 0); // r = b - A x
   if (!last) {
     Level &Lc = *lev[l + 1];
     csr_spmv(*L.R, L.r.p, Lc.b.p);                  // restrict
     cycle(l + 1, Lc.b.p, Lc.x.p);
-    csr_spmv(*L.P, Lc.x.p, x, 1.0, x, 1.0);         // x += P xc
+    csr_spmv(*L.P, Lc.x.p, x, 1.0, x, 1.0, false, hA, L.A->halo_dof); // x += P xc
   } else {
     // bridge to the replicated coarse hierarchy: restrict into my part of the coarse vector, all-gather, reorder to
     // the natural numbering, run the remaining levels redundantly on every rank, take my part back, interpolate
@@ -214,9 +219,12 @@ void MgOp::cycle(int l, const double *b, double *x) {
     vec_permute_scatter(ctx, (int64_t)bridge_cnt * ctx->size, gather_map.p, g_all.p, nat_b.p);
     replicated->apply(nat_b.p, nat_x.p);
     vec_permute_gather(ctx, bridge_nloc, local_map.p, nat_x.p, loc_x.p);
-    csr_spmv(*L.P, loc_x.p, x, 1.0, x, 1.0);
+    csr_spmv(*L.P, loc_x.p, x, 1.0, x, 1.0, false, hA, L.A->halo_dof);
   }
+  Halo *hUp = l > 0 && lev[l - 1]->P ? lev[l - 1]->P->halo.get() : nullptr; // the finer level interpolates this level's x
+  L.smooth->push_after = hUp; L.smooth->push_after_dof = hUp ? lev[l - 1]->P->halo_dof : 0;
   L.smooth->solve(b, x, true);
+  L.smooth->push_after = nullptr;
 }
 void MgOp::apply(const double *b, double *x) { cycle(0, b, x); } // level 0 works on the caller's vectors: no copies
 std::string MgOp::view(int indent) const {
@@ -355,11 +363,13 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
     // When the operator is a CSR matrix each sweep after the first is ONE kernel: the SpMV's epilogue forms the
     // residual, applies Jacobi and the three-term update (SpmvEpi::cheb) -- r is never written to memory.
     const Csr *Ac = A->csr();
-    auto sweep = [&](const double *pm1_, double ca, const double *cur_, double cb, double cc, double *out) {
+    // `more`: another sweep multiplies `out` by the same matrix next; otherwise the caller's hint (push_after) applies
+    auto sweep = [&](const double *pm1_, double ca, const double *cur_, double cb, double cc, double *out, bool more) {
       if (Ac) {
         SpmvEpi e;
         e.cheb = 1; e.z = b; e.pm1 = pm1_; e.pk = cur_; e.dinv = dinv; e.ca = ca; e.cb = cb; e.cc = cc;
-        csr_spmv_epi(*Ac, cur_, out, e);
+        Halo *pt = more ? Ac->halo.get() : push_after;
+        csr_spmv_epi(*Ac, cur_, out, e, false, pt, more ? Ac->halo_dof : push_after_dof);
       } else {
         A->residual(b, cur_, r);
         vec_cheb_update(ctx, n, ca, pm1_, cb, cur_, cc, dinv, r, out);
@@ -370,8 +380,14 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
     double *cur;
     if (guess_nonzero) {
       cur = w2.p;                                   // p1 = x0 + scale * M^-1 (b - A x0); never in place: the SpMV gathers x0
-      sweep(x, 1.0, x, 0.0, scale, cur);
-      if (max_it == 1) vec_copy(ctx, n, cur, x);
+      if (max_it == 1) { // the copy below changes the vector the consumer sees: no push hint
+        Halo *keep = push_after; push_after = nullptr;
+        sweep(x, 1.0, x, 0.0, scale, cur, false);
+        push_after = keep;
+        vec_copy(ctx, n, cur, x);
+      } else {
+        sweep(x, 1.0, x, 0.0, scale, cur, true);
+      }
     } else {
       cur = max_it == 1 ? x : w2.p;
       vec_cheb_update(ctx, n, 0.0, b, 0.0, b, scale, dinv, b, cur); // p1 = scale * M^-1 b
@@ -381,7 +397,7 @@ int Ksp::solve_chebyshev(const double *b, double *x, bool guess_nonzero) {
       ckp1 = 2.0 * mu * ck - ckm1;
       omega = omegaprod * ck / ckp1;
       double *out = (i == max_it - 1) ? x : (cur == w2.p ? w3.p : w2.p);
-      sweep(pm1, (1.0 - omega) * am1, cur, omega, omega * scale, out);
+      sweep(pm1, (1.0 - omega) * am1, cur, omega, omega * scale, out, i < max_it - 1);
       pm1 = cur; am1 = 1.0; cur = out;
       ckm1 = ck; ck = ckp1;
       its = i + 1;

@@ -162,6 +162,11 @@ struct Ksp {
   // CUDA-graph replay of the preconditioner application (outer KSP only): one instantiated graph per (input, output)
   // vector pair -- the Krylov basis vectors are persistent, so the pairs repeat from solve to solve
   struct PcGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  // smoother inside PCMG on a row-partitioned level: the halo (and dof) of the matrix that multiplies this solver's
+  // OUTPUT next (the level operator for the residual, or the finer level's interpolation), so the last sweep can push
+  // its boundary values from inside the SpMV kernel (csr_spmv_epi push_to)
+  Halo *push_after = nullptr;
+  int push_after_dof = 0;
   bool use_pc_graph = false, pc_warmed = false;
   std::map<std::pair<const double *, double *>, PcGraph> pc_graphs;
   ~Ksp();
