@@ -143,6 +143,66 @@ def test_spmv_other_kernels_and_ragged_matrices(ctx):
     assert np.array_equal(ye.numpy(), np.zeros(3))
 
 
+def test_spmv_compressed_storage(ctx):
+    """The default TMA kernel streams a losslessly compressed matrix (block column index + tile-local value dictionary):
+    the format is reported, declines where it cannot pay, survives value changes, and never changes a bit."""
+    import scipy.sparse as sps
+    nx, ny = 96, 64
+    dev = sp.SaddlePointProblem(ctx, nx, ny, kkt=True)
+    orc = so.Problem(nx, ny, kkt=True)
+    for name, blk in (("A", (2, 2)), ("Bt", (2, 1)), ("B", (1, 2))):
+        D, O = getattr(dev, name), getattr(orc, name)
+        x = rand_vec(O.ncols, 21)
+        xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, O.nrows)
+        D.mult(xd, yd)
+        fmt = D.spmv_format()
+        assert fmt["block"] == blk and fmt["value_dict"], (name, fmt)
+        nnz = D.size()[2]
+        assert fmt["matrix_bytes"] < 0.5 * 12 * nnz, (name, fmt)       # less than half of the CSR bytes
+        assert same_bits(yd.numpy(), O.mult(x)), name
+    # values change after the dictionary was built (MatZeroRowsColumns): it is rebuilt, results follow the new values
+    D, O = dev.A, orc.A
+    rows = np.array([0, 1, 7, 500, 501, 2 * 97 * 30 + 11], dtype=np.int32)
+    rp, ci, v = D.csr()
+    D.zero_rows_columns(rows, 3.0)
+    ri = np.repeat(np.arange(O.nrows), np.diff(rp))
+    hit_r, hit_c = np.isin(ri, rows), np.isin(ci, rows)
+    v = v.copy()
+    v[hit_r | hit_c] = 0.0
+    v[hit_r & (ri == ci)] = 3.0
+    O2 = so.Csr.from_arrays(O.nrows, O.ncols, rp, ci, v)
+    x = rand_vec(O.ncols, 22)
+    xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, O.nrows)
+    D.mult(xd, yd)
+    assert D.spmv_format()["value_dict"]
+    assert same_bits(yd.numpy(), O2.mult(x))
+    # unstructured values: every entry distinct -> the dictionary declines, plain value stream, still bit-exact
+    rng = np.random.default_rng(11)
+    n = 6000
+    R = sps.random(n, n, density=14.0 / n, random_state=5, format="csr")
+    R.sort_indices()
+    Dr = sp.Mat.from_scipy(ctx, R)
+    Or = so.Csr.from_arrays(n, n, R.indptr, R.indices, R.data)
+    x = rand_vec(n, 23)
+    xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, n)
+    if Dr.spmv_plan()["kernel"] == 3:
+        Dr.mult(xd, yd)
+        assert not Dr.spmv_format()["value_dict"]
+        assert same_bits(yd.numpy(), Or.mult(x))
+    # few distinct values, some of them awkward (signed zero, denormal, huge, tiny): dictionary on a plain-CSR matrix
+    palette = np.array([-0.0, 0.0, 5e-324, -1.7976931348623157e308, 1e-300, 0.1, -0.1, 1.0 / 3.0])
+    S = R.copy()
+    S.data = palette[rng.integers(0, len(palette), size=S.nnz)]
+    Ds = sp.Mat.from_scipy(ctx, S)
+    Os = so.Csr.from_arrays(n, n, S.indptr, S.indices, S.data)
+    x = rand_vec(n, 24) * 1e-3
+    xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, n)
+    if Ds.spmv_plan()["kernel"] == 3:
+        Ds.mult(xd, yd)
+        assert Ds.spmv_format()["value_dict"] and Ds.spmv_format()["block"] == (1, 1)
+        assert same_bits(yd.numpy(), Os.mult(x))
+
+
 def test_spmv_linearity_at_scale(ctx):
     """size-independent property at a large size: A(ax+by) == aAx + bAy to rounding, and the nest apply
     equals the sum of its blocks."""
