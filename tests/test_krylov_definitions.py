@@ -239,3 +239,40 @@ def test_two_level_mg_vcycle_matches_the_dense_error_propagation():
     so.lib().or_op_apply(s.ksp.contents.M, so.dptr(b), so.dptr(y))
     ref = (np.eye(n) - E) @ (Ainv @ b)
     assert np.linalg.norm(y - ref) < 1e-9 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("pre", ["a11", "selfp", "lsc", "lsc_scaled"])
+def test_schur_preconditioning_matrices_match_their_definitions(pre):
+    """-pc_fieldsplit_schur_precondition a11 | selfp and PCLSC (with and without -pc_lsc_scale_diag), each with Jacobi as
+    the innermost solve so that the whole preconditioner is an explicit product of known matrices."""
+    p = so.Problem(6, 6, kkt=True, rhs_kind=1)
+    base = ("-ksp_type fgmres -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type upper "
+            "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type jacobi -fieldsplit_1_ksp_type preonly ")
+    if pre in ("a11", "selfp"):
+        opts = base + "-pc_fieldsplit_schur_precondition %s -fieldsplit_1_pc_type jacobi" % pre
+    else:
+        opts = base + ("-pc_fieldsplit_schur_precondition self -fieldsplit_1_pc_type lsc -fieldsplit_1_lsc_ksp_type preonly "
+                       "-fieldsplit_1_lsc_pc_type jacobi" + (" -fieldsplit_1_pc_lsc_scale_diag" if pre == "lsc_scaled" else ""))
+    s = so.Solver(p, opts)
+    n0, n1 = p.nu, p.np_
+    A, Bt, B, C = (m.scipy().toarray() for m in (p.A, p.Bt, p.B, p.C))
+    Dinv = np.diag(1.0 / np.diag(A))
+    if pre == "a11":
+        dd = np.diag(C)
+        Sinv = np.diag(1.0 / np.where(dd == 0, 1.0, dd))
+    elif pre == "selfp":                                     # Sp = A11 - A10 diag(A00)^-1 A01
+        dd = np.diag(C - B @ Dinv @ Bt)
+        Sinv = np.diag(1.0 / np.where(dd == 0, 1.0, dd))
+    else:                                                    # PCLSC: L^-1 A10 [D^-1] A00 [D^-1] A01 L^-1, L = A10 [D^-1] A01
+        W = Dinv if pre == "lsc_scaled" else np.eye(n0)
+        dl = np.diag(B @ W @ Bt)
+        Linv = np.diag(1.0 / np.where(dl == 0, 1.0, dl))
+        Sinv = Linv @ B @ W @ A @ W @ Bt @ Linv
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal(n0 + n1)
+    y1 = Sinv @ b[n0:]
+    y0 = Dinv @ (b[:n0] - Bt @ y1)                           # UPPER factorisation
+    y = np.empty(n0 + n1)
+    so.lib().or_op_apply(s.ksp.contents.M, so.dptr(b), so.dptr(y))
+    ref = np.concatenate([y0, y1])
+    assert np.max(np.abs(y - ref)) < 1e-11 * np.max(np.abs(ref)), pre
