@@ -583,7 +583,7 @@ int b200sp_ksp_set_dmda(b200sp_ksp ksp, b200sp_dmda da) { API_BEGIN ksp->s.have_
 int b200sp_ksp_setup(b200sp_ksp ksp) { API_BEGIN ksp->s.setup(); API_END }
 int b200sp_ksp_solve(b200sp_ksp ksp, b200sp_vec b, b200sp_vec x) {
   API_BEGIN
-  if (!ksp->s.is_setup) ksp->s.setup();
+  if (!ksp->s.current()) ksp->s.setup(); // also when matrix values changed since KSPSetUp (PETSc: object state)
   B2_REQUIRE(b->v.n == ksp->s.outer->n && x->v.n == b->v.n && b != x, "KSPSolve: size mismatch or aliasing");
   ksp->s.outer->solve(b->v.d, x->v.d, false);
   ksp->s.ctx->sync();
@@ -591,7 +591,7 @@ int b200sp_ksp_solve(b200sp_ksp ksp, b200sp_vec b, b200sp_vec x) {
 }
 int b200sp_ksp_solve_host(b200sp_ksp ksp, const double *b_host, double *x_host, int64_t n) {
   API_BEGIN
-  if (!ksp->s.is_setup) ksp->s.setup();
+  if (!ksp->s.current()) ksp->s.setup(); // also when matrix values changed since KSPSetUp (PETSc: object state)
   Ctx *c = ksp->s.ctx;
   B2_REQUIRE(n == ksp->s.outer->n, "KSPSolve(host): size mismatch");
   // staging vectors live with the KSP (allocated once): the call itself only copies and solves
@@ -616,7 +616,7 @@ int b200sp_ksp_get_residual_history(b200sp_ksp ksp, double *hist, int cap, int *
 }
 int b200sp_ksp_pc_apply(b200sp_ksp ksp, b200sp_vec x, b200sp_vec y) {
   API_BEGIN
-  if (!ksp->s.is_setup) ksp->s.setup();
+  if (!ksp->s.current()) ksp->s.setup(); // also when matrix values changed since KSPSetUp (PETSc: object state)
   B2_REQUIRE(x->v.n == ksp->s.outer->n && y->v.n == x->v.n && x != y, "PCApply: size mismatch or aliasing");
   if (ksp->s.outer_pc) ksp->s.outer_pc->apply(x->v.d, y->v.d);
   else vec_copy(ksp->s.ctx, x->v.n, x->v.d, y->v.d);

@@ -193,6 +193,7 @@ struct Csr {
   std::shared_ptr<Layout> layout;  // node layout of a square DMDA matrix (multigrid coarsening)
   int64_t row_gstart = 0, col_gstart = 0; // first global row / owned global column of this rank (PETSc numbering)
   void plan();           // histogram + kernel choice (device reduction)
+  int64_t state = 0;     // bumped whenever values change (PetscObjectState): a KSP set up on an older state sets up again
 };
 constexpr int CSR_PAD = 8; // zero entries appended to col/val so vector loads may overrun a row tile
 
@@ -201,6 +202,12 @@ struct Mat {
   bool nest = false;
   std::shared_ptr<Csr> csr;               // plain matrix
   std::shared_ptr<Csr> blk[2][2];         // nest blocks (blk[1][1] may be null)
+  int64_t state() const { // sum of the block states
+    if (!nest) return csr ? csr->state : 0;
+    int64_t s = 0;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (blk[i][j]) s += blk[i][j]->state;
+    return s;
+  }
   int nrows() const { return nest ? blk[0][0]->nrows + blk[1][0]->nrows : csr->nrows; }
   int ncols() const { return nest ? blk[0][0]->ncols + blk[0][1]->ncols : csr->ncols; }
 };

@@ -339,6 +339,7 @@ void csr_zero_rows_cols(Csr &A, int n, const int *rows_host, double diag, bool d
   }
   c->sync(); // temporaries are freed on return
   csr_drop_value_dict(A); // values changed
+  A.state++;
 }
 
 } // namespace b200sp

@@ -980,6 +980,7 @@ void Solver::setup() {
   outer->keep_history = true;
   outer->use_pc_graph = pc && opt("b200sp_pc_graph", "1") != "0" && pc->capturable() && (!ctx->dcomm || ctx->dcomm->capturable());
   ctx->sync();
+  setup_state = Amat->state() + Pmat->state() + (schur_user ? schur_user->state : 0);
   is_setup = true;
 }
 

@@ -205,6 +205,8 @@ struct Solver {
   Ksp *outer = nullptr;
   Op *outer_pc = nullptr;
   bool is_setup = false;
+  int64_t setup_state = 0; // Amat/Pmat value state at setup(); KSPSolve sets up again when the matrices changed since
+  bool current() const { return is_setup && Amat && Pmat && Amat->state() + Pmat->state() + (schur_user ? schur_user->state : 0) == setup_state; }
   DevBuf<double> host_b, host_x; // device staging for b200sp_ksp_solve_host
   explicit Solver(Ctx *c) : ctx(c) {}
   void set_options(const char *text);
