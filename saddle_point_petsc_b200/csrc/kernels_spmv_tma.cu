@@ -6,8 +6,17 @@
 // waits for the arithmetic and costs no registers or issue slots.  Consumers: one thread per row walks its
 // row in CSR order out of shared memory, gathers x through L1/L2 and accumulates product-then-add, i.e.
 // bit-identical to the sequential MatMult_SeqAIJ loop (same result as SPMV_STREAM).
-//   shared memory per stage = 12 B x (max tile nnz + pad); A block (18 nnz/row, R = 512): 110.7 KB x 2 stages.
+//   shared memory per stage = 12 B x (max tile nnz + pad); A block (18 nnz/row, R = 128): 27.8 KB x 2 stages, 4 CTAs/SM.
 //   algorithmic bytes per launch: 12 nnz + 4 (rows+1) + 8 rows + 8 cols  (SURVEY 8d).
+//
+// Three kernels share that pipeline and differ in WHAT is streamed (all give bit-identical results):
+//   k_spmv_tma        values 8 B + column 4 B per nonzero                      (plain CSR; C, Q, unstructured matrices)
+//   k_spmv_tma_blk    values 8 B + one block-column id per BR x BC node block   (A 9 B/nnz; when the dictionary declines)
+//   k_spmv_tma_dict   16-bit codes into a per-tile dictionary of distinct values + block-column ids, one thread per
+//                     node block row (A 3.74 B/nnz; default for A, B^T, B, P, R)
+// Row-partitioned matrices: ghost columns are read from the halo buffer (XSrc); with peer-to-peer halos the kernel
+// itself waits for the neighbours' flags when it reaches the first tile that has a ghost column (tiles without come
+// first, Csr::wait_order) and can push the boundary rows of the vector it produces to the neighbours (SpmvEpi::push).
 #include "dev.cuh"
 #include <algorithm>
 #include <cstdlib>
