@@ -50,6 +50,7 @@ _SIGS = {
     "b200sp_dmda_element_corners": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_ip],
     "b200sp_dmda_global_node": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip],
     "b200sp_dmda_halo_plan": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip],
+    "b200sp_dmda_halo_push_table": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_ip, c_ip],
     "b200sp_dmda_create": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "b200sp_dmda_destroy": [_vp],
     "b200sp_dmda_get_info": [_vp, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip],
@@ -188,6 +189,16 @@ def dmda_halo_plan(M, N, size, rank):
     sr, sl = np.zeros(ns.value, dtype=np.int32), np.zeros(ns.value, dtype=np.int32)
     _chk(lib().b200sp_dmda_halo_plan(M, N, size, rank, C.byref(ng), _iptr(gg), _iptr(go), C.byref(ns), _iptr(sr), _iptr(sl)))
     return {"ghost_gnode": gg, "ghost_owner": go, "send_rank": sr, "send_lnode": sl}
+
+
+def dmda_halo_push_table(M, N, size, rank):
+    """Node-keyed send table (fused halo push): node_ent per owned node, entry -> (destination rank, position)."""
+    no, ne = C.c_int(), C.c_int()
+    _chk(lib().b200sp_dmda_halo_push_table(M, N, size, rank, C.byref(no), None, C.byref(ne), None, None))
+    ent = np.zeros(no.value, dtype=np.int32)
+    er, ep = np.zeros(ne.value, dtype=np.int32), np.zeros(ne.value, dtype=np.int32)
+    _chk(lib().b200sp_dmda_halo_push_table(M, N, size, rank, C.byref(no), _iptr(ent), C.byref(ne), _iptr(er), _iptr(ep)))
+    return {"node_ent": ent, "entry_rank": er, "entry_pos": ep}
 
 
 # ---------------------------------------------------------------- objects

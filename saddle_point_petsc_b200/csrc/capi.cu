@@ -221,32 +221,28 @@ int b200sp_dmda_halo_plan(int M, int N, int size, int rank, int *nghost, int *gh
   API_BEGIN
   Layout L(M, N, size);
   B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
-  const int pi = rank % L.m, pj = rank / L.m;
-  const int xs = L.xoff[pi], ys = L.yoff[pj], xm = L.lx[pi], ym = L.ly[pj];
-  // ghosts: the ring of width 1 around the owned box, clipped to the domain (box stencil -> corners included)
-  std::vector<std::pair<int, int>> gh; // (global node, owner)
-  for (int j = std::max(ys - 1, 0); j <= std::min(ys + ym, N - 1); ++j)
-    for (int i = std::max(xs - 1, 0); i <= std::min(xs + xm, M - 1); ++i)
-      if (i < xs || i >= xs + xm || j < ys || j >= ys + ym) gh.push_back({L.gnode(i, j), L.owner(i, j)});
-  std::sort(gh.begin(), gh.end()); // MPIAIJ garray order
-  if (nghost) *nghost = (int)gh.size();
-  if (ghost_gnode) for (size_t t = 0; t < gh.size(); ++t) ghost_gnode[t] = gh[t].first;
-  if (ghost_owner) for (size_t t = 0; t < gh.size(); ++t) ghost_owner[t] = gh[t].second;
-  // sends: for every neighbour rank q (ascending), the owned nodes inside q's ghost ring, ordered by OUR
-  // global id == the order in which they appear in q's sorted ghost list restricted to owner==rank
-  std::vector<std::pair<int, int>> snd; // (dest rank, local node)
-  for (int q = 0; q < size; ++q) {
-    if (q == rank) continue;
-    const int qi = q % L.m, qj = q / L.m;
-    const int qxs = L.xoff[qi], qys = L.yoff[qj], qxm = L.lx[qi], qym = L.ly[qj];
-    const int i0 = std::max(std::max(qxs - 1, 0), xs), i1 = std::min(std::min(qxs + qxm, M - 1), xs + xm - 1);
-    const int j0 = std::max(std::max(qys - 1, 0), ys), j1 = std::min(std::min(qys + qym, N - 1), ys + ym - 1);
-    for (int j = j0; j <= j1; ++j)
-      for (int i = i0; i <= i1; ++i) snd.push_back({q, (j - ys) * xm + (i - xs)});
-  }
-  if (nsend_total) *nsend_total = (int)snd.size();
-  if (send_rank) for (size_t t = 0; t < snd.size(); ++t) send_rank[t] = snd[t].first;
-  if (send_lnode) for (size_t t = 0; t < snd.size(); ++t) send_lnode[t] = snd[t].second;
+  const HaloPlan P = plan_halo(L, rank); // the same plan the device halo is built from
+  if (nghost) *nghost = (int)P.ghost_gnode.size();
+  if (ghost_gnode) std::copy(P.ghost_gnode.begin(), P.ghost_gnode.end(), ghost_gnode);
+  if (ghost_owner) std::copy(P.ghost_owner.begin(), P.ghost_owner.end(), ghost_owner);
+  if (nsend_total) *nsend_total = (int)P.send_lnode.size();
+  if (send_rank)
+    for (const HaloMsg &m : P.msgs)
+      for (int64_t k = 0; k < m.send_cnt; ++k) send_rank[m.send_off + k] = m.peer;
+  if (send_lnode) std::copy(P.send_lnode.begin(), P.send_lnode.end(), send_lnode);
+  API_END
+}
+int b200sp_dmda_halo_push_table(int M, int N, int size, int rank, int *n_owned, int *node_ent, int *n_entries, int *entry_rank, int *entry_pos) {
+  API_BEGIN
+  Layout L(M, N, size);
+  B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
+  const HaloPlan P = plan_halo(L, rank);
+  B2_REQUIRE(P.push_valid, "halo push table: a node goes to more than 3 neighbours (boxes thinner than 2 nodes)");
+  if (n_owned) *n_owned = P.n_owned;
+  if (node_ent) std::copy(P.push_node_ent.begin(), P.push_node_ent.begin() + P.n_owned, node_ent);
+  if (n_entries) *n_entries = (int)P.push_ent_msg.size();
+  if (entry_rank) for (size_t e = 0; e < P.push_ent_msg.size(); ++e) entry_rank[e] = e ? P.msgs[(size_t)P.push_ent_msg[e]].peer : -1;
+  if (entry_pos) std::copy(P.push_ent_pos.begin(), P.push_ent_pos.end(), entry_pos);
   API_END
 }
 int b200sp_dmda_create(b200sp_ctx ctx, int M, int N, b200sp_dmda *da) {

@@ -439,28 +439,14 @@ static void setup_p2p(Halo &h, const Layout &L, int rank) {
     q.peer_recv_off = pr.recv_off[slot];
     q.pad = 0;
   }
-  { // node-keyed send tables for pushes fused into producing kernels
-    const int ngrp = (h.n_owned + 63) / 64 + 1;
-    std::vector<unsigned char> grp((size_t)ngrp, 0);
-    std::vector<int> cnt((size_t)h.n_owned + 1, 0), first((size_t)h.n_owned + 1, 0), ent((size_t)h.n_owned + 1, 0);
-    for (int m = 0; m < h.n_msgs; ++m)
-      for (int64_t k = 0; k < h.node_msgs[(size_t)m].send_cnt; ++k) cnt[(size_t)h.h_send_lnode[(size_t)(h.node_msgs[(size_t)m].send_off + k)]]++;
-    int total = 1; // entry 0 is never used so that "0" can mean "none"
-    for (int v = 0; v < h.n_owned; ++v) { B2_REQUIRE(cnt[(size_t)v] <= 3, "halo: a node goes to more than 3 neighbours"); first[(size_t)v] = total; total += cnt[(size_t)v]; }
-    std::vector<int2> ents((size_t)total + 1, make_int2(0, 0));
-    std::vector<int> fill((size_t)h.n_owned + 1, 0);
-    for (int m = 0; m < h.n_msgs; ++m)
-      for (int64_t k = 0; k < h.node_msgs[(size_t)m].send_cnt; ++k) {
-        const int v = h.h_send_lnode[(size_t)(h.node_msgs[(size_t)m].send_off + k)];
-        ents[(size_t)(first[(size_t)v] + fill[(size_t)v]++)] = make_int2(m, (int)k);
-      }
-    for (int v = 0; v < h.n_owned; ++v)
-      if (cnt[(size_t)v]) { ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; grp[(size_t)(v >> 6)] = 1; }
-    h.d_push_grp.alloc(grp.size());
-    h.d_push_node_ent.alloc(ent.size());
-    h.d_push_ents.alloc(ents.size());
-    B2_CUDA(cudaMemcpyAsync(h.d_push_grp.p, grp.data(), grp.size(), cudaMemcpyHostToDevice, c->stream));
-    B2_CUDA(cudaMemcpyAsync(h.d_push_node_ent.p, ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, c->stream));
+  { // node-keyed send tables for pushes fused into producing kernels (built by plan_halo)
+    std::vector<int2> ents(h.h_push_ent_msg.size());
+    for (size_t e = 0; e < ents.size(); ++e) ents[e] = make_int2(h.h_push_ent_msg[e], h.h_push_ent_pos[e]);
+    h.d_push_grp.alloc(h.h_push_grp.size() + 1);
+    h.d_push_node_ent.alloc(h.h_push_node_ent.size() + 1);
+    h.d_push_ents.alloc(ents.size() + 1);
+    B2_CUDA(cudaMemcpyAsync(h.d_push_grp.p, h.h_push_grp.data(), h.h_push_grp.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(h.d_push_node_ent.p, h.h_push_node_ent.data(), sizeof(int) * h.h_push_node_ent.size(), cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaMemcpyAsync(h.d_push_ents.p, ents.data(), sizeof(int2) * ents.size(), cudaMemcpyHostToDevice, c->stream));
     c->sync();
   }
@@ -470,49 +456,82 @@ static void setup_p2p(Halo &h, const Layout &L, int rank) {
   h.p2p = true;
 }
 
-std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
-  auto h = std::make_shared<Halo>();
-  h->ctx = c;
-  h->M = L.M; h->N = L.N;
-  L.box(rank, &h->xs, &h->ys, &h->xm, &h->ym);
-  const int xs = h->xs, ys = h->ys, xm = h->xm, ym = h->ym;
-  B2_REQUIRE(L.size == 1 || (xm >= 2 && ym >= 2), "dmda: every rank must own at least 2 x 2 nodes");
-  h->n_owned = xm * ym;
+HaloPlan plan_halo(const Layout &L, int rank) {
+  HaloPlan P;
+  L.box(rank, &P.xs, &P.ys, &P.xm, &P.ym);
+  const int xs = P.xs, ys = P.ys, xm = P.xm, ym = P.ym;
+  P.n_owned = xm * ym;
+  // ghosts: the ring of width 1 around the owned box, clipped to the domain (box stencil -> corners included)
   struct G { int g, owner, i, j; };
   std::vector<G> gh;
   for (int j = std::max(ys - 1, 0); j <= std::min(ys + ym, L.N - 1); ++j)
     for (int i = std::max(xs - 1, 0); i <= std::min(xs + xm, L.M - 1); ++i)
       if (i < xs || i >= xs + xm || j < ys || j >= ys + ym) gh.push_back({L.gnode(i, j), L.owner(i, j), i, j});
   std::sort(gh.begin(), gh.end(), [](const G &a, const G &b) { return a.g < b.g; });
-  h->n_ghost = (int)gh.size();
-  std::vector<int> ring((size_t)(2 * (xm + 2) + 2 * ym), -1);
-  ColSpace cs{xs, ys, xm, ym, nullptr};
-  for (int t = 0; t < h->n_ghost; ++t) {
-    h->ghost_gnode.push_back(gh[(size_t)t].g);
-    h->ghost_i.push_back(gh[(size_t)t].i);
-    h->ghost_j.push_back(gh[(size_t)t].j);
-    ring[(size_t)cs.ring_id(gh[(size_t)t].i, gh[(size_t)t].j)] = t;
-  }
-  // messages: neighbours in ascending rank; receives are contiguous ranges of the sorted ghost list
-  std::vector<int> send_lnode;
+  for (const G &g : gh) { P.ghost_gnode.push_back(g.g); P.ghost_owner.push_back(g.owner); P.ghost_i.push_back(g.i); P.ghost_j.push_back(g.j); }
+  // messages: neighbours in ascending rank.  Sends: the owned nodes inside q's ghost ring in OUR global order, which is
+  // the order in which they appear in q's sorted ghost list restricted to owner == rank; receives: that range of ours.
   for (int q = 0; q < L.size; ++q) {
     if (q == rank) continue;
     int qxs, qys, qxm, qym;
     L.box(q, &qxs, &qys, &qxm, &qym);
     const int i0 = std::max(std::max(qxs - 1, 0), xs), i1 = std::min(std::min(qxs + qxm, L.M - 1), xs + xm - 1);
     const int j0 = std::max(std::max(qys - 1, 0), ys), j1 = std::min(std::min(qys + qym, L.N - 1), ys + ym - 1);
-    HaloMsg msg{q, (int64_t)send_lnode.size(), 0, 0, 0};
+    HaloMsg msg{q, (int64_t)P.send_lnode.size(), 0, 0, 0};
     for (int j = j0; j <= j1; ++j)
-      for (int i = i0; i <= i1; ++i) { send_lnode.push_back((j - ys) * xm + (i - xs)); msg.send_cnt++; }
+      for (int i = i0; i <= i1; ++i) { P.send_lnode.push_back((j - ys) * xm + (i - xs)); msg.send_cnt++; }
     int first = -1, cnt = 0;
-    for (int t = 0; t < h->n_ghost; ++t)
-      if (gh[(size_t)t].owner == q) { if (first < 0) first = t; cnt++; }
+    for (size_t t = 0; t < gh.size(); ++t)
+      if (gh[t].owner == q) { if (first < 0) first = (int)t; cnt++; }
     msg.recv_off = first < 0 ? 0 : first;
     msg.recv_cnt = cnt;
-    if (msg.send_cnt || msg.recv_cnt) h->node_msgs.push_back(msg);
+    if (msg.send_cnt || msg.recv_cnt) P.msgs.push_back(msg);
   }
+  // node-keyed send tables
+  const int n = P.n_owned;
+  P.push_grp.assign((size_t)(n + 63) / 64 + 1, 0);
+  P.push_node_ent.assign((size_t)n + 1, 0);
+  std::vector<int> cnt((size_t)n + 1, 0), first((size_t)n + 1, 0), fill((size_t)n + 1, 0);
+  for (const HaloMsg &m : P.msgs)
+    for (int64_t k = 0; k < m.send_cnt; ++k) cnt[(size_t)P.send_lnode[(size_t)(m.send_off + k)]]++;
+  int total = 1; // entry 0 is never used so that "0" can mean "none"
+  for (int v = 0; v < n; ++v) {
+    if (cnt[(size_t)v] > 3) P.push_valid = false; // boxes thinner than 2 nodes: the 2-bit count cannot hold it (no fused push, no peer-to-peer)
+    first[(size_t)v] = total;
+    total += cnt[(size_t)v];
+  }
+  P.push_ent_msg.assign((size_t)total, 0);
+  P.push_ent_pos.assign((size_t)total, 0);
+  for (size_t mi = 0; mi < P.msgs.size(); ++mi)
+    for (int64_t k = 0; k < P.msgs[mi].send_cnt; ++k) {
+      const int v = P.send_lnode[(size_t)(P.msgs[mi].send_off + k)];
+      const int e = first[(size_t)v] + fill[(size_t)v]++;
+      P.push_ent_msg[(size_t)e] = (int)mi;
+      P.push_ent_pos[(size_t)e] = (int)k;
+    }
+  for (int v = 0; v < n; ++v)
+    if (cnt[(size_t)v] && P.push_valid) { P.push_node_ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; P.push_grp[(size_t)(v >> 6)] = 1; }
+  return P;
+}
+
+std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
+  auto h = std::make_shared<Halo>();
+  h->ctx = c;
+  h->M = L.M; h->N = L.N;
+  HaloPlan P = plan_halo(L, rank);
+  h->xs = P.xs; h->ys = P.ys; h->xm = P.xm; h->ym = P.ym;
+  const int xs = h->xs, ys = h->ys, xm = h->xm, ym = h->ym;
+  B2_REQUIRE(L.size == 1 || (xm >= 2 && ym >= 2), "dmda: every rank must own at least 2 x 2 nodes");
+  h->n_owned = P.n_owned;
+  h->n_ghost = (int)P.ghost_gnode.size();
+  h->ghost_gnode = P.ghost_gnode; h->ghost_i = P.ghost_i; h->ghost_j = P.ghost_j;
+  std::vector<int> ring((size_t)(2 * (xm + 2) + 2 * ym), -1);
+  ColSpace cs{xs, ys, xm, ym, nullptr};
+  for (int t = 0; t < h->n_ghost; ++t) ring[(size_t)cs.ring_id(P.ghost_i[(size_t)t], P.ghost_j[(size_t)t])] = t;
+  h->node_msgs = P.msgs;
+  const std::vector<int> &send_lnode = P.send_lnode;
+  h->h_push_grp = P.push_grp; h->h_push_node_ent = P.push_node_ent; h->h_push_ent_msg = P.push_ent_msg; h->h_push_ent_pos = P.push_ent_pos;
   h->n_send = (int)send_lnode.size();
-  h->h_send_lnode = send_lnode;
   h->d_send_lnode.alloc((size_t)h->n_send + 1);
   h->d_ring2ghost.alloc(ring.size() + 1);
   if (h->n_send) B2_CUDA(cudaMemcpyAsync(h->d_send_lnode.p, send_lnode.data(), sizeof(int) * send_lnode.size(), cudaMemcpyHostToDevice, c->stream));
@@ -526,6 +545,7 @@ std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
   // every message must carry data in both directions for the flag protocol (true for a box-stencil ring)
   bool symmetric = true;
   for (const HaloMsg &m : h->node_msgs) symmetric = symmetric && m.send_cnt > 0 && m.recv_cnt > 0;
+  symmetric = symmetric && P.push_valid;
   if (c->dcomm && c->dcomm->p2p_capable() && L.size > 1 && symmetric) setup_p2p(*h, L, rank);
   return h;
 }

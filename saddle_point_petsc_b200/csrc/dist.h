@@ -77,6 +77,23 @@ struct Layout {
   Layout coarsen() const;
 };
 
+// ---------------------------------------------------------------- halo plan (host index arithmetic only)
+// Everything a rank needs to know about its box-stencil halo on a layout.  One implementation serves the device halo
+// (make_halo), the host-only C ABI (b200sp_dmda_halo_plan / b200sp_dmda_halo_push_table) and therefore the CPU tests.
+struct HaloPlan {
+  int xs = 0, ys = 0, xm = 0, ym = 0, n_owned = 0;
+  std::vector<int> ghost_gnode, ghost_owner, ghost_i, ghost_j; // ascending PETSc global node id (MPIAIJ garray order)
+  std::vector<HaloMsg> msgs;      // one per neighbour, ascending rank; offsets/counts in NODES; receives are
+                                  // contiguous ranges of the sorted ghost list
+  std::vector<int> send_lnode;    // owned local node ids to send, grouped by message, in the receiver's ghost order
+  // node-keyed view of the send lists (pushes fused into producing kernels, PushOut in core.h)
+  std::vector<unsigned char> push_grp; // per 64 owned nodes: any of them sent?
+  std::vector<int> push_node_ent;      // per owned node: (first entry << 2) | count (<= 3); 0 = not sent
+  std::vector<int> push_ent_msg, push_ent_pos; // entry -> message index, position inside that message; entry 0 unused
+  bool push_valid = true;              // false when some node has more than 3 destinations (boxes thinner than 2 nodes)
+};
+HaloPlan plan_halo(const Layout &L, int rank);
+
 // ---------------------------------------------------------------- halo of one rank on one layout
 struct Halo {
   Ctx *ctx = nullptr;
@@ -102,7 +119,8 @@ struct Halo {
   DevBuf<P2PMsg> d_p2p;                           // per outgoing message
   std::vector<void *> ipc_opened;
   // fused push (PushOut in core.h): which owned nodes go where, keyed by node
-  std::vector<int> h_send_lnode;
+  std::vector<unsigned char> h_push_grp;          // host copies of the plan's push tables, uploaded by the peer-to-peer setup
+  std::vector<int> h_push_node_ent, h_push_ent_msg, h_push_ent_pos;
   DevBuf<unsigned char> d_push_grp;
   DevBuf<int> d_push_node_ent;
   DevBuf<int2> d_push_ents;

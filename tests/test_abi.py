@@ -75,6 +75,38 @@ def test_halo_plan_is_consistent_across_ranks(M, N, size):
             assert sent == want.tolist()
 
 
+@pytest.mark.parametrize("M,N,size", [(5, 5, 4), (9, 7, 2), (12, 9, 8), (33, 33, 8), (6, 6, 1), (64, 48, 6)])
+def test_halo_push_table_is_the_send_list_keyed_by_node(M, N, size):
+    """A kernel that pushes the halo while it PRODUCES the vector looks its rows up in this table: every (node ->
+    destination rank, position) entry must be exactly one element of the per-neighbour send lists, position = index of
+    the node inside the message (= inside the neighbour's receive range for this rank), nothing missing, nothing extra."""
+    for r in range(size):
+        plan = sp.dmda_halo_plan(M, N, size, r)
+        tab = sp.dmda_halo_push_table(M, N, size, r)
+        xs, ys, xm, ym = sp.dmda_corners(M, N, size, r)
+        assert len(tab["node_ent"]) == xm * ym
+        want = {}                                             # (node, dest) -> position inside the message to dest
+        for q in np.unique(plan["send_rank"]):
+            nodes = plan["send_lnode"][plan["send_rank"] == q]
+            for pos, v in enumerate(nodes):
+                assert (int(v), int(q)) not in want
+                want[(int(v), int(q))] = pos
+        got = {}
+        for v, e in enumerate(tab["node_ent"]):
+            first, cnt = int(e) >> 2, int(e) & 3
+            assert (e == 0) == (cnt == 0)
+            for k in range(cnt):
+                key = (v, int(tab["entry_rank"][first + k]))
+                assert key not in got and first + k >= 1
+                got[key] = int(tab["entry_pos"][first + k])
+        assert got == want
+        assert len(tab["entry_rank"]) == 1 + len(want)        # entry 0 is the unused "none" slot
+        # only boundary nodes of the owned box are ever sent
+        for (v, _q) in want:
+            i, j = v % xm, v // xm
+            assert i in (0, xm - 1) or j in (0, ym - 1)
+
+
 def test_no_cpu_fallback():
     try:
         import torch
