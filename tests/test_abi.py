@@ -118,3 +118,35 @@ def test_no_cpu_fallback():
     with pytest.raises(sp.B200spError) as e:
         sp.Context()
     assert e.value.code == 2  # B200SP_ERR_NO_DEVICE
+
+
+def test_partition_and_halo_fuzz_against_oracle():
+    """Property test over random grids and rank counts (hypothesis): process grid, ownership, element ranges and the
+    PETSc numbering equal the oracle's, and every ghost of every rank is sent by exactly its owner."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.integers(3, 70), st.integers(3, 70), st.integers(1, 12))
+    def run(M, N, size):
+        m, n = sp.dmda_proc_grid(M, N, size)
+        assert (m, n) == so.dmda_proc_grid(M, N, size) and m * n == size
+        lx, ly = sp.dmda_ownership(M, m), sp.dmda_ownership(N, n)
+        assert lx.tolist() == so.dmda_ownership(M, m).tolist() and ly.tolist() == so.dmda_ownership(N, n).tolist()
+        assert lx.sum() == M and ly.sum() == N
+        if lx.min() < 1 or ly.min() < 1:
+            return                                            # more ranks than nodes in a direction: PETSc errors out too
+        nm, ow = so.dmda_natural_to_petsc(M, N, size)
+        for r in range(size):
+            assert sp.dmda_element_corners(M, N, size, r) == so.dmda_element_range(M, N, size, r)
+        for (i, j) in ((0, 0), (M - 1, N - 1), (M // 2, N // 3), (M - 1, 0)):
+            assert sp.dmda_global_node(M, N, size, i, j) == (nm[j * M + i], ow[j * M + i])
+        plans = [sp.dmda_halo_plan(M, N, size, r) for r in range(size)]
+        nsent = sum(len(p["send_lnode"]) for p in plans)
+        nghost = sum(len(p["ghost_gnode"]) for p in plans)
+        assert nsent == nghost                                 # every ghost value is sent exactly once
+        for q in range(size):
+            for p in range(size):
+                if p != q:
+                    assert (plans[q]["ghost_owner"] == p).sum() == (plans[p]["send_rank"] == q).sum()
+
+    run()
