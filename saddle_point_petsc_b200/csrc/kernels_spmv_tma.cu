@@ -624,8 +624,6 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   if (per_sm < 1) per_sm = 1;
   if (per_sm * R > 2048) per_sm = 2048 / R;
   int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
-  const double mean = A.nrows ? (double)A.nnz / A.nrows : 0.0;
-  (void)mean;
   if (A.dict_state == 0) { // lazily, never while a CUDA graph is being recorded
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     B2_CUDA(cudaStreamIsCapturing(c->stream, &st));
