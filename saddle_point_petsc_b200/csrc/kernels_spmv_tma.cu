@@ -385,7 +385,7 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
 // count pass sizes the dictionaries, the write pass fills dictionaries and codes.
 __global__ void __launch_bounds__(256) k_dict_build(int nrows, int R, const int *__restrict__ rowptr, const double *__restrict__ val, int write,
                                                     int *dcnt, const int *__restrict__ dptr, double *dict, unsigned short *codes, int *stat) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+  extern __shared__ __align__(128) unsigned char s_raw[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
   int *minpos = reinterpret_cast<int *>(keys + DICT_T);
   unsigned short *rank = reinterpret_cast<unsigned short *>(minpos + DICT_T);
