@@ -76,10 +76,6 @@ static void v_scale(int n, double a, double *y) {
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n; ++i) y[i] *= a;
 }
-static void v_waxpy(int n, double a, const double *x, const double *y, double *w) { /* w = a x + y */
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < n; ++i) w[i] = a * x[i] + y[i];
-}
 static int v_bad(double r) { return isnan(r) || isinf(r); }
 
 void or_hash_vector(int n, double *v) {
