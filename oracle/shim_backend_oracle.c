@@ -10,6 +10,8 @@
 
 struct shimbk_mat_s { OrCsr *A; int M, N, dof; };
 static char g_err[512];
+static double *g_hist = NULL;
+static int g_hist_len = 0;
 const char *shimbk_name(void) { return "sp_oracle (CPU, test infrastructure)"; }
 const char *shimbk_last_error(void) { return g_err; }
 int shimbk_init(void) { return 0; }
@@ -93,8 +95,18 @@ int shimbk_ksp_solve(shimbk_mat A, const char *options, int n, const double *b, 
   if ((v = find_opt(options, "ksp_max_it", buf, sizeof(buf)))) k->max_it = atoi(v);
   if ((v = find_opt(options, "ksp_gmres_restart", buf, sizeof(buf)))) k->restart = atoi(v);
   (void)n;
+  or_ksp_set_history(k, k->max_it + 2 + k->max_it / (k->restart > 0 ? k->restart : 1));
   or_ksp_solve(k, b, x, 0);
   *its = k->its; *reason = k->reason; *rnorm = k->rnorm;
+  free(g_hist);
+  g_hist_len = k->hist_len;
+  g_hist = (double *)malloc(sizeof(double) * (size_t)(g_hist_len > 0 ? g_hist_len : 1));
+  for (int i = 0; i < g_hist_len; ++i) g_hist[i] = k->hist[i];
   or_ksp_free(k); or_op_free(Aop); if (M) or_op_free(M);
+  return 0;
+}
+int shimbk_ksp_history(double *hist, int cap, int *len) {
+  if (len) *len = g_hist_len;
+  if (hist) for (int i = 0; i < g_hist_len && i < cap; ++i) hist[i] = g_hist[i];
   return 0;
 }

@@ -456,6 +456,19 @@ PetscErrorCode KSPCreate(MPI_Comm comm, KSP *ksp) { (void)comm; *ksp = (KSP)call
 PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P) { ksp->A = A; ksp->P = P; return 0; }
 PetscErrorCode KSPSetFromOptions(KSP ksp) { (void)ksp; return 0; } /* options are read at solve time from the database */
 PetscErrorCode KSPSetUp(KSP ksp) { if (!ksp->A) return SHIM_ERR("KSPSetUp: operators not set"); return 0; }
+static const char *ksp_reason_name(int r) { /* KSPConvergedReasons[] spellings */
+  switch (r) {
+  case 2: return "CONVERGED_RTOL";
+  case 3: return "CONVERGED_ATOL";
+  case 4: return "CONVERGED_ITS";
+  case -3: return "DIVERGED_ITS";
+  case -4: return "DIVERGED_DTOL";
+  case -5: return "DIVERGED_BREAKDOWN";
+  case -8: return "DIVERGED_INDEFINITE_PC";
+  case -9: return "DIVERGED_NANORINF";
+  default: return r > 0 ? "CONVERGED_UNKNOWN" : "DIVERGED_UNKNOWN";
+  }
+}
 PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
   if (!ksp->A || !ksp->A->bk) return SHIM_ERR("KSPSolve: operator not assembled");
   if (ksp->A != ksp->P) return SHIM_ERR("KSPSolve: Amat != Pmat is not supported by the shim (the reference passes A,A)");
@@ -464,9 +477,22 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
   int rc = shimbk_ksp_solve(ksp->A->bk, opts, b->n, b->a, x->a, &ksp->its, &ksp->reason, &ksp->rnorm);
   free(opts);
   if (rc) { fprintf(stderr, "[petsc-shim] back end '%s' error: %s\n", shimbk_name(), shimbk_last_error()); return 76; }
+  if (opt_get("ksp_monitor")) { /* KSPMonitorResidual's line format; GMRES-type methods log the cycle start again at every restart */
+    int len = 0;
+    shimbk_ksp_history(NULL, 0, &len);
+    double *h = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+    shimbk_ksp_history(h, len, &len);
+    const char *t = opt_get("ksp_type"), *rs = opt_get("ksp_gmres_restart");
+    const int gmres_like = !t || !strcmp(t, "gmres") || !strcmp(t, "fgmres"); /* KSPGMRES is the default type */
+    const int restart = rs ? atoi(rs) : 30;
+    for (int i = 0; i < len; ++i) {
+      const int it = gmres_like && restart > 0 ? (i / (restart + 1)) * restart + i % (restart + 1) : i;
+      printf("%3d KSP Residual norm %14.12e \n", it, h[i]);
+    }
+    free(h);
+  }
   if (opt_get("ksp_converged_reason"))
-    printf("Linear solve %s due to reason %d iterations %d\n", ksp->reason > 0 ? "converged" : "did not converge", ksp->reason, ksp->its);
-  if (opt_get("ksp_monitor")) printf("  final KSP residual norm %.12e after %d iterations\n", ksp->rnorm, ksp->its);
+    printf("Linear solve %s due to %s iterations %d\n", ksp->reason > 0 ? "converged" : "did not converge", ksp_reason_name(ksp->reason), ksp->its);
   return 0;
 }
 PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its) { *its = ksp->its; return 0; }

@@ -1,4 +1,4 @@
-/* shim_backend.h -- the six operations the PETSc shim (petsc_shim.c) needs from a solver back end.
+/* shim_backend.h -- the operations the PETSc shim (petsc_shim.c) needs from a solver back end.
  * Selected at LINK time:
  *   saddle_point_petsc_b200/csrc/shim_backend_b200sp.c  -> libb200sp C ABI (the product, GPU only)
  *   oracle/shim_backend_oracle.c                        -> the CPU oracle (test infrastructure, oracle/_ref only)
@@ -25,6 +25,10 @@ int shimbk_mat_get_csr(shimbk_mat A, int *nrows, long *nnz, int *rowptr, int *co
 int shimbk_mat_destroy(shimbk_mat A);
 /* KSPSetFromOptions + KSPSetUp + KSPSolve with host vectors; options is PETSc options-database text */
 int shimbk_ksp_solve(shimbk_mat A, const char *options, int n, const double *b, double *x, int *its, int *reason, double *rnorm);
+
+/* residual history of the last shimbk_ksp_solve (what KSPMonitor would have been called with, in order; GMRES/FGMRES log
+ * the recomputed residual again at the start of every restart cycle).  hist may be NULL to query the length. */
+int shimbk_ksp_history(double *hist, int cap, int *len);
 
 #ifdef __cplusplus
 }

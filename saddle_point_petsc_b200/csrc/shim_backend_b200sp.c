@@ -8,6 +8,8 @@
 struct shimbk_mat_s { b200sp_mat m; };
 static b200sp_ctx g_ctx = NULL;
 static char g_err[1024];
+static double *g_hist = NULL;
+static int g_hist_len = 0;
 
 #define CK(call) do { int rc_ = (call); if (rc_) { snprintf(g_err, sizeof(g_err), "%s -> %d: %s", #call, rc_, b200sp_last_error()); return rc_; } } while (0)
 
@@ -51,7 +53,22 @@ int shimbk_ksp_solve(shimbk_mat A, const char *options, int n, const double *b, 
   if (!rc) rc = b200sp_ksp_get_iteration_number(ksp, its);
   if (!rc) rc = b200sp_ksp_get_converged_reason(ksp, reason);
   if (!rc) rc = b200sp_ksp_get_residual_norm(ksp, rnorm);
+  if (!rc) { /* keep the residual history for -ksp_monitor */
+    int len = 0;
+    rc = b200sp_ksp_get_residual_history(ksp, NULL, 0, &len);
+    if (!rc) {
+      free(g_hist);
+      g_hist = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+      g_hist_len = 0;
+      rc = b200sp_ksp_get_residual_history(ksp, g_hist, len, &g_hist_len);
+    }
+  }
   if (rc) snprintf(g_err, sizeof(g_err), "KSP -> %d: %s", rc, b200sp_last_error());
   b200sp_ksp_destroy(&ksp);
   return rc;
+}
+int shimbk_ksp_history(double *hist, int cap, int *len) {
+  if (len) *len = g_hist_len;
+  if (hist) for (int i = 0; i < g_hist_len && i < cap; ++i) hist[i] = g_hist[i];
+  return 0;
 }
