@@ -26,6 +26,7 @@ typedef struct b200sp_vec_s *b200sp_vec;
 typedef struct b200sp_mat_s *b200sp_mat;
 typedef struct b200sp_ksp_s *b200sp_ksp;
 typedef struct b200sp_dmda_s *b200sp_dmda;
+typedef struct b200sp_pc_s *b200sp_pc;
 
 enum {
   B200SP_OK = 0,
@@ -150,6 +151,9 @@ int b200sp_mat_mult(b200sp_mat A, b200sp_vec x, b200sp_vec y);              /* M
 int b200sp_mat_mult_add(b200sp_mat A, b200sp_vec x, b200sp_vec y, b200sp_vec z); /* MatMultAdd: z = y + A x */
 int b200sp_mat_residual(b200sp_mat A, b200sp_vec b, b200sp_vec x, b200sp_vec r); /* r = b - A x (fused) */
 int b200sp_mat_get_diagonal(b200sp_mat A, b200sp_vec d);                    /* MatGetDiagonal */
+/* MatMultTranspose: y = A^T x.  The explicit transpose is built on the device once per value state and cached, so the
+ * entries of a column are added by ascending row -- the order of PETSc's sequential scatter loop.  Single rank only. */
+int b200sp_mat_mult_transpose(b200sp_mat A, b200sp_vec x, b200sp_vec y);
 int b200sp_mat_transpose(b200sp_mat A, b200sp_mat *At);                     /* MatTranspose (explicit) */
 int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C);          /* MatMatMult (device SpGEMM) */
 /* MatZeroRowsColumns(A,n,rows,diag,NULL,NULL): local row ids; pattern preserved (Appendix A.4) */
@@ -192,6 +196,18 @@ int b200sp_ksp_get_iteration_number(b200sp_ksp ksp, int *its);
 int b200sp_ksp_get_residual_norm(b200sp_ksp ksp, double *rnorm);
 int b200sp_ksp_get_converged_reason(b200sp_ksp ksp, int *reason);
 int b200sp_ksp_get_residual_history(b200sp_ksp ksp, double *hist, int cap, int *len);
+/* ---- PC as an object of its own: what a PETSc PCRegister'ed type binds (PCSetOperators / PCSetFromOptions /
+ *      PCSetUp / PCApply / PCView / PCDestroy); the reference reaches it through KSPSetFromOptions
+ *      (src/SaddlePointProblem.c:67) and -pc_type.  Same options text, same setup, same kernels as inside a KSP. ---- */
+int b200sp_pc_create(b200sp_ctx ctx, b200sp_pc *pc);
+int b200sp_pc_destroy(b200sp_pc *pc);
+int b200sp_pc_set_operators(b200sp_pc pc, b200sp_mat Amat, b200sp_mat Pmat);
+int b200sp_pc_set_options(b200sp_pc pc, const char *options);      /* "-pc_type fieldsplit -pc_fieldsplit_schur_fact_type upper ..." */
+int b200sp_pc_set_schur_user_mat(b200sp_pc pc, b200sp_mat Q);
+int b200sp_pc_set_dmda(b200sp_pc pc, b200sp_dmda da);
+int b200sp_pc_setup(b200sp_pc pc);
+int b200sp_pc_apply(b200sp_pc pc, b200sp_vec x, b200sp_vec y);     /* y = M^-1 x */
+int b200sp_pc_view(b200sp_pc pc, char *buf, int buflen);
 /* apply only the preconditioner / only the operator (parity tests of PCApply / MatMult on nests) */
 int b200sp_ksp_pc_apply(b200sp_ksp ksp, b200sp_vec x, b200sp_vec y);
 int b200sp_ksp_view(b200sp_ksp ksp, char *buf, int buflen);

@@ -96,6 +96,16 @@ _SIGS = {
     "b200sp_assemble_rhs": [_vp, C.c_int, C.c_int, _vp],
     "b200sp_assemble_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_interp_q1": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
+    "b200sp_mat_mult_transpose": [_vp, _vp, _vp],
+    "b200sp_pc_create": [_vp, C.POINTER(_vp)],
+    "b200sp_pc_destroy": [C.POINTER(_vp)],
+    "b200sp_pc_set_operators": [_vp, _vp, _vp],
+    "b200sp_pc_set_options": [_vp, C.c_char_p],
+    "b200sp_pc_set_schur_user_mat": [_vp, _vp],
+    "b200sp_pc_set_dmda": [_vp, _vp],
+    "b200sp_pc_setup": [_vp],
+    "b200sp_pc_apply": [_vp, _vp, _vp],
+    "b200sp_pc_view": [_vp, C.c_char_p, C.c_int],
     "b200sp_ksp_create": [_vp, C.POINTER(_vp)],
     "b200sp_ksp_destroy": [C.POINTER(_vp)],
     "b200sp_ksp_set_operators": [_vp, _vp, _vp],
@@ -441,6 +451,9 @@ class Mat:
     def mult(self, x, y):
         _chk(lib().b200sp_mat_mult(self.h, x.h, y.h))
 
+    def mult_transpose(self, x, y):
+        _chk(lib().b200sp_mat_mult_transpose(self.h, x.h, y.h))
+
     def mult_add(self, x, y, z):
         _chk(lib().b200sp_mat_mult_add(self.h, x.h, y.h, z.h))
 
@@ -515,6 +528,46 @@ class DMDA:
         if self.h:
             _chk(lib().b200sp_dmda_destroy(self.h))
             self.h = _vp()
+
+
+class PC:
+    """PCCreate / PCSetOperators / PCSetFromOptions / PCSetUp / PCApply as an object of its own."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = _vp()
+        _chk(lib().b200sp_pc_create(ctx.h, C.byref(self.h)))
+        self._keep = []
+
+    def set_operators(self, A, P=None):
+        P = A if P is None else P
+        self._keep += [A, P]
+        _chk(lib().b200sp_pc_set_operators(self.h, A.h, P.h))
+
+    def set_options(self, text):
+        _chk(lib().b200sp_pc_set_options(self.h, text.encode()))
+
+    def set_schur_user_mat(self, Q):
+        self._keep.append(Q)
+        _chk(lib().b200sp_pc_set_schur_user_mat(self.h, Q.h))
+
+    def set_dmda(self, da):
+        _chk(lib().b200sp_pc_set_dmda(self.h, da.h))
+
+    def setup(self):
+        _chk(lib().b200sp_pc_setup(self.h))
+
+    def apply(self, x, y):
+        _chk(lib().b200sp_pc_apply(self.h, x.h, y.h))
+
+    def view(self):
+        buf = C.create_string_buffer(1 << 16)
+        _chk(lib().b200sp_pc_view(self.h, buf, len(buf)))
+        return buf.value.decode()
+
+    def destroy(self):
+        if self.h:
+            _chk(lib().b200sp_pc_destroy(C.byref(self.h)))
 
 
 class KSP:

@@ -11,8 +11,13 @@ using namespace b200sp;
 
 struct b200sp_ctx_s { Ctx c; };
 struct b200sp_vec_s { Vec v; b200sp_vec_s(Ctx *c, int64_t n) : v(c, n) {} };
-struct b200sp_mat_s { Mat m; };
+struct b200sp_mat_s {
+  Mat m;
+  std::shared_ptr<Csr> t; // explicit transpose cached by b200sp_mat_mult_transpose, valid for the value state t_state
+  int64_t t_state = -1;
+};
 struct b200sp_ksp_s { Solver s; explicit b200sp_ksp_s(Ctx *c) : s(c) {} };
+struct b200sp_pc_s { Solver s; explicit b200sp_pc_s(Ctx *c) : s(c) {} }; // a PC is the preconditioner half of the same solver object
 struct b200sp_dmda_s { Dmda d; };
 
 static thread_local std::string g_last_error;
@@ -502,6 +507,17 @@ int b200sp_mat_get_diagonal(b200sp_mat A, b200sp_vec d) {
   csr_get_diagonal(M, d->v.d);
   API_END
 }
+int b200sp_mat_mult_transpose(b200sp_mat A, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN
+  Csr &M = plain(A);
+  B2_REQUIRE(!M.halo, "MatMultTranspose: not available for row-partitioned matrices (assemble the transpose explicitly)");
+  B2_REQUIRE(x->v.n == M.nrows && y->v.n == M.ncols && x != y, "MatMultTranspose: size mismatch or aliasing");
+  // the transpose is built once per value state by the stable device sort; its rows list the entries of a column of A by
+  // ascending row, i.e. the order in which MatMultTranspose_SeqAIJ adds them -> same bits as the sequential scatter loop
+  if (!A->t || A->t_state != M.state) { A->t = csr_transpose(M); A->t_state = M.state; }
+  csr_spmv(*A->t, x->v.d, y->v.d);
+  API_END
+}
 int b200sp_mat_transpose(b200sp_mat A, b200sp_mat *At) { API_BEGIN *At = wrap(A->m.ctx, csr_transpose(plain(A))); API_END }
 int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C) { API_BEGIN *C = wrap(A->m.ctx, csr_matmat(plain(A), plain(B))); API_END }
 int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag) {
@@ -617,6 +633,41 @@ int b200sp_ksp_pc_apply(b200sp_ksp ksp, b200sp_vec x, b200sp_vec y) {
   if (ksp->s.outer_pc) ksp->s.outer_pc->apply(x->v.d, y->v.d);
   else vec_copy(ksp->s.ctx, x->v.n, x->v.d, y->v.d);
   ksp->s.ctx->sync();
+  API_END
+}
+// ---- PC as an object of its own (PCCreate / PCSetOperators / PCSetFromOptions / PCSetUp / PCApply / PCDestroy)
+int b200sp_pc_create(b200sp_ctx ctx, b200sp_pc *pc) { API_BEGIN B2_REQUIRE(ctx && pc, "pc_create: bad arguments"); *pc = new b200sp_pc_s(&ctx->c); API_END }
+int b200sp_pc_destroy(b200sp_pc *pc) {
+  API_BEGIN
+  if (pc && *pc) { (*pc)->s.ctx->sync(); delete *pc; *pc = nullptr; }
+  API_END
+}
+int b200sp_pc_set_operators(b200sp_pc pc, b200sp_mat Amat, b200sp_mat Pmat) {
+  API_BEGIN
+  B2_REQUIRE(pc && Amat && Pmat, "PCSetOperators: null argument");
+  pc->s.Amat = &Amat->m; pc->s.Pmat = &Pmat->m; pc->s.is_setup = false;
+  API_END
+}
+int b200sp_pc_set_options(b200sp_pc pc, const char *options) { API_BEGIN pc->s.set_options(options); pc->s.is_setup = false; API_END }
+int b200sp_pc_set_schur_user_mat(b200sp_pc pc, b200sp_mat Q) { API_BEGIN pc->s.schur_user = plain(Q).ctx ? Q->m.csr : nullptr; pc->s.is_setup = false; API_END }
+int b200sp_pc_set_dmda(b200sp_pc pc, b200sp_dmda da) { API_BEGIN pc->s.have_grid = true; pc->s.grid_M = da->d.M; pc->s.grid_N = da->d.N; API_END }
+int b200sp_pc_setup(b200sp_pc pc) { API_BEGIN pc->s.setup(); API_END }
+int b200sp_pc_apply(b200sp_pc pc, b200sp_vec x, b200sp_vec y) {
+  API_BEGIN
+  if (!pc->s.current()) pc->s.setup();
+  B2_REQUIRE(x->v.n == pc->s.outer->n && y->v.n == x->v.n && x != y, "PCApply: size mismatch or aliasing");
+  if (pc->s.outer_pc) pc->s.outer_pc->apply(x->v.d, y->v.d);
+  else vec_copy(pc->s.ctx, x->v.n, x->v.d, y->v.d); // PCNONE
+  pc->s.ctx->sync();
+  API_END
+}
+int b200sp_pc_view(b200sp_pc pc, char *buf, int buflen) {
+  API_BEGIN
+  B2_REQUIRE(buf && buflen > 0, "pc_view: no buffer");
+  const std::string s = pc->s.outer_pc ? pc->s.outer_pc->view(0) : std::string(pc->s.is_setup ? "PC none\n" : "PC not set up\n");
+  const size_t n = std::min(s.size(), (size_t)buflen - 1);
+  std::memcpy(buf, s.c_str(), n);
+  buf[n] = 0;
   API_END
 }
 int b200sp_ksp_view(b200sp_ksp ksp, char *buf, int buflen) {
