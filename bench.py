@@ -8,12 +8,22 @@ A "step" is one complete KSPSolve (zero initial guess, rtol 1e-8) of the assembl
   value   = seconds per solve with b and x resident in HBM (CUDA events on the library's compute stream)
   e2e     = the same solve through the C-ABI host-buffer entry point b200sp_ksp_solve_host: H2D copy of
             the right-hand side from pinned memory and D2H copy of the solution inside the timed region
-  roofline= the A-block SpMV kernel: algorithmic bytes (12 nnz + 4(rows+1) + 8 rows + 8 cols) / its average
-            launch duration measured with CUDA events DURING a solve, against MEASURED_PEAKS.json
+  roofline= the A-block SpMV kernel.  `frac` is the MOVED-bytes fraction of the measured HBM peak: bytes of the
+            stored (losslessly compressed) matrix format + x + y + the epilogue's operand vectors, per launch
+            variant (plain / axpby / cheb), over the CUDA-event time of those launches DURING a solve.  The
+            CSR-algorithmic rate (12 nnz + 4(rows+1) + 8 rows + 8 cols per launch) is kept next to it
+            as `csr_algorithmic_gbs` / `speedup_vs_csr_roofline`: it exceeds 1 because the kernel does not move
+            the CSR bytes.
+  parity  = (N=1) the same system solved by the CPU oracle: iteration counts, final relative residuals and the
+            solutions compared at north_star's tolerances (+-1, 1e-10, 1e-8); the process exits non-zero when
+            they are not met.  (N>1) `dist_check`: before the timed region every rank checks, at a small size,
+            its rows of every distributed matrix bit for bit against the oracle, distributed MatMult on both
+            ghost-buffer parities, and one distributed solve against the oracle.
   cpu_baseline = the CPU oracle (a port of the PETSc algorithms the reference selects; PETSc itself is not
             installable here) on the host cores of the GPU box, same workload.
---impl reference times that CPU oracle as the reference arm (oracle/ is test infrastructure; this and
-cpu_baseline are the only places bench.py touches it).
+--impl reference times that CPU oracle as the reference arm (oracle/ is test infrastructure; this, `parity`,
+`dist_check` and cpu_baseline are the only places bench.py touches it).
+--config sweep runs BASELINE config 5 (SpMV / vector-kernel bandwidth sweep) instead of a solve.
 """
 import argparse
 import json
@@ -28,25 +38,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FS = ("-pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type {fact} -pc_fieldsplit_schur_precondition user "
+      "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {{levels}} "
+      "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
 CONFIGS = {
     # BASELINE config 3: FGMRES(30), right PC, Schur factorisation with a multigrid A00 solve and the
     # pressure-mass-matrix Schur approximation
-    "fgmres_schur_mg": ("-ksp_type fgmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur "
-                        "-pc_fieldsplit_schur_fact_type upper -pc_fieldsplit_schur_precondition user "
-                        "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {levels} "
-                        "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
+    "fgmres_schur_mg": "-ksp_type fgmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 " + FS.format(fact="upper"),
     # BASELINE config 2: GMRES(30), left PC, Schur full factorisation (multigrid instead of plain Jacobi for
     # A00 so that it converges at this size)
-    "gmres_schur_mg": ("-ksp_type gmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur "
-                       "-pc_fieldsplit_schur_fact_type full -pc_fieldsplit_schur_precondition user "
-                       "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {levels} "
-                       "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
+    "gmres_schur_mg": "-ksp_type gmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 " + FS.format(fact="full"),
     # BASELINE config 4 (2-D analogue): MINRES + block-diagonal, Chebyshev/Jacobi smoothed multigrid
-    "minres_diag_mg": ("-ksp_type minres -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur "
-                       "-pc_fieldsplit_schur_fact_type diag -pc_fieldsplit_schur_precondition user "
-                       "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {levels} "
-                       "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
+    "minres_diag_mg": "-ksp_type minres -ksp_rtol 1e-8 " + FS.format(fact="diag"),
+    # BASELINE config 3 AS NAMED: FGMRES + Schur with `self` + LSC on S (L = A10 diag(A00)^-1 A01 solved by
+    # Chebyshev(8)/Jacobi).  Iterations grow with the grid: benchmarked at the size given by --nx
+    "fgmres_schur_lsc": ("-ksp_type fgmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -ksp_max_it 2000 -pc_type fieldsplit -pc_fieldsplit_type schur "
+                         "-pc_fieldsplit_schur_fact_type upper -pc_fieldsplit_schur_precondition self "
+                         "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {levels} "
+                         "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type lsc -fieldsplit_1_pc_lsc_scale_diag "
+                         "-fieldsplit_1_lsc_ksp_type chebyshev -fieldsplit_1_lsc_ksp_max_it 8 -fieldsplit_1_lsc_pc_type jacobi"),
+    # BASELINE config 2 AS NAMED: GMRES + Schur (full) with plain Jacobi for A00 (iterations grow quickly with the grid)
+    "gmres_schur_jacobi": ("-ksp_type gmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -ksp_max_it 20000 -pc_type fieldsplit -pc_fieldsplit_type schur "
+                           "-pc_fieldsplit_schur_fact_type full -pc_fieldsplit_schur_precondition user "
+                           "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type jacobi -fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
 }
+# north_star tolerances (BASELINE.json): iterations +-1, final relative residual 1e-10, solution rel 1e-8
+TOL_ITS, TOL_RES, TOL_X = 1, 1e-10, 1e-8
 
 
 def mg_levels(nx):
@@ -58,11 +75,23 @@ def mg_levels(nx):
     return max(lev, 2)
 
 
+def options_for(config, nx):
+    lev = int(os.environ.get("B200SP_BENCH_MG_LEVELS", "0")) or mg_levels(nx)
+    return CONFIGS[config].format(levels=lev)
+
+
 def peak_hbm():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -104,43 +133,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_solve_setup(nx, opts):
+def oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sp_oracle as so
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the oracle takes all host threads it may use
+    so.lib().or_set_threads(host_threads())
+    return so
+
+
+def oracle_solve_setup(nx, opts):
+    so = oracle()
     t0 = time.perf_counter()
     prob = so.Problem(nx, nx, kkt=True, rhs_kind=1)
     solver = so.Solver(prob, opts)
     return so, prob, solver, time.perf_counter() - t0
 
 
+def workload(args, dof, opts):
+    return {"workload": "kkt2d_%s" % args.config, "grid_elements": [args.nx, args.nx], "dof": int(dof), "solver_options": opts,
+            "rtol": 1e-8, "l2_policy": "inputs (5 GB of matrices, 128 MB vectors) far larger than the 126 MB L2; no explicit flush",
+            "parallelism": "dmda_row_partition_x%d" % args.gpus}
+
+
 def run_reference(args, opts):
-    """reference arm: the CPU oracle on all host threads, same config; K timed solves after W warm-ups"""
+    """reference arm: the CPU oracle on all host threads, same config.  A solve takes seconds on the CPU, so at most
+    3 timed solves after at most 1 warm-up are run whatever --steps/--warmup say (the line reports what was run)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     so, prob, solver, t_setup = oracle_solve_setup(args.nx, opts)
     cores = so.lib().or_get_threads()
-    for _ in range(max(args.warmup, 0)):
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    for _ in range(warmup):
         solver.solve(history=False)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         r = solver.solve(history=False)
-    dt = (time.perf_counter() - t0) / args.steps
-    line = {"impl": "reference", "metric": "time_to_solve_rtol1e-8", "value": dt, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+    dt = (time.perf_counter() - t0) / steps
+    line = {"impl": "reference", "metric": "time_to_solve_rtol1e-8", "value": dt, "unit": "s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload(args, prob.nu + prob.np_),
+            "config": workload(args, prob.nu + prob.np_, opts),
             "iterations": r["its"], "converged_reason": r["reason"],
             "cpu_baseline": {"value": dt, "unit": "s", "cores": cores, "kind": "port",
-                             "sample": "full workload: one complete solve per step (assembly %.1fs and setup untimed)" % t_setup},
+                             "sample": "full workload: one complete solve per step, %d timed (assembly+setup %.1fs untimed)" % (steps, t_setup)},
+            "setup_s": t_setup,
             "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
-
-
-def workload(args, dof):
-    return {"workload": "kkt2d_%s" % args.config, "grid_elements": [args.nx, args.nx], "dof": int(dof), "solver_options": None,
-            "rtol": 1e-8, "l2_policy": "inputs (5 GB of matrices, 128 MB vectors) far larger than the 126 MB L2; no explicit flush",
-            "parallelism": "dmda_row_partition_x%d" % args.gpus}
 
 
 _REAL_STDOUT = None
@@ -149,6 +189,135 @@ _REAL_STDOUT = None
 def emit(line):
     """the ONE JSON line of the contract, on the process's real stdout"""
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
+def compare_with_oracle(x, ro, rd, nu, perm_u=None, perm_p=None, g0=0, nl=None):
+    """GPU solution (this rank's part) against the oracle's: the quantities north_star names.  perm_*: natural ->
+    PETSc numbering when the GPU run is row-partitioned."""
+    xo = ro["x"]
+    nug = len(perm_u) if perm_u is not None else nu
+    xu, xp = xo[:nug], xo[nug:]
+    if perm_u is not None:
+        t = np.zeros(nug); t[perm_u] = xu; xu = t[2 * g0:2 * (g0 + nl)]
+        t = np.zeros(len(xp)); t[perm_p] = xp; xp = t[g0:g0 + nl]
+    du = float(np.max(np.abs(x[:nu] - xu)))
+    dp = x[nu:] - xp
+    return {"du": du, "umax": float(np.max(np.abs(ro["x"][:nug]))), "dp": dp, "pmax": float(np.max(np.abs(ro["x"][nug:])))}
+
+
+def dist_check(sp, ctx, dist, nx=96):
+    """tools/dist_check.py in-process (N>1, before the timed region): global CSR rows bit-exact against the oracle,
+    distributed MatMult on both ghost parities, one distributed solve against the oracle."""
+    import scipy.sparse as sps
+    so = oracle()
+    rank, size = ctx.rank, ctx.size
+    M = N = nx + 1
+    out = {"nx": nx, "ok": False}
+    try:
+        orc = so.Problem(nx, nx, kkt=True, rhs_kind=1)
+        nm, ow = so.dmda_natural_to_petsc(M, N, size)
+
+        def perm(dof):
+            return np.repeat(nm.astype(np.int64) * dof, dof) + np.tile(np.arange(dof), M * N)
+
+        def petsc(A, dr, dc):
+            Cm = A.scipy().tocoo()
+            P = sps.csr_matrix((Cm.data, (perm(dr)[Cm.row], perm(dc)[Cm.col])), shape=Cm.shape)
+            P.sort_indices()
+            return P
+
+        prob = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+        nl = prob.da.n_nodes_local
+        g0 = int(np.sum(ow < rank))
+        rng = np.random.default_rng(3)
+        xg = {1: rng.uniform(-1, 1, M * N), 2: rng.uniform(-1, 1, 2 * M * N)}
+        bit_exact, mm_err = True, 0.0
+        for name, (dr, dc) in {"A": (2, 2), "Bt": (2, 1), "B": (1, 2), "C": (1, 1)}.items():
+            m = getattr(prob, name)
+            R = petsc(getattr(orc, name), dr, dc)
+            rp, col, val = m.csr()
+            Rl = R[g0 * dr:(g0 + nl) * dr]
+            bit_exact = bit_exact and np.array_equal(rp, Rl.indptr) and np.array_equal(col, Rl.indices) and \
+                np.array_equal(val.view(np.uint64), Rl.data.view(np.uint64))
+            for rep in range(3):                                   # repeated exchanges exercise both ghost parities
+                x = sp.Vec.from_numpy(ctx, (rep + 1.0) * xg[dc][g0 * dc:(g0 + nl) * dc])
+                y = sp.Vec(ctx, nl * dr)
+                m.mult(x, y)
+                yr = (rep + 1.0) * (R @ xg[dc])
+                mm_err = max(mm_err, float(np.max(np.abs(y.numpy() - yr[g0 * dr:(g0 + nl) * dr])) / max(1.0, np.max(np.abs(yr)))))
+        opts = CONFIGS["fgmres_schur_mg"].format(levels=mg_levels(nx))
+        ro = so.Solver(orc, opts).solve()
+        ksp = prob.make_ksp(opts)
+        x = sp.Vec(ctx, prob.n)
+        its = []
+        for rep in range(3):                                       # the second and third solves replay the CUDA graphs
+            r = ksp.solve(prob.rhs, x)
+            its.append(r["its"])
+        c = compare_with_oracle(x.numpy(), ro, r, 2 * nl, perm(2), perm(1), g0, nl)
+        loc = {"bit_exact": bool(bit_exact), "mm_err": mm_err, "its": its, "reason": r["reason"], "du": c["du"], "dp": c["dp"],
+               "rel_res": r["rnorm"] / r["history"][0]}
+        ksp.destroy()
+    except Exception as e:  # noqa: BLE001 -- reported in the JSON line; the bench goes on so that the failure is visible
+        loc = {"error": repr(e)}
+        ro = None
+    allr = [None] * size
+    dist.all_gather_object(allr, loc)
+    if rank != 0:
+        return None
+    errs = [a["error"] for a in allr if "error" in a]
+    if errs or ro is None:
+        out["error"] = errs[0] if errs else "oracle failed"
+        return out
+    umax, pmax = float(np.max(np.abs(ro["x"][:2 * M * N]))), float(np.max(np.abs(ro["x"][2 * M * N:])))
+    dp = np.concatenate([a["dp"] for a in allr])
+    rel_o = ro["rnorm"] / ro["history"][0]
+    out.update({"csr_rows_bit_exact": all(a["bit_exact"] for a in allr), "matmult_max_rel_err": max(a["mm_err"] for a in allr),
+                "solve_iterations": allr[0]["its"], "oracle_iterations": ro["its"],
+                "rel_residual_diff": abs(allr[0]["rel_res"] - rel_o),
+                "max_rel_velocity_diff": max(a["du"] for a in allr) / umax,
+                "max_rel_pressure_diff_mean_removed": float(np.max(np.abs(dp - dp.mean()))) / pmax})
+    out["ok"] = bool(out["csr_rows_bit_exact"] and out["matmult_max_rel_err"] < 1e-14 and all(a["reason"] == 2 for a in allr)
+                     and all(abs(i - ro["its"]) <= TOL_ITS for a in allr for i in a["its"])
+                     and out["max_rel_velocity_diff"] <= TOL_X and out["max_rel_pressure_diff_mean_removed"] <= TOL_X
+                     and (allr[0]["its"][-1] != ro["its"] or out["rel_residual_diff"] <= TOL_RES))
+    return out
+
+
+def time_solves(ctx, ksp, b, x, steps, warmup):
+    for _ in range(warmup):
+        ksp.solve(b, x)
+    ctx.synchronize()
+    ctx.timer_start()
+    for _ in range(steps):
+        res = ksp.solve(b, x)
+    ms = ctx.timer_stop()
+    return ms / 1e3 / steps, res
+
+
+def secondary_config(sp, ctx, name, nx, steps=3, warmup=2):
+    """one more BASELINE configuration on this GPU (N=1 only), device-resident timing, true residual reported"""
+    opts = options_for(name, nx)
+    prob = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+    t0 = time.perf_counter()
+    ksp = prob.make_ksp(opts)
+    ksp.setup()
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t0
+    x = sp.Vec(ctx, prob.n)
+    dt, res = time_solves(ctx, ksp, prob.rhs, x, steps, warmup)
+    r = sp.Vec(ctx, prob.n)
+    prob.K.residual(prob.rhs, x, r)
+    out = {"config": name, "grid_elements": [nx, nx], "dof": prob.n, "solver_options": opts, "value": dt, "unit": "s", "steps": steps,
+           "warmup": warmup, "iterations": res["its"], "converged_reason": res["reason"], "true_relative_residual": r.norm() / prob.rhs.norm(),
+           "ksp_setup_s": t_setup}
+    ksp.destroy()
+    return out
+
+
+def spmv_moved_bytes(fmt, rows, cols, variant):
+    """bytes one SpMV launch has to move: stored matrix format + x + y + the epilogue's operand vectors"""
+    extra = {"plain": 0, "axpby": 8 * rows, "cheb": 32 * rows}[variant]   # z | z, dinv, p_{k-1}, p_k
+    return fmt["matrix_bytes"] + 8 * rows + 8 * cols + extra
 
 
 def main():
@@ -165,12 +334,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=2304, help="elements per side (2304 -> 15.9M DOF; 576 -> 1.0M DOF)")
-    ap.add_argument("--config", default="fgmres_schur_mg", choices=sorted(CONFIGS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="fgmres_schur_mg", choices=sorted(CONFIGS) + ["sweep"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (cpu_baseline and parity)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (N=1)")
+    ap.add_argument("--no-dist-check", action="store_true", help="skip the in-run distributed parity check (N>1)")
     args = ap.parse_args()
-    ap_levels = int(os.environ.get("B200SP_BENCH_MG_LEVELS", "0")) or mg_levels(args.nx)
-    opts = CONFIGS[args.config].format(levels=ap_levels)
 
+    if args.config == "sweep":
+        import tools.kernel_sweep as ks
+        ks.bench_main(args, emit)
+        return
+    opts = options_for(args.config, args.nx)
     if args.impl == "reference":
         run_reference(args, opts)
         return
@@ -211,6 +385,10 @@ def main():
             dist.barrier()
 
     ctx = sp.Context(device=local_rank, rank=rank, size=world, nccl_id=nccl_id)
+    dcheck = None
+    if world > 1 and not args.no_dist_check:
+        dcheck = dist_check(sp, ctx, dist)
+        barrier()
     t0 = time.perf_counter()
     prob = sp.SaddlePointProblem(ctx, args.nx, args.nx, kkt=True, rhs_kind=1)
     ctx.synchronize()
@@ -224,7 +402,11 @@ def main():
     x = sp.Vec(ctx, n)
 
     # ---- device-resident timing: W warm-up solves, then exactly K timed solves between events + syncs
-    for _ in range(args.warmup):
+    t0 = time.perf_counter()
+    ksp.solve(prob.rhs, x)     # the first solve also builds the lazily derived SpMV formats and records the CUDA graphs
+    ctx.synchronize()
+    t_first_solve = time.perf_counter() - t0
+    for _ in range(max(args.warmup - 1, 0)):
         ksp.solve(prob.rhs, x)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -241,6 +423,7 @@ def main():
     launches = ctx.launch_count() - l0
     clocks = sampler.stop()
     t_solve = max_over_ranks(ms) / 1e3 / args.steps   # device time, max over ranks
+    x_dev = x.numpy() if (world == 1 and not args.no_cpu_baseline) else None
 
     # ---- end to end through the host-buffer C-ABI entry point, pinned host memory
     import torch
@@ -265,33 +448,52 @@ def main():
     pk, pk_src = peak_hbm()
     rA, cA, nnzA = prob.A.size()
     bytes_A = 12 * nnzA + 4 * (rA + 1) + 8 * rA + 8 * cA
-    pa = prof.get("spmv:A", {"ms": 0.0, "launches": 0})
-    avg_ms = pa["ms"] / max(pa["launches"], 1)
-    achieved = bytes_A / avg_ms / 1e6 if avg_ms > 0 else 0.0
-    # wall-clock split of one un-profiled solve is not available per class; report the host-side time of the same
-    # profiled solve next to the sum of its device classes so launch gaps / exposed communication are visible
-    prof_total_ms = sum(v["ms"] for v in prof.values())
-    total_prof = sum(v["ms"] for v in prof.values())
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this matrix, from the committed ncu capture
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")))
-        if tr["nx"] == args.nx and tr["n_gpus"] == world and tr.get("value_dict", False) == prob.A.spmv_format()["value_dict"]:
-            traffic = tr["traffic"]
-    except Exception:
-        pass
     fmt = prob.A.spmv_format()
-    kname = ("k_spmv_tma_dict<%d,%d>" % fmt["block"]) if fmt["value_dict"] else ("k_spmv_tma_blk<%d,%d>" % fmt["block"]) if fmt["block"] != (1, 1) else "k_spmv_tma"
-    stored = fmt["matrix_bytes"] + 8 * rA + 8 * cA   # what the kernel has to move for the stored (losslessly compressed) format
-    # `achieved` follows the contract: ALGORITHMIC (plain CSR) bytes / launch time.  The kernel streams a
-    # compressed matrix (block column index + tile-local value dictionary), so this can exceed the HBM peak; the
-    # bytes really moved are `traffic` (ncu) ~ `stored_format_bytes_per_launch`, and `frac_of_peak_moved` is that rate.
-    roofline = {"kernel": "%s on the A block (%d x %d, %d nnz per GPU)" % (kname, rA, cA, nnzA), "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": pk, "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk, 4), "traffic": traffic,
-                "algorithmic_bytes_per_launch": bytes_A, "stored_format_bytes_per_launch": stored,
-                "frac_of_peak_moved": round((traffic if traffic else stored) / avg_ms / 1e6 / pk, 4) if avg_ms > 0 else None,
-                "avg_launch_ms": round(avg_ms, 5), "launches_per_solve": pa["launches"],
-                "share_of_solve_device_time": round(pa["ms"] / total_prof, 4) if total_prof else None}
-    classes = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    variants, tot_ms, tot_n, tot_moved = {}, 0.0, 0, 0.0
+    for key, v in prof.items():
+        if not key.startswith("spmv:A|") or not v["launches"]:
+            continue
+        var = key.split("|")[1]
+        moved = spmv_moved_bytes(fmt, rA, cA, var)
+        avg = v["ms"] / v["launches"]
+        variants[var] = {"launches_per_solve": v["launches"], "avg_launch_ms": round(avg, 5), "moved_bytes_per_launch": moved,
+                         "moved_gbs": round(moved / avg / 1e6, 1), "frac": round(moved / avg / 1e6 / pk, 4),
+                         "csr_algorithmic_gbs": round(bytes_A / avg / 1e6, 1)}
+        tot_ms += v["ms"]; tot_n += v["launches"]; tot_moved += moved * v["launches"]
+    avg_ms = tot_ms / max(tot_n, 1)
+    moved_avg = tot_moved / max(tot_n, 1)
+    total_prof = sum(v["ms"] for v in prof.values())
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the plain-epilogue launch of this kernel on this matrix (ncu --set full)
+    for tf in ("r02_spmv_traffic.json", "r01_spmv_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if tr["nx"] == args.nx and tr["n_gpus"] == world and tr.get("format") == fmt.get("format", tr.get("format")) and \
+                    tr.get("value_dict", False) == fmt["value_dict"]:
+                traffic = tr["traffic"]
+                break
+        except Exception:
+            pass
+    kname = fmt.get("kernel") or (("k_spmv_tma_dict<%d,%d>" % fmt["block"]) if fmt["value_dict"] else
+                                  ("k_spmv_tma_blk<%d,%d>" % fmt["block"]) if fmt["block"] != (1, 1) else "k_spmv_tma")
+    achieved = moved_avg / avg_ms / 1e6 if avg_ms > 0 else 0.0
+    roofline = {"kernel": "%s on the A block (%d x %d, %d nnz per GPU)" % (kname, rA, cA, nnzA), "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": pk, "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk, 4),
+                "frac_definition": "bytes the kernel has to move (stored matrix format + x + y + epilogue operand vectors, launch-weighted over "
+                                   "the variants below) / CUDA-event time of the A-block launches inside one solve / measured HBM peak",
+                "traffic": traffic, "traffic_note": "ncu dram bytes of ONE plain-epilogue launch (profiles/); compare with variants.plain.moved_bytes_per_launch",
+                "moved_bytes_per_launch_avg": int(moved_avg), "stored_matrix_bytes": fmt["matrix_bytes"],
+                "csr_algorithmic_bytes_per_launch": bytes_A, "csr_algorithmic_gbs": round(bytes_A / avg_ms / 1e6, 1) if avg_ms > 0 else None,
+                "speedup_vs_csr_roofline": round(bytes_A / avg_ms / 1e6 / pk, 4) if avg_ms > 0 else None,
+                "avg_launch_ms": round(avg_ms, 5), "launches_per_solve": tot_n, "variants": variants,
+                "share_of_solve_device_time": round(tot_ms / total_prof, 4) if total_prof else None}
+    # classes: epilogue variants of one matrix merged back; "profiled": every launch was bracketed by events and a
+    # host synchronisation, so the SUM exceeds `value` -- use the shares, not the absolute numbers
+    merged = {}
+    for k, v in prof.items():
+        kk = k.split("|")[0]
+        e = merged.setdefault(kk, {"ms": 0.0, "launches": 0})
+        e["ms"] += v["ms"]; e["launches"] += v["launches"]
+    classes = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in sorted(merged.items(), key=lambda kv: -kv[1]["ms"])}
 
     # true residual of the last solve (device SpMV), reported for the record
     r = sp.Vec(ctx, n)
@@ -299,7 +501,6 @@ def main():
     true_rel = r.norm() / prob.rhs.norm()
 
     if dist is not None:
-        import torch
         t = torch.tensor([float(n)], dtype=torch.float64)
         dist.all_reduce(t)
         n_global = int(t[0])
@@ -311,26 +512,60 @@ def main():
     if rank != 0:
         ctx.synchronize()
         return
-    cpu = None
+
+    # ---- N=1: the same system through the CPU oracle -> cpu_baseline + parity at the benchmarked size
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
         so, oprob, osolver, t_osetup = oracle_solve_setup(args.nx, opts)
         t0 = time.perf_counter()
-        orr = osolver.solve(history=False)
+        orr = osolver.solve(history=True)
         t_cpu = time.perf_counter() - t0
         cpu = {"value": t_cpu, "unit": "s", "cores": so.lib().or_get_threads(), "kind": "port",
-               "sample": "full workload, one solve (oracle assembly+setup %.1fs untimed)" % t_osetup, "iterations": orr["its"]}
+               "sample": "full workload, one solve (oracle assembly+setup %.1fs untimed)" % t_osetup, "iterations": orr["its"],
+               "setup_s": t_osetup}
+        c = compare_with_oracle(x_dev, orr, res, prob.nu)
+        rel_d, rel_o = res["rnorm"] / res["history"][0], orr["rnorm"] / orr["history"][0]
+        m = min(len(res["history"]), len(orr["history"]))
+        hist_dev = float(np.max(np.abs(res["history"][:m] - orr["history"][:m]) / orr["history"][:m])) if m else None
+        parity = {"against": "CPU oracle (oracle/sp_oracle.c), same grid, right-hand side and options", "size": "nx=%d (benchmarked size)" % args.nx,
+                  "iterations": res["its"], "oracle_iterations": orr["its"], "reason": res["reason"], "oracle_reason": orr["reason"],
+                  "rel_residual": rel_d, "oracle_rel_residual": rel_o, "rel_residual_diff": abs(rel_d - rel_o),
+                  "max_rel_velocity_diff": c["du"] / c["umax"],
+                  "max_rel_pressure_diff_mean_removed": float(np.max(np.abs(c["dp"] - c["dp"].mean()))) / c["pmax"],
+                  "max_rel_history_diff": hist_dev,
+                  "tolerances": {"iterations": TOL_ITS, "rel_residual": TOL_RES, "solution": TOL_X}}
+        parity["ok"] = bool(res["reason"] == orr["reason"] and abs(res["its"] - orr["its"]) <= TOL_ITS
+                            and (res["its"] != orr["its"] or parity["rel_residual_diff"] <= TOL_RES)
+                            and parity["max_rel_velocity_diff"] <= TOL_X and parity["max_rel_pressure_diff_mean_removed"] <= TOL_X)
+        del osolver, oprob
 
-    cfg = workload(args, n_global)
-    cfg["solver_options"] = opts
+    secondary = None
+    if world == 1 and not args.no_secondary and args.config == "fgmres_schur_mg":
+        secondary = []
+        for name, nx2 in (("gmres_schur_mg", 576), ("fgmres_schur_lsc", 192), ("minres_diag_mg", args.nx)):
+            try:
+                secondary.append(secondary_config(sp, ctx, name, nx2))
+            except Exception as e:  # noqa: BLE001
+                secondary.append({"config": name, "grid_elements": [nx2, nx2], "error": repr(e)})
+
+    cfg = workload(args, n_global, opts)
     cfg["dof_per_gpu"] = n
     line = {"metric": "time_to_solve_rtol1e-8", "value": t_solve, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_solve * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg, "iterations": res["its"], "converged_reason": res["reason"],
             "iterations_per_s": res["its"] / t_solve, "true_relative_residual": true_rel,
             "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_classes_ms_per_solve": classes, "kernel_classes_total_ms": round(prof_total_ms, 3), "assembly_s": t_assembly, "ksp_setup_s": t_setup}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "dist_check": dcheck,
+            "kernel_classes_ms_per_solve": {"profiled": True, "note": "one extra solve with CUDA events + a host sync around every launch: use shares",
+                                            "total_ms": round(total_prof, 3), "classes": classes},
+            "assembly_s": t_assembly, "ksp_setup_s": t_setup, "first_solve_s": t_first_solve,
+            "setup_plus_solve_s": t_setup + t_first_solve, "secondary": secondary}
     emit(line)
+    bad = (parity is not None and not parity["ok"]) or (dcheck is not None and not dcheck["ok"])
+    if bad:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED: %s\n" % json.dumps(parity if parity is not None and not parity["ok"] else dcheck))
+        sys.stderr.flush()
+        os._exit(3)
 
 
 if __name__ == "__main__":

@@ -144,9 +144,13 @@ int b200sp_mat_get_csr_host(b200sp_mat A, int *rowptr, int *col, double *val); /
 int b200sp_mat_get_spmv_plan(b200sp_mat A, int64_t hist[14], int *kernel, int *max_row_nnz);
 int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel); /* override (tests / sweeps) */
 /* storage the TMA SpMV actually streams for this matrix (after the first mult): block size of the block-compressed
- * column index (1 x 1 = plain CSR columns), whether the tile-local value dictionary is in use (16-bit codes +
- * per-tile dictionaries instead of 8-byte values), and the resulting matrix bytes per launch (without x and y) */
+ * column index (1 x 1 = plain CSR columns), whether the tile-local pattern/value dictionaries are in use (one byte
+ * per nonzero + per-tile dictionaries instead of 8-byte values and 4-byte columns), and the resulting matrix bytes
+ * per launch (without x and y) */
 int b200sp_mat_get_spmv_format(b200sp_mat A, int *block_r, int *block_c, int *value_dict, int64_t *matrix_bytes);
+/* choose what the SpMV may derive from the CSR arrays (benchmarks of the general-matrix paths; results are bit-identical
+ * in every format): block_index 0 = plain CSR columns, value_dict 0 = plain 8-byte values */
+int b200sp_mat_set_spmv_format(b200sp_mat A, int block_index, int value_dict);
 int b200sp_mat_mult(b200sp_mat A, b200sp_vec x, b200sp_vec y);              /* MatMult */
 int b200sp_mat_mult_add(b200sp_mat A, b200sp_vec x, b200sp_vec y, b200sp_vec z); /* MatMultAdd: z = y + A x */
 int b200sp_mat_residual(b200sp_mat A, b200sp_vec b, b200sp_vec x, b200sp_vec r); /* r = b - A x (fused) */

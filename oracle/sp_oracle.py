@@ -342,6 +342,8 @@ class Solver:
         """pc on an assembled matrix: none | jacobi | mg | lu"""
         L = self.L
         t = self._get(prefix + "pc_type", default)
+        if t == "petsc-default":   # PETSc would pick ILU(0) here; neither the oracle nor the CUDA library has it
+            raise ValueError("oracle: -%spc_type must be given explicitly (PETSc's default is ILU(0))" % prefix)
         if t == "none":
             return None
         if t == "jacobi":
@@ -414,7 +416,7 @@ class Solver:
         # K0: fieldsplit_0 KSP on A00
         A00op = L.or_op_csr(prob.A.ptr)
         self.keep.append(A00op)
-        pc0 = self._make_simple_pc("fieldsplit_0_", prob.A, grid=(prob.M, prob.N), dof=2, default="jacobi")
+        pc0 = self._make_simple_pc("fieldsplit_0_", prob.A, grid=(prob.M, prob.N), dof=2, default="petsc-default")
         k0 = self._make_ksp("fieldsplit_0_", A00op, pc0, default_type="preonly")
         K0 = self._ksp_op(k0)
         # S = A11 - A10 ksp(A00) A01, with its own (identically configured) inner KSP
@@ -439,7 +441,7 @@ class Solver:
         else:
             raise ValueError(pre)
         self.Sp = Sp
-        pt = self._get("fieldsplit_1_pc_type", "jacobi" if Sp is not None else "none")
+        pt = self._get("fieldsplit_1_pc_type", "petsc-default" if Sp is not None else "none")
         if pt == "lsc":
             scale_diag = self._get("fieldsplit_1_pc_lsc_scale_diag") is not None
             if scale_diag:
@@ -452,16 +454,16 @@ class Solver:
             self.Lmat = Lm
             Lop = L.or_op_csr(Lm.ptr)
             self.keep += [Lm, Lop]
-            pcl = self._make_simple_pc("fieldsplit_1_lsc_", Lm, default="jacobi")
-            kl = self._make_ksp("fieldsplit_1_lsc_", Lop, pcl, default_type="preonly")
+            pcl = self._make_simple_pc("fieldsplit_1_lsc_", Lm, default="petsc-default")
+            kl = self._make_ksp("fieldsplit_1_lsc_", Lop, pcl, default_type="gmres")   # a fresh KSP in PETSc: GMRES
             Linv = self._ksp_op(kl)
             pcS = L.or_op_lsc(prob.A.ptr, prob.Bt.ptr, prob.B.ptr, Linv, int(scale_diag))
             self.keep.append(pcS)
         elif pt == "none" or Sp is None:
             pcS = None
         else:
-            pcS = self._make_simple_pc("fieldsplit_1_", Sp, default="jacobi")
-        kS = self._make_ksp("fieldsplit_1_", S, pcS, default_type="preonly")
+            pcS = self._make_simple_pc("fieldsplit_1_", Sp, default="petsc-default")
+        kS = self._make_ksp("fieldsplit_1_", S, pcS, default_type="gmres")   # the Schur KSP is a fresh KSP in PETSc: GMRES
         KS = self._ksp_op(kS)
         fs = L.or_op_fieldsplit(fact, prob.Bt.ptr, prob.B.ptr, K0, KS, scale)
         self.keep.append(fs)

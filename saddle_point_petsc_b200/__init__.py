@@ -82,6 +82,7 @@ _SIGS = {
     "b200sp_mat_get_spmv_plan": [_vp, C.POINTER(C.c_int64), c_ip, c_ip],
     "b200sp_mat_get_spmv_format": [_vp, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)],
     "b200sp_mat_set_spmv_kernel": [_vp, C.c_int],
+    "b200sp_mat_set_spmv_format": [_vp, C.c_int, C.c_int],
     "b200sp_mat_mult": [_vp, _vp, _vp],
     "b200sp_mat_mult_add": [_vp, _vp, _vp, _vp],
     "b200sp_mat_residual": [_vp, _vp, _vp, _vp],
@@ -444,6 +445,10 @@ class Mat:
         br, bc, vd, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
         _chk(lib().b200sp_mat_get_spmv_format(self.h, C.byref(br), C.byref(bc), C.byref(vd), C.byref(nb)))
         return {"block": (br.value, bc.value), "value_dict": bool(vd.value), "matrix_bytes": nb.value}
+
+    def set_spmv_format(self, block_index=True, value_dict=True):
+        """Restrict what the SpMV derives from the CSR arrays (general-matrix paths for benchmarks; same bits)."""
+        _chk(lib().b200sp_mat_set_spmv_format(self.h, int(block_index), int(value_dict)))
 
     def set_spmv_kernel(self, k):
         _chk(lib().b200sp_mat_set_spmv_kernel(self.h, k))

@@ -22,6 +22,22 @@ struct b200sp_dmda_s { Dmda d; };
 
 static thread_local std::string g_last_error;
 
+// One host thread may drive contexts on several devices (single-process multi-GPU): every entry point that launches
+// work first makes its context's device current.
+static inline void use_device(Ctx *c) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device) B2_CUDA(cudaSetDevice(c->device));
+}
+// device-side waits (peer-to-peer halos, small collectives) report a timeout through the context's mapped error word;
+// it is checked -- and cleared, so that one failure does not poison every later call -- after every solve and PC apply
+static inline void check_device_error(Ctx *c) {
+  if (c->h_err && *c->h_err) {
+    const int code = *c->h_err;
+    *c->h_err = 0;
+    throw Error(B200SP_ERR_NCCL, "peer-to-peer exchange timed out waiting for a neighbour (code " + std::to_string(code) + "); results of this call are invalid");
+  }
+}
+
 #define API_BEGIN try {
 #define API_END                                                    \
   return B200SP_OK;                                                \
@@ -253,6 +269,7 @@ int b200sp_dmda_halo_push_table(int M, int N, int size, int rank, int *n_owned, 
 int b200sp_dmda_create(b200sp_ctx ctx, int M, int N, b200sp_dmda *da) {
   API_BEGIN
   B2_REQUIRE(ctx && da, "dmda_create: bad arguments");
+  use_device(&ctx->c);
   Layout L(M, N, ctx->c.size);
   auto *h = new b200sp_dmda_s();
   Dmda &d = h->d;
@@ -286,6 +303,7 @@ int b200sp_dmda_bc_ids(b200sp_dmda da, int dof, int *n, int *ids) {
 int b200sp_vec_create(b200sp_ctx ctx, int64_t n, b200sp_vec *v) {
   API_BEGIN
   B2_REQUIRE(ctx && v && n >= 0, "vec_create: bad arguments");
+  use_device(&ctx->c);
   *v = new b200sp_vec_s(&ctx->c, n);
   API_END
 }
@@ -459,11 +477,22 @@ int b200sp_mat_get_spmv_format(b200sp_mat A, int *block_r, int *block_c, int *va
   if (value_dict) *value_dict = dict ? 1 : 0;
   if (matrix_bytes) {
     const int br = blk ? M.blk_r : 1, bc = blk ? M.blk_c : 1;
-    int64_t bytes = 4 * (M.nnz / (br * bc)) + 4 * (int64_t)(M.nrows / br + 1); // (block) column index + its row pointer
-    if (dict) bytes += 2 * M.nnz + M.dict_bytes + 4 * (int64_t)((M.nrows + M.dict_rows - 1) / M.dict_rows + 1);
-    else bytes += 8 * M.nnz + (blk ? 4 * (int64_t)(M.nrows + 1) : 0); // the block-index kernel also reads rowptr
+    int64_t bytes;
+    if (dict) bytes = M.dict_bytes; // tile blobs (values, patterns, codes) + the tile offsets: nothing else is read
+    else bytes = 8 * M.nnz + 4 * (M.nnz / (br * bc)) + 4 * (int64_t)(M.nrows + 1) + (blk ? 4 * (int64_t)(M.nrows / br + 1) : 0);
     *matrix_bytes = bytes;
   }
+  API_END
+}
+int b200sp_mat_set_spmv_format(b200sp_mat A, int block_index, int value_dict) {
+  API_BEGIN
+  Csr &M = plain(A);
+  use_device(M.ctx);
+  M.ctx->sync();
+  csr_drop_value_dict(M);
+  M.no_value_dict = value_dict == 0;
+  if (!block_index) { M.bcol.release(); M.bptr.release(); M.blk_r = M.blk_c = 1; }
+  else if (!M.bcol.p && M.dof_r > 0 && M.dof_c > 0 && M.dof_r * M.dof_c > 1) csr_try_block_index(M, M.dof_r, M.dof_c);
   API_END
 }
 int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel) {
@@ -475,6 +504,7 @@ int b200sp_mat_set_spmv_kernel(b200sp_mat A, int kernel) {
   API_END
 }
 static void mat_apply(Mat &m, const double *x, double *y, double alpha, const double *z, double beta_z) {
+  use_device(m.ctx);
   if (!m.nest) { csr_spmv(*m.csr, x, y, alpha, z, beta_z); return; }
   const int64_t n0c = m.blk[0][0]->ncols, n0r = m.blk[0][0]->nrows;
   csr_spmv(*m.blk[0][0], x, y, alpha, z, beta_z);
@@ -557,7 +587,7 @@ int b200sp_mat_create_nest(b200sp_mat A00, b200sp_mat A01, b200sp_mat A10, b200s
 }
 
 // ---------------------------------------------------------------- assembly
-int b200sp_assemble_stress(b200sp_dmda da, int as_written, b200sp_mat *A) { API_BEGIN *A = wrap(da->d.ctx, assemble_stress(da->d, as_written)); API_END }
+int b200sp_assemble_stress(b200sp_dmda da, int as_written, b200sp_mat *A) { API_BEGIN use_device(da->d.ctx); *A = wrap(da->d.ctx, assemble_stress(da->d, as_written)); API_END }
 int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec f) {
   API_BEGIN
   B2_REQUIRE(f->v.n >= (int64_t)da->d.xm * da->d.ym * 2, "assemble_rhs: vector too short");
@@ -567,6 +597,7 @@ int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec
 int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q) {
   API_BEGIN
   std::shared_ptr<Csr> bt, b, c, q;
+  use_device(da->d.ctx);
   assemble_kkt(da->d, Bt ? &bt : nullptr, B ? &b : nullptr, C ? &c : nullptr, Q ? &q : nullptr);
   if (Bt) *Bt = wrap(da->d.ctx, bt);
   if (B) *B = wrap(da->d.ctx, b);
@@ -586,23 +617,26 @@ int b200sp_ksp_destroy(b200sp_ksp *ksp) {
 int b200sp_ksp_set_operators(b200sp_ksp ksp, b200sp_mat Amat, b200sp_mat Pmat) {
   API_BEGIN
   B2_REQUIRE(Amat && Pmat, "KSPSetOperators: null matrix");
-  ksp->s.Amat = &Amat->m; ksp->s.Pmat = &Pmat->m; ksp->s.is_setup = false;
+  use_device(ksp->s.ctx); ksp->s.set_operators(Amat->m, Pmat->m);
   API_END
 }
 int b200sp_ksp_set_options(b200sp_ksp ksp, const char *options) { API_BEGIN ksp->s.set_options(options); API_END }
 int b200sp_ksp_set_schur_user_mat(b200sp_ksp ksp, b200sp_mat Q) { API_BEGIN ksp->s.schur_user = plain(Q).ctx ? Q->m.csr : nullptr; ksp->s.is_setup = false; API_END }
 int b200sp_ksp_set_dmda(b200sp_ksp ksp, b200sp_dmda da) { API_BEGIN ksp->s.have_grid = true; ksp->s.grid_M = da->d.M; ksp->s.grid_N = da->d.N; API_END }
-int b200sp_ksp_setup(b200sp_ksp ksp) { API_BEGIN ksp->s.setup(); API_END }
+int b200sp_ksp_setup(b200sp_ksp ksp) { API_BEGIN use_device(ksp->s.ctx); ksp->s.setup(); API_END }
 int b200sp_ksp_solve(b200sp_ksp ksp, b200sp_vec b, b200sp_vec x) {
   API_BEGIN
+  use_device(ksp->s.ctx);
   if (!ksp->s.current()) ksp->s.setup(); // also when matrix values changed since KSPSetUp (PETSc: object state)
   B2_REQUIRE(b->v.n == ksp->s.outer->n && x->v.n == b->v.n && b != x, "KSPSolve: size mismatch or aliasing");
   ksp->s.outer->solve(b->v.d, x->v.d, false);
   ksp->s.ctx->sync();
+  check_device_error(ksp->s.ctx);
   API_END
 }
 int b200sp_ksp_solve_host(b200sp_ksp ksp, const double *b_host, double *x_host, int64_t n) {
   API_BEGIN
+  use_device(ksp->s.ctx);
   if (!ksp->s.current()) ksp->s.setup(); // also when matrix values changed since KSPSetUp (PETSc: object state)
   Ctx *c = ksp->s.ctx;
   B2_REQUIRE(n == ksp->s.outer->n, "KSPSolve(host): size mismatch");
@@ -613,6 +647,7 @@ int b200sp_ksp_solve_host(b200sp_ksp ksp, const double *b_host, double *x_host, 
   ksp->s.outer->solve(b.p, x.p, false);
   B2_CUDA(cudaMemcpyAsync(x_host, x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   c->sync();
+  check_device_error(c);
   API_END
 }
 int b200sp_ksp_get_iteration_number(b200sp_ksp ksp, int *its) { API_BEGIN B2_REQUIRE(ksp->s.outer, "KSP not set up"); *its = ksp->s.outer->its; API_END }
@@ -633,6 +668,7 @@ int b200sp_ksp_pc_apply(b200sp_ksp ksp, b200sp_vec x, b200sp_vec y) {
   if (ksp->s.outer_pc) ksp->s.outer_pc->apply(x->v.d, y->v.d);
   else vec_copy(ksp->s.ctx, x->v.n, x->v.d, y->v.d);
   ksp->s.ctx->sync();
+  check_device_error(ksp->s.ctx);
   API_END
 }
 // ---- PC as an object of its own (PCCreate / PCSetOperators / PCSetFromOptions / PCSetUp / PCApply / PCDestroy)
@@ -645,13 +681,13 @@ int b200sp_pc_destroy(b200sp_pc *pc) {
 int b200sp_pc_set_operators(b200sp_pc pc, b200sp_mat Amat, b200sp_mat Pmat) {
   API_BEGIN
   B2_REQUIRE(pc && Amat && Pmat, "PCSetOperators: null argument");
-  pc->s.Amat = &Amat->m; pc->s.Pmat = &Pmat->m; pc->s.is_setup = false;
+  use_device(pc->s.ctx); pc->s.set_operators(Amat->m, Pmat->m);
   API_END
 }
 int b200sp_pc_set_options(b200sp_pc pc, const char *options) { API_BEGIN pc->s.set_options(options); pc->s.is_setup = false; API_END }
 int b200sp_pc_set_schur_user_mat(b200sp_pc pc, b200sp_mat Q) { API_BEGIN pc->s.schur_user = plain(Q).ctx ? Q->m.csr : nullptr; pc->s.is_setup = false; API_END }
 int b200sp_pc_set_dmda(b200sp_pc pc, b200sp_dmda da) { API_BEGIN pc->s.have_grid = true; pc->s.grid_M = da->d.M; pc->s.grid_N = da->d.N; API_END }
-int b200sp_pc_setup(b200sp_pc pc) { API_BEGIN pc->s.setup(); API_END }
+int b200sp_pc_setup(b200sp_pc pc) { API_BEGIN use_device(pc->s.ctx); pc->s.setup(); API_END }
 int b200sp_pc_apply(b200sp_pc pc, b200sp_vec x, b200sp_vec y) {
   API_BEGIN
   if (!pc->s.current()) pc->s.setup();
@@ -659,6 +695,7 @@ int b200sp_pc_apply(b200sp_pc pc, b200sp_vec x, b200sp_vec y) {
   if (pc->s.outer_pc) pc->s.outer_pc->apply(x->v.d, y->v.d);
   else vec_copy(pc->s.ctx, x->v.n, x->v.d, y->v.d); // PCNONE
   pc->s.ctx->sync();
+  check_device_error(pc->s.ctx);
   API_END
 }
 int b200sp_pc_view(b200sp_pc pc, char *buf, int buflen) {

@@ -56,6 +56,7 @@ struct Ctx {
   double *h_scalars = nullptr; // pinned mirror
   int *h_err = nullptr, *d_err = nullptr; // pinned+mapped error word: device-side waits that time out report here
   int64_t launches = 0;
+  unsigned attr_mask = 0; // which kernel families had their MaxDynamicSharedMemorySize raised ON THIS CONTEXT'S DEVICE (the attribute is per device)
   bool profile = false;
   std::map<std::string, ProfEntry> prof;
   cudaEvent_t pev0 = nullptr, pev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -176,13 +177,14 @@ struct Csr {
   // block-compressed column index (kernels_spmv_tma.cu): one block-column id per blk_r x blk_c node block
   DevBuf<int> bptr, bcol;
   int blk_r = 1, blk_c = 1;
-  // tile-local value dictionary (kernels_spmv_tma.cu): per TMA_TILE_ROWS-row tile the distinct values + a 16-bit code per
-  // nonzero; built lazily by the first SpMV (state 0 = not tried, 1 = in use, -1 = declined), dropped when values change
-  mutable DevBuf<double> dict;
-  mutable DevBuf<int> dptr;
-  mutable DevBuf<unsigned short> codes;
-  mutable int dict_state = 0, dict_cap = 0, dict_rows = 0; // dict_rows: rows per dictionary tile (TMA_TILE_ROWS x block rows)
+  // tile-local pattern/value dictionaries (kernels_spmv_tma.cu, "pd" format): one blob per tile of 128 block rows holding
+  // the distinct values grouped by stencil position, the distinct column patterns and one byte per nonzero; built lazily
+  // by the first SpMV (state 0 = not tried, 1 = in use, -1 = declined), dropped when values change
+  mutable DevBuf<unsigned char> pd_blob;
+  mutable DevBuf<int> pd_off;                 // blob offsets per tile, in 16-byte units
+  mutable int dict_state = 0, pd_cap = 0, dict_rows = 0; // pd_cap: largest blob (bytes); dict_rows: rows per tile
   mutable int64_t dict_bytes = 0;
+  bool no_value_dict = false;                 // b200sp_mat_set_spmv_format: keep the plain value stream
   // tile order for kernels that wait for the halo themselves: tiles (of wait_order_rows rows) without ghost columns first
   mutable DevBuf<int> wait_order;
   mutable int wait_order_rows = 0, wait_n_nowait = 0;
@@ -198,7 +200,7 @@ struct Csr {
 constexpr int CSR_PAD = 8; // zero entries appended to col/val so vector loads may overrun a row tile
 
 struct Mat {
-  Ctx *ctx;
+  Ctx *ctx = nullptr;
   bool nest = false;
   std::shared_ptr<Csr> csr;               // plain matrix
   std::shared_ptr<Csr> blk[2][2];         // nest blocks (blk[1][1] may be null)

@@ -162,6 +162,8 @@ inline int grid_for(Ctx *c, int64_t n) {
 } // namespace
 
 std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d) {
+  if (A.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_scale_cols: row-partitioned matrices are not supported by this routine (ghost columns)");
+
   Ctx *c = A.ctx;
   auto C = csr_alloc(c, A.nrows, A.ncols, A.nnz);
   B2_CUDA(cudaMemcpyAsync(C->rowptr.p, A.rowptr.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
@@ -177,6 +179,8 @@ std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d) {
 }
 
 std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double s, const Csr &B) {
+  if (A.halo || B.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_add_scaled: row-partitioned matrices are not supported by this routine (ghost columns)");
+
   Ctx *c = A.ctx;
   B2_REQUIRE(A.nrows == B.nrows && A.ncols == B.ncols, "csr_add_scaled: shape mismatch");
   DevBuf<int> cnt((size_t)A.nrows + 1);
@@ -256,6 +260,8 @@ __global__ void __launch_bounds__(128) k_spgemm_numeric(int nrows, const int *__
 } // namespace
 
 std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B) {
+  if (A.halo || B.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_matmat: row-partitioned matrices are not supported by this routine (ghost columns)");
+
   Ctx *c = A.ctx;
   B2_REQUIRE(A.ncols == B.nrows, "csr_matmat: inner dimensions differ");
   const int n = A.nrows;
@@ -491,6 +497,8 @@ __global__ void __launch_bounds__(256) k_expand_rows(int nrows, const int *__res
 }
 } // namespace
 std::shared_ptr<Csr> csr_transpose(const Csr &A) {
+  if (A.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_transpose: row-partitioned matrices are not supported by this routine (ghost columns)");
+
   Ctx *c = A.ctx;
   DevBuf<int> rows((size_t)A.nnz + 1);
   if (A.nrows) {
@@ -644,6 +652,8 @@ __global__ void __launch_bounds__(256) k_dense_matvec(int n, const double *__res
 } // namespace
 
 void dense_inverse_from_csr(const Csr &A, double *Ainv) {
+  if (A.halo) throw Error(B200SP_ERR_UNSUPPORTED, "dense_inverse_from_csr: row-partitioned matrices are not supported by this routine (ghost columns)");
+
   Ctx *c = A.ctx;
   const int n = A.nrows;
   B2_REQUIRE(n == A.ncols && n > 0 && n <= 8192, "dense_inverse_from_csr: matrix must be square with n <= 8192");

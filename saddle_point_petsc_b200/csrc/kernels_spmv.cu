@@ -243,17 +243,19 @@ static bool csr_spmv_launch(const Csr &A, const double *x, double *y, SpmvEpi &e
     }
   }
   if (A.nrows <= 0) return false;
-  LaunchScope ls(c, A.tag.c_str());
+  // measurement pass: one profile class per matrix AND epilogue variant (they move different numbers of vectors)
+  std::string cls_variant;
+  if (c->profile) cls_variant = A.tag + (epi.cheb ? "|cheb" : epi.z ? "|axpby" : "|plain");
+  LaunchScope ls(c, c->profile ? cls_variant.c_str() : A.tag.c_str());
   if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return epi.push.grp != nullptr;
   epi.push = PushOut(); // the kernels below do not push
   if (pending_wait) { A.halo->end(); xs.wait_flags = nullptr; } // the TMA kernel declined: wait with the separate kernel
   if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(c->attr_mask & 1u)) {
       B2_CUDA(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_MAX_GROUP_NNZ * 8 * STREAM_WARPS + 64));
-      attr_set = true;
+      c->attr_mask |= 1u;
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 8) per_sm = 8;

@@ -237,48 +237,57 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
   if (epi.push.grp) epi.push.finish(); // fused halo push: fence, ticket, last CTA raises the neighbours' flags
 }
 
-// ---- tile-local value dictionary (CSR-VI style value indexing, per tile) ------------------------------------------
-// Finite-element matrices on structured grids repeat a small set of element-matrix sums: a 128-row tile of the A block
-// holds ~2300 values but only ~300 DISTINCT bit patterns.  Each tile therefore stores its distinct values once (8 B
-// each, in order of first occurrence) and one 16-bit code per nonzero; the kernel streams dictionary + codes + column
-// index (A: ~3.7 B/nnz instead of 9) and looks the value up in shared memory.  The value fed to the multiply is the
-// identical double, in the identical CSR order, so the result is bit-for-bit the same as every other SpMV kernel.
-// Matrices whose tiles do not compress (unstructured values) keep the plain value stream.
-constexpr int DICT_T = 8192;             // hash slots per tile in the build kernel
-constexpr int DICT_MAX_TILE_NNZ = 6144;  // larger tiles: no dictionary
-constexpr int DICT_MAX_ENTRIES = 2048;   // per tile (8 KB of shared memory per stage at most)
-constexpr unsigned long long DICT_EMPTY = ~0ull;
+// ---- tile-local pattern / value dictionaries ("pd" format) ---------------------------------------------------------
+// Finite-element matrices on structured grids repeat themselves: inside a tile of 128 block rows (nodes) the COLUMN
+// PATTERN of a row (its block columns relative to the row) takes one or a few values, and at a given position of the
+// stencil the VALUE takes a handful of distinct bit patterns (they are not all equal because (i+1)h - ih rounds
+// differently from element to element).  A tile is therefore stored as ONE contiguous blob
+//     header | dict: distinct values, grouped BY POSITION (block k, entry (rr,cc)), order of first occurrence
+//            | patterns: {number of blocks, block-column offsets}  | posoff: start of every position's group (u16)
+//            | pid: one pattern id per block row (u8)               | codes: [block k][row][BR*BC] one byte per nonzero
+// and the kernel streams ~1 byte per nonzero instead of 12 (A block: 0.58 GB instead of 2.5 GB per MatMult; the
+// previous tile-global 16-bit dictionary + explicit block columns moved 0.88 GB).  The value fed to the multiply is the
+// identical double, in the identical CSR order, so the result is bit-for-bit that of every other SpMV kernel.
+// Two things make the lookups cheap: codes and pattern ids are stored ELL-style inside the tile (consecutive lanes read
+// consecutive bytes: no bank conflicts), and because the dictionary is grouped by position, the 32 lanes of a warp --
+// which look up the SAME position for neighbouring nodes -- hit a few CONSECUTIVE entries (broadcast or distinct banks)
+// instead of random entries of a tile-wide dictionary (the measured limiter of the previous format: 40 % of the
+// shared-memory wavefronts were bank-conflict replays).  Matrices whose tiles do not compress keep the plain streams.
+constexpr int PD_NB = 128;         // block rows per tile (= blockDim.x of the SpMV kernel)
+constexpr int PD_MAX_K = 16;       // blocks per block row
+constexpr int PD_MAX_DICT = 2048;  // (position, value) pairs per tile
 
-// One thread per BLOCK ROW (node): the BR rows of a node share their block columns, so one x load (16 bytes when
-// BC = 2) and one index load serve BR x BC nonzeros -- the kernel is bound by L1/shared-memory wavefronts once the
-// stream is this small, not by HBM.  Each row still accumulates its own entries in CSR order.  A tile is blockDim.x
-// block rows (BR * 128 rows); rowptr is not needed: row I*BR + rr starts at (bptr[I] * BR + rr * nb) * BC.
-// BR = BC = 1 is plain CSR (bptr = rowptr, bcol = col).
+__host__ __device__ inline int pd_pad16(int bytes) { return (bytes + 15) & ~15; }
+struct PdLayout { int nbmax, npat, ndict, o_dict, o_pat, o_pos, o_pid, o_codes, bytes; };
+template <int BR, int BC>
+__host__ __device__ inline PdLayout pd_layout(int nbmax, int npat, int ndict) {
+  PdLayout L;
+  L.nbmax = nbmax; L.npat = npat; L.ndict = ndict;
+  L.o_dict = 16;
+  L.o_pat = L.o_dict + pd_pad16(ndict * 8);
+  L.o_pos = L.o_pat + pd_pad16(npat * (nbmax + 1) * 4);
+  L.o_pid = L.o_pos + pd_pad16(nbmax * BR * BC * 2);
+  L.o_codes = L.o_pid + PD_NB;
+  L.bytes = L.o_codes + nbmax * PD_NB * BR * BC;
+  return L;
+}
+
+// One thread per BLOCK ROW (node): one x load (16 bytes when BC = 2) serves BR x BC nonzeros; each row accumulates its
+// own entries in CSR order (block k ascending, then column).  One bulk copy per tile, two stages per CTA.
 template <int BR, int BC, int UB>
-__global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ tile_list, const int *__restrict__ bptr, const int *__restrict__ bcol,
-                                const int *__restrict__ dptr, const double *__restrict__ dict, const unsigned short *__restrict__ codes, XSrc xs,
-                                double *y, SpmvEpi epi, int capc, int capb, int dcap, int stages, int n_nowait) {
+__global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const int *__restrict__ order, const int *__restrict__ toff,
+                                                   const unsigned char *__restrict__ blob, XSrc xs, double *y, SpmvEpi epi, int cap, int stages,
+                                                   int n_nowait) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  const int NB = blockDim.x;
-  const size_t off_codes = (size_t)dcap * 8, off_bcol = off_codes + (size_t)capc * 2; // capc is a multiple of 8
-  const size_t stage_bytes = off_bcol + (size_t)capb * 4;
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + stage_bytes * stages);
+  constexpr int BRBC = BR * BC;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + (size_t)cap * stages);
   const int tid = threadIdx.x;
   auto issue = [&](int idx, int stage) { // one thread
-    const int tile = tile_list ? tile_list[idx] : idx;
-    const int I0 = tile * NB;
-    const int I1 = min(I0 + NB, nbrows);
-    const int g0 = bptr[I0], g1 = bptr[I1];
-    const int s0 = (g0 * (BR * BC)) & ~7;
-    const int cnt = (g1 * (BR * BC) - s0 + 7) & ~7;
-    const int b0 = g0 & ~3;
-    const int bcnt = (g1 - b0 + 3) & ~3;
-    const int d0 = dptr[tile], dcnt = dptr[tile + 1] - d0;
-    unsigned char *base = s_raw + stage_bytes * stage;
-    mbar_expect_tx(&full[stage], (unsigned)dcnt * 8u + (unsigned)cnt * 2u + (unsigned)bcnt * 4u);
-    if (dcnt > 0) bulk_g2s(base, dict + d0, (unsigned)dcnt * 8u, &full[stage]);
-    if (cnt > 0) bulk_g2s(base + off_codes, codes + s0, (unsigned)cnt * 2u, &full[stage]);
-    if (bcnt > 0) bulk_g2s(base + off_bcol, bcol + b0, (unsigned)bcnt * 4u, &full[stage]);
+    const int tile = order ? order[idx] : idx;
+    const long long o0 = toff[tile], o1 = toff[tile + 1];
+    const unsigned bytes = (unsigned)(o1 - o0) * 16u;
+    mbar_expect_tx(&full[stage], bytes);
+    if (bytes) bulk_g2s(s_raw + (size_t)cap * stage, blob + o0 * 16, bytes, &full[stage]);
   };
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
@@ -292,48 +301,56 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
     }
   }
   bool waited = xs.wait_flags == nullptr; // tiles before n_nowait read no ghost column: the wait is deferred until the first one that does
-  // values of block b of this thread's rows and the x entries they multiply
-  auto fetch = [&](const double *sd, const unsigned short *sc, const int *sb, int L, int b, double (&av)[BR][BC], double (&xv)[BC]) {
-    const int c0 = sb[b] * BC;
-    if (BC == 2) {
-      const double2 x2 = xs.load2(c0);
-      xv[0] = x2.x; xv[BC - 1] = x2.y;
-#pragma unroll
-      for (int rr = 0; rr < BR; ++rr) { // (row start + rr*L + 2b) is even: both codes in one 32-bit load
-        const unsigned pr = *reinterpret_cast<const unsigned *>(sc + rr * L + b * 2);
-        av[rr][0] = sd[pr & 0xffffu]; av[rr][BC - 1] = sd[pr >> 16];
-      }
-    } else {
-      xv[0] = xs.load(c0);
-#pragma unroll
-      for (int rr = 0; rr < BR; ++rr) av[rr][0] = sd[sc[rr * L + b]];
-    }
-  };
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
-    const int tile = tile_list ? tile_list[idx] : idx;
+    const int tile = order ? order[idx] : idx;
     if (!waited && idx >= n_nowait) { halo_wait_cta(xs); waited = true; }
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
-    const int I = tile * NB + tid;
-    const int g_al = bptr[tile * NB];
-    const int bs = bptr[I < nbrows ? I : nbrows];
-    const int be = bptr[I + 1 < nbrows ? I + 1 : nbrows];
+    const int I = tile * PD_NB + tid;
     mbar_wait(&full[stage], parity);
-    const unsigned char *base = s_raw + stage_bytes * stage;
-    const double *sd = reinterpret_cast<const double *>(base);
-    const unsigned short *sc = reinterpret_cast<const unsigned short *>(base + off_codes) + (bs * (BR * BC) - ((g_al * (BR * BC)) & ~7));
-    const int *sb = reinterpret_cast<const int *>(base + off_bcol) + (bs - (g_al & ~3));
+    const unsigned char *base = s_raw + (size_t)cap * stage;
     if (I < nbrows) {
+      const int4 hdr = *reinterpret_cast<const int4 *>(base);
+      const PdLayout L = pd_layout<BR, BC>(hdr.x, hdr.y, hdr.z);
+      const double *sd = reinterpret_cast<const double *>(base + L.o_dict);
+      const int *sp = reinterpret_cast<const int *>(base + L.o_pat) + (int)base[L.o_pid + tid] * (L.nbmax + 1);
+      const unsigned short *spos = reinterpret_cast<const unsigned short *>(base + L.o_pos);
+      const unsigned char *sc = base + L.o_codes + tid * BRBC;
+      const int nb = sp[0];
+      // values of block k of this thread's rows and the x entries they multiply
+      auto fetch = [&](int k, double (&av)[BR][BC], double (&xv)[BC]) {
+        const int c0 = (I + sp[1 + k]) * BC;
+        if (BC == 2) {
+          const double2 x2 = xs.load2(c0);
+          xv[0] = x2.x; xv[BC - 1] = x2.y;
+        } else {
+          xv[0] = xs.load(c0);
+        }
+        if (BRBC == 4) {
+          const unsigned cw = *reinterpret_cast<const unsigned *>(sc + (size_t)k * (PD_NB * 4));
+          const uint2 po = *reinterpret_cast<const uint2 *>(spos + k * 4);
+          av[0][0] = sd[(po.x & 0xffffu) + (cw & 0xffu)];
+          av[0][BC - 1] = sd[(po.x >> 16) + ((cw >> 8) & 0xffu)];
+          av[BR - 1][0] = sd[(po.y & 0xffffu) + ((cw >> 16) & 0xffu)];
+          av[BR - 1][BC - 1] = sd[(po.y >> 16) + (cw >> 24)];
+        } else if (BRBC == 2) {
+          const unsigned cw = *reinterpret_cast<const unsigned short *>(sc + (size_t)k * (PD_NB * 2));
+          const unsigned po = *reinterpret_cast<const unsigned *>(spos + k * 2);
+          av[0][0] = sd[(po & 0xffffu) + (cw & 0xffu)];
+          av[BR - 1][BC - 1] = sd[(po >> 16) + (cw >> 8)];
+        } else {
+          av[0][0] = sd[(unsigned)spos[k] + (unsigned)sc[(size_t)k * PD_NB]];
+        }
+      };
       double sum[BR];
 #pragma unroll
       for (int rr = 0; rr < BR; ++rr) sum[rr] = 0.0;
-      const int nb = be - bs, L = nb * BC;
       int b = 0;
       for (; b + UB <= nb; b += UB) {
         double av[UB][BR][BC], xv[UB][BC];
 #pragma unroll
-        for (int u = 0; u < UB; ++u) fetch(sd, sc, sb, L, b + u, av[u], xv[u]);
+        for (int u = 0; u < UB; ++u) fetch(b + u, av[u], xv[u]);
 #pragma unroll
         for (int u = 0; u < UB; ++u)
 #pragma unroll
@@ -345,7 +362,7 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
         double av[UB - 1][BR][BC], xv[UB - 1][BC];
 #pragma unroll
         for (int u = 0; u < UB - 1; ++u)
-          if (b + u < nb) fetch(sd, sc, sb, L, b + u, av[u], xv[u]);
+          if (b + u < nb) fetch(b + u, av[u], xv[u]);
 #pragma unroll
         for (int u = 0; u < UB - 1; ++u)
           if (b + u < nb) {
@@ -380,68 +397,139 @@ __global__ void k_spmv_tma_dict(int nbrows, int ntiles, const int *__restrict__ 
   if (epi.push.grp) epi.push.finish(); // fused halo push: fence, ticket, last CTA raises the neighbours' flags
 }
 
-// one CTA per tile: distinct bit patterns through a shared-memory hash set; codes are ranks in order of FIRST
-// OCCURRENCE (atomicMin of the position per key + a block scan), so the format is deterministic.  Run twice: the
-// count pass sizes the dictionaries, the write pass fills dictionaries and codes.
-__global__ void __launch_bounds__(256) k_dict_build(int nrows, int R, const int *__restrict__ rowptr, const double *__restrict__ val, int write,
-                                                    int *dcnt, const int *__restrict__ dptr, double *dict, unsigned short *codes, int *stat) {
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
-  int *minpos = reinterpret_cast<int *>(keys + DICT_T);
-  unsigned short *rank = reinterpret_cast<unsigned short *>(minpos + DICT_T);
-  unsigned short *slot = rank + DICT_T;
-  __shared__ int s_scan[256];
-  __shared__ int s_total;
-  const int tid = threadIdx.x, tile = blockIdx.x;
-  const int r0 = tile * R, r1 = min(r0 + R, nrows);
-  const int j0 = rowptr[r0], n = rowptr[r1] - j0;
-  if (n > DICT_MAX_TILE_NNZ) {
-    if (tid == 0) { stat[0] = 1; if (!write) dcnt[tile] = 0; }
+// One CTA per tile builds (write = 0: sizes only) the blob described above.  Everything is decided by position in the
+// tile (first occurrence wins, ranks are prefix counts), so the format is deterministic.  Reads the CSR arrays; the
+// block structure (BR rows of a node share their columns, columns come in aligned runs of BC) was verified by
+// k_blk_check when BR*BC > 1.
+template <int BR, int BC>
+__global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                                                  int write, int *tsize16, const int *__restrict__ toff, unsigned char *blob, int *stat) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int BRBC = BR * BC, PMAX = PD_MAX_K * BRBC;
+  int *s_delta = reinterpret_cast<int *>(s_raw);                                                   // [PD_NB][PD_MAX_K + 1]: nb, offsets
+  unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_delta + PD_NB * (PD_MAX_K + 1)); // [PMAX][PD_NB] value bits
+  unsigned char *s_first = reinterpret_cast<unsigned char *>(s_val + (size_t)PMAX * PD_NB);         // [PMAX][PD_NB] first row with this value
+  unsigned char *s_rank = s_first + (size_t)PMAX * PD_NB;                                          // [PMAX][PD_NB] rank of a first occurrence
+  __shared__ int s_pfirst[PD_NB], s_prank[PD_NB], s_cnt[PMAX], s_posoff[PMAX + 1], s_w[4];
+  __shared__ int s_nbmax, s_bad, s_npat;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+  const int I0 = tile * PD_NB;
+  if (tid == 0) { s_nbmax = 0; s_bad = 0; }
+  __syncthreads();
+  if (tid < PD_NB) {
+    const int I = I0 + tid;
+    int nb = 0;
+    if (I < nbrows) {
+      const int rs = rowptr[I * BR];
+      nb = (rowptr[I * BR + 1] - rs) / BC;
+      if (nb > PD_MAX_K) { s_bad = 1; nb = 0; }
+      for (int k = 0; k < nb; ++k) s_delta[tid * (PD_MAX_K + 1) + 1 + k] = col[rs + k * BC] / BC - I;
+    }
+    s_delta[tid * (PD_MAX_K + 1)] = nb;
+    atomicMax(&s_nbmax, nb);
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) { stat[0] = 1; if (!write) tsize16[tile] = 0; }
     return;
   }
-  for (int h = tid; h < DICT_T; h += 256) { keys[h] = DICT_EMPTY; minpos[h] = 0x7fffffff; }
-  __syncthreads();
-  for (int j = tid; j < n; j += 256) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(val[j0 + j]);
-    if (bits == DICT_EMPTY) { stat[0] = 1; slot[j] = 0; continue; } // the one pattern the set cannot hold: no dictionary
-    unsigned h = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 51) & (DICT_T - 1);
-    for (;;) {
-      const unsigned long long prev = atomicCAS(&keys[h], DICT_EMPTY, bits);
-      if (prev == DICT_EMPTY || prev == bits) break;
-      h = (h + 1) & (DICT_T - 1);
+  const int nbmax = s_nbmax, P = nbmax * BRBC;
+  // value bits by position
+  for (int idx = tid; idx < P * PD_NB; idx += 256) {
+    const int p = idx / PD_NB, i = idx % PD_NB, k = p / BRBC, e = p % BRBC, rr = e / BC, cc = e % BC;
+    unsigned long long bits = 0ull;
+    if (k < s_delta[i * (PD_MAX_K + 1)]) bits = (unsigned long long)__double_as_longlong(val[rowptr[(I0 + i) * BR + rr] + k * BC + cc]);
+    s_val[idx] = bits;
+  }
+  // column patterns: first row with the same {nb, offsets}
+  if (tid < PD_NB) {
+    const int *mine = s_delta + tid * (PD_MAX_K + 1);
+    int first = tid;
+    for (int j = 0; j < tid; ++j) {
+      const int *o = s_delta + j * (PD_MAX_K + 1);
+      bool same = o[0] == mine[0];
+      for (int k = 0; k < mine[0] && same; ++k) same = o[1 + k] == mine[1 + k];
+      if (same) { first = j; break; }
     }
-    atomicMin(&minpos[h], j);
-    slot[j] = (unsigned short)h;
+    s_pfirst[tid] = first;
   }
   __syncthreads();
-  const int C = (n + 255) / 256;
-  const int b = min(tid * C, n), e = min(b + C, n);
-  int cnt = 0;
-  for (int j = b; j < e; ++j) cnt += minpos[slot[j]] == j;
-  s_scan[tid] = cnt;
+  if (tid < PD_NB) { // rank of the first occurrences (prefix count over the tile)
+    const bool isf = s_pfirst[tid] == tid;
+    const unsigned bal = __ballot_sync(FULL, isf);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    s_prank[tid] = __popc(bal & ((1u << lane) - 1u)); // completed below with the warps before this one
+  }
+  __syncthreads();
+  if (tid < PD_NB) {
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+    s_prank[tid] += base;
+    if (tid == 0) s_npat = s_w[0] + s_w[1] + s_w[2] + s_w[3];
+  }
+  // values: first row of the tile that holds the same bits at the same position
+  for (int idx = tid; idx < P * PD_NB; idx += 256) {
+    const int p = idx / PD_NB, i = idx % PD_NB, k = p / BRBC;
+    int first = 255; // absent
+    if (k < s_delta[i * (PD_MAX_K + 1)]) {
+      const unsigned long long v = s_val[idx];
+      first = i;
+      for (int j = 0; j < i; ++j)
+        if (k < s_delta[j * (PD_MAX_K + 1)] && s_val[p * PD_NB + j] == v) { first = j; break; }
+    }
+    s_first[idx] = (unsigned char)first;
+  }
+  __syncthreads();
+  for (int p = warp; p < P; p += 8) { // one warp per position: ranks of the first occurrences, in row order
+    int base = 0;
+    for (int c = 0; c < PD_NB / 32; ++c) {
+      const int i = c * 32 + lane;
+      const bool isf = s_first[p * PD_NB + i] == i;
+      const unsigned bal = __ballot_sync(FULL, isf);
+      s_rank[p * PD_NB + i] = (unsigned char)(base + __popc(bal & ((1u << lane) - 1u)));
+      base += __popc(bal);
+    }
+    if (lane == 0) s_cnt[p] = base;
+  }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
-    for (int t = 0; t < 256; ++t) { const int v = s_scan[t]; s_scan[t] = acc; acc += v; }
-    s_total = acc;
+    for (int p = 0; p < P; ++p) { s_posoff[p] = acc; acc += s_cnt[p]; }
+    s_posoff[P] = acc;
+    if (acc > PD_MAX_DICT) s_bad = 1;
   }
   __syncthreads();
-  const int total = s_total;
-  if (!write) {
-    if (tid == 0) {
-      dcnt[tile] = (total + 1) & ~1; // 16-byte granules for the bulk copy
-      atomicMax(&stat[1], total);
-      if (total > DICT_MAX_ENTRIES) stat[0] = 1;
-    }
+  const int ndict = s_posoff[P], npat = s_npat;
+  if (s_bad) {
+    if (tid == 0) { stat[0] = 1; if (!write) tsize16[tile] = 0; }
     return;
   }
-  int at = s_scan[tid];
-  const int d0 = dptr[tile];
-  for (int j = b; j < e; ++j)
-    if (minpos[slot[j]] == j) { rank[slot[j]] = (unsigned short)at; dict[d0 + at] = val[j0 + j]; ++at; }
-  if (tid == 0 && (total & 1)) dict[d0 + total] = 0.0;
-  __syncthreads();
-  for (int j = tid; j < n; j += 256) codes[j0 + j] = rank[slot[j]];
+  const PdLayout L = pd_layout<BR, BC>(nbmax, npat, ndict);
+  if (!write) {
+    if (tid == 0) { tsize16[tile] = L.bytes / 16; atomicMax(&stat[1], L.bytes); }
+    return;
+  }
+  unsigned char *out = blob + (size_t)toff[tile] * 16; // zero-filled by the caller: padding stays zero
+  if (tid == 0) { int *h = reinterpret_cast<int *>(out); h[0] = nbmax; h[1] = npat; h[2] = ndict; h[3] = 0; }
+  double *dict = reinterpret_cast<double *>(out + L.o_dict);
+  int *pat = reinterpret_cast<int *>(out + L.o_pat);
+  unsigned short *pos = reinterpret_cast<unsigned short *>(out + L.o_pos);
+  for (int idx = tid; idx < P * PD_NB; idx += 256) {
+    const int p = idx / PD_NB, i = idx % PD_NB, k = p / BRBC, e = p % BRBC;
+    const int first = s_first[idx];
+    if (first == i) dict[s_posoff[p] + s_rank[idx]] = __longlong_as_double((long long)s_val[idx]);
+    out[L.o_codes + ((size_t)k * PD_NB + i) * BRBC + e] = first == 255 ? (unsigned char)0 : s_rank[p * PD_NB + first];
+  }
+  if (tid < PD_NB) {
+    out[L.o_pid + tid] = (unsigned char)s_prank[s_pfirst[tid]];
+    if (s_pfirst[tid] == tid) {
+      const int *mine = s_delta + tid * (PD_MAX_K + 1);
+      int *q = pat + s_prank[tid] * (nbmax + 1);
+      q[0] = mine[0];
+      for (int k = 0; k < nbmax; ++k) q[1 + k] = k < mine[0] ? mine[1 + k] : 0;
+    }
+  }
+  for (int p = tid; p < P; p += 256) pos[p] = (unsigned short)s_posoff[p];
 }
 
 // verify the block structure of block row I and count its blocks
@@ -541,54 +629,69 @@ static void ensure_wait_order(const Csr &A, int T) {
   A.wait_order_rows = T;
 }
 
-// build (or decline) the tile-local value dictionary of A; called lazily from the first un-captured TMA SpMV
-static void build_value_dict(const Csr &A) {
-  static const bool off = getenv("B200SP_NO_VALUE_DICT") && atoi(getenv("B200SP_NO_VALUE_DICT"));
+// build (or decline) the tile-local pattern/value dictionaries of A; called lazily from the first un-captured TMA SpMV
+template <int BR, int BC>
+static void build_pd(const Csr &A, int force) {
   Ctx *c = A.ctx;
-  A.dict_state = -1;
-  if (off || A.nrows == 0 || A.nnz < 4096 || spmv_tma_tile_rows() != TMA_TILE_ROWS) return;
-  const int R = TMA_TILE_ROWS * (A.bcol.p ? A.blk_r : 1), ntiles = (A.nrows + R - 1) / R; // one thread per block row
-  A.dict_rows = R;
-  DevBuf<int> cnt((size_t)ntiles + 1), stat(2);
+  const int nbrows = A.nrows / BR, ntiles = (nbrows + PD_NB - 1) / PD_NB;
+  DevBuf<int> tsize((size_t)ntiles + 1), stat(2);
   stat.zero(c->stream);
-  const size_t smem = (size_t)DICT_T * 14 + (size_t)DICT_MAX_TILE_NNZ * 2;
-  static bool attr = false;
-  if (!attr) { B2_CUDA(cudaFuncSetAttribute(k_dict_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  { LaunchScope ls(c, "setup"); k_dict_build<<<ntiles, 256, smem, c->stream>>>(A.nrows, R, A.rowptr.p, A.val.p, 0, cnt.p, nullptr, nullptr, nullptr, stat.p); check_launch("k_dict_build"); }
+  constexpr int PMAX = PD_MAX_K * BR * BC;
+  const size_t smem = (size_t)PD_NB * (PD_MAX_K + 1) * 4 + (size_t)PMAX * PD_NB * 10;
+  // (the attribute is per device and this kernel has four instantiations: set it on every build, setup path only)
+  B2_CUDA(cudaFuncSetAttribute(k_pd_build<BR, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 0, tsize.p, nullptr, nullptr, stat.p); check_launch("k_pd_build"); }
   int h_stat[2] = {0, 0};
   B2_CUDA(cudaMemcpyAsync(h_stat, stat.p, sizeof(h_stat), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
-  if (h_stat[0]) return;
-  A.dptr.alloc((size_t)ntiles + 1);
-  int total = 0;
-  exclusive_scan_i32(c, cnt.p, A.dptr.p, ntiles, &total);
-  // worth it only if dictionary + codes are clearly smaller than the 8 B/nnz value stream
-  if ((double)total * 8.0 + (double)A.nnz * 2.0 > 0.75 * 8.0 * (double)A.nnz) { A.dptr.release(); return; }
-  A.dict.alloc((size_t)total + 16);
-  A.codes.alloc((size_t)A.nnz + 32);
-  A.codes.zero(c->stream);
-  { LaunchScope ls(c, "setup"); k_dict_build<<<ntiles, 256, smem, c->stream>>>(A.nrows, R, A.rowptr.p, A.val.p, 1, nullptr, A.dptr.p, A.dict.p, A.codes.p, stat.p); check_launch("k_dict_build"); }
+  if (h_stat[0]) return; // a row with more than PD_MAX_K blocks, or a tile with too many distinct values
+  A.pd_off.alloc((size_t)ntiles + 1);
+  int total16 = 0;
+  exclusive_scan_i32(c, tsize.p, A.pd_off.p, ntiles, &total16);
+  const double total = 16.0 * (double)total16;
+  // worth it only if the blobs are clearly smaller than what the plain kernels stream (values + (block) column index)
+  const double alt = 8.0 * (double)A.nnz + 4.0 * (double)A.nnz / (double)(BR * BC);
+  if (force < 2 && total > 0.6 * alt) { A.pd_off.release(); return; }
+  A.pd_blob.alloc((size_t)total16 * 16 + 256);
+  A.pd_blob.zero(c->stream);
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 1, nullptr, A.pd_off.p, A.pd_blob.p, stat.p); check_launch("k_pd_build"); }
   c->sync();
-  // Measured (profiles/r01_value_dict_sweep.txt): the dictionary wins whenever the block-row kernel applies (A 2x2,
-  // B^T 2x1, B 1x2: 1.7-1.9x over the plain value stream), for long scalar rows, and for tiny dictionaries (R: the
-  // lookup is a shared-memory broadcast); for scalar matrices with 9 nnz/row and a few hundred distinct values per
-  // tile (C, Q) the extra dependent shared-memory lookup costs more than the smaller stream saves.
-  static const int force = getenv("B200SP_VALUE_DICT") ? atoi(getenv("B200SP_VALUE_DICT")) : 0;
-  if (force < 2 && !A.bcol.p && (double)A.nnz / A.nrows < 12.0 && h_stat[1] > 32) { A.dptr.release(); A.dict.release(); A.codes.release(); return; }
-  A.dict_cap = (h_stat[1] + 1) & ~1;
-  if (A.dict_cap < 2) A.dict_cap = 2;
-  A.dict_bytes = (int64_t)total * 8;
+  A.pd_cap = (h_stat[1] + 127) & ~127;
+  A.dict_rows = PD_NB * BR;
+  A.dict_bytes = (int64_t)total16 * 16 + 4 * (int64_t)(ntiles + 1);
   A.dict_state = 1;
 }
+static void build_value_dict(const Csr &A) {
+  static const bool off = getenv("B200SP_NO_VALUE_DICT") && atoi(getenv("B200SP_NO_VALUE_DICT"));
+  static const int force = getenv("B200SP_VALUE_DICT") ? atoi(getenv("B200SP_VALUE_DICT")) : 0;
+  A.dict_state = -1;
+  if (off || A.no_value_dict || A.nrows == 0 || A.nnz < 4096) return;
+  const int br = A.bcol.p ? A.blk_r : 1, bc = A.bcol.p ? A.blk_c : 1;
+  if (br == 2 && bc == 2) build_pd<2, 2>(A, force);
+  else if (br == 2 && bc == 1) build_pd<2, 1>(A, force);
+  else if (br == 1 && bc == 2) build_pd<1, 2>(A, force);
+  else build_pd<1, 1>(A, force);
+}
 void csr_drop_value_dict(Csr &A) {
-  A.dict.release(); A.dptr.release(); A.codes.release();
-  A.dict_state = 0; A.dict_cap = 0; A.dict_rows = 0; A.dict_bytes = 0;
+  A.pd_blob.release(); A.pd_off.release();
+  A.dict_state = 0; A.pd_cap = 0; A.dict_rows = 0; A.dict_bytes = 0;
 }
 
 // returns false when the matrix does not fit the shared-memory tiling (caller falls back)
 int spmv_tma_tile_rows() {
   static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;
   return env_R ? env_R : TMA_TILE_ROWS;
+}
+
+// co-resident CTAs per SM for `smem` bytes of dynamic shared memory and `threads` threads per CTA.  Every CTA also
+// reserves 1 KB of the SM's 228 KB: ignoring that asked for 8 CTAs per SM where 7 fit, and the persistent grid ran a
+// second, nearly empty wave (C block: 0.171 ms instead of 0.112 ms).
+static int ctas_per_sm(size_t smem, int threads) {
+  int n = (int)((size_t)(228 * 1024) / (smem + 1024));
+  if (n < 1) n = 1;
+  if (n * threads > 2048) n = 2048 / threads;
+  if (n > 32) n = 32;
+  return n;
 }
 
 bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list, int nlist) {
@@ -611,18 +714,15 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   }
   if (!R) return false;
   const size_t smem = (size_t)cap * 12 * stages + 8 * TMA_MAX_STAGES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(c->attr_mask & 4u)) {
     B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
+    c->attr_mask |= 4u;
   }
   if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
   const int ntiles = tile_list ? nlist : (A.nrows + R - 1) / R;
   if (ntiles <= 0) return true;
-  int per_sm = (int)(budget / smem);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm * R > 2048) per_sm = 2048 / R;
+  const int per_sm = ctas_per_sm(smem, R);
   int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
   if (A.dict_state == 0) { // lazily, never while a CUDA graph is being recorded
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -630,62 +730,49 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     if (st == cudaStreamCaptureStatusNone) build_value_dict(A);
   }
   const int dbr = A.bcol.p ? A.blk_r : 1, dbc = A.bcol.p ? A.blk_c : 1;
-  if (A.dict_state == 1 && R == TMA_TILE_ROWS && !tile_list && A.dict_rows == TMA_TILE_ROWS * dbr &&
-      (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // tile-local value dictionary, one thread per block row
-    const int capt = cap * dbr;                       // nonzeros per tile of 128 block rows
-    const int capc = (capt + 16) & ~7;
-    const int capb = ((capt / (dbr * dbc) + 8) + 3) & ~3;
-    const size_t smem_d = ((size_t)A.dict_cap * 8 + (size_t)capc * 2 + (size_t)capb * 4) * stages + 8 * TMA_MAX_STAGES;
-    if (smem_d <= budget) {
-      static bool attr_d = false;
-      if (!attr_d) {
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_dict<1, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_d = true;
-      }
-      int psm = (int)(budget / smem_d);
-      if (psm < 1) psm = 1;
-      if (psm * R > 2048) psm = 2048 / R;
-      static const int env_psm = getenv("B200SP_TMA_CTAS") ? atoi(getenv("B200SP_TMA_CTAS")) : 0;
-      if (env_psm && env_psm < psm) psm = env_psm;
-      const int nbrows = A.nrows / dbr;
-      const int ntd = (nbrows + R - 1) / R;
-      const int gridd = ntd < c->num_sms * psm ? ntd : c->num_sms * psm;
-      const int *bp = A.bcol.p ? A.bptr.p : A.rowptr.p, *bc = A.bcol.p ? A.bcol.p : A.col.p;
-      const int *order = nullptr;
-      int n_nowait = 0;
-      if (xs.wait_flags) { ensure_wait_order(A, R * dbr); if (A.wait_order_rows == R * dbr) { order = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
-      auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-      SpmvEpi e2 = epi;
-      e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
-#define B200SP_DICT_LAUNCH(BR_, BC_, UB_) \
-  k_spmv_tma_dict<BR_, BC_, UB_><<<gridd, R, smem_d, c->stream>>>(nbrows, ntd, order, bp, bc, A.dptr.p, A.dict.p, A.codes.p, xs, y, e2, capc, capb, A.dict_cap, stages, n_nowait)
-      if (dbr == 2 && dbc == 2) B200SP_DICT_LAUNCH(2, 2, 3);
-      else if (dbr == 2 && dbc == 1) B200SP_DICT_LAUNCH(2, 1, 3);
-      else if (dbr == 1 && dbc == 2) B200SP_DICT_LAUNCH(1, 2, 3);
-      else B200SP_DICT_LAUNCH(1, 1, 6);
-#undef B200SP_DICT_LAUNCH
-      check_launch("k_spmv_tma_dict");
-      return true;
+  if (A.dict_state == 1 && !tile_list && (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // tile-local dictionaries, one thread per block row
+    const size_t smem_d = (size_t)A.pd_cap * 2 + 8 * TMA_MAX_STAGES;
+    if (!(c->attr_mask & 8u)) {
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<1, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      c->attr_mask |= 8u;
     }
+    int psm = ctas_per_sm(smem_d, PD_NB);
+    static const int env_psm = getenv("B200SP_TMA_CTAS") ? atoi(getenv("B200SP_TMA_CTAS")) : 0;
+    if (env_psm && env_psm < psm) psm = env_psm;
+    const int nbrows = A.nrows / dbr;
+    const int ntd = (nbrows + PD_NB - 1) / PD_NB;
+    const int gridd = ntd < c->num_sms * psm ? ntd : c->num_sms * psm;
+    const int *order = nullptr;
+    int n_nowait = 0;
+    if (xs.wait_flags) { ensure_wait_order(A, PD_NB * dbr); if (A.wait_order_rows == PD_NB * dbr) { order = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    SpmvEpi e2 = epi;
+    e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
+#define B200SP_PD_LAUNCH(BR_, BC_, UB_) \
+  k_spmv_pd<BR_, BC_, UB_><<<gridd, PD_NB, smem_d, c->stream>>>(nbrows, ntd, order, A.pd_off.p, A.pd_blob.p, xs, y, e2, A.pd_cap, 2, n_nowait)
+    if (dbr == 2 && dbc == 2) B200SP_PD_LAUNCH(2, 2, 3);
+    else if (dbr == 2 && dbc == 1) B200SP_PD_LAUNCH(2, 1, 3);
+    else if (dbr == 1 && dbc == 2) B200SP_PD_LAUNCH(1, 2, 3);
+    else B200SP_PD_LAUNCH(1, 1, 3);
+#undef B200SP_PD_LAUNCH
+    check_launch("k_spmv_pd");
+    return true;
   }
   int n_nowait = 0;
   if (xs.wait_flags && !tile_list) { ensure_wait_order(A, R); if (A.wait_order_rows == R) { tile_list = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
   if (A.bcol.p) { // block-compressed column index: 8 + 4/(BR*BC) bytes per nonzero (R is a multiple of BR)
     const int capb = ((cap / (A.blk_r * A.blk_c) + 8) + 3) & ~3;
     const size_t smem_b = ((size_t)cap * 8 + (size_t)capb * 4) * stages + 8 * TMA_MAX_STAGES;
-    static bool attr_b = false;
-    if (!attr_b) {
+    if (!(c->attr_mask & 16u)) {
       B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<1, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      attr_b = true;
+      c->attr_mask |= 16u;
     }
-    int psm = (int)(budget / smem_b);
-    if (psm < 1) psm = 1;
-    if (psm * R > 2048) psm = 2048 / R;
+    const int psm = ctas_per_sm(smem_b, R);
     const int gridb = ntiles < c->num_sms * psm ? ntiles : c->num_sms * psm;
     if (A.blk_r == 2 && A.blk_c == 2)
       k_spmv_tma_blk<2, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages, n_nowait);

@@ -18,7 +18,11 @@ void Ctx::fetch_scalars(const double *d, int k, double *host) {
   B2_REQUIRE(k <= N_SCALARS, "fetch_scalars: too many scalars");
   B2_CUDA(cudaMemcpyAsync(h_scalars, d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, stream));
   B2_CUDA(cudaStreamSynchronize(stream));
-  if (h_err && *h_err) throw Error(B200SP_ERR_NCCL, "peer-to-peer halo exchange timed out waiting for a neighbour (code " + std::to_string(*h_err) + ")");
+  if (h_err && *h_err) { // sticky on the device side only until reported: clear it so that later calls are judged on their own
+    const int code = *h_err;
+    *h_err = 0;
+    throw Error(B200SP_ERR_NCCL, "peer-to-peer halo exchange timed out waiting for a neighbour (code " + std::to_string(code) + ")");
+  }
   std::memcpy(host, h_scalars, sizeof(double) * (size_t)k);
 }
 static void allreduce_sum(Ctx *c, double *d, int k) { // MPI_Allreduce(SUM) equivalent for VecDot/VecMDot/VecNorm
@@ -670,8 +674,27 @@ void Solver::set_options(const char *text) {
   is_setup = false;
 }
 std::string Solver::opt(const std::string &key, const std::string &def) const {
+  used[key] = true;
   auto it = opts.find(key);
   return it == opts.end() ? def : it->second;
+}
+
+// PETSc prints unused options with -options_left; here an unused SOLVER option is an error: it means a mistyped key or a
+// feature this library does not have, and either way the solve would silently differ from what PETSc would run.
+// Options the caller handles itself (monitors, viewers) are exempt.
+void Solver::check_options_left() const {
+  static const char *caller_side[] = {"ksp_monitor", "ksp_monitor_true_residual", "ksp_converged_reason", "ksp_view", "ksp_view_pre", "pc_view", nullptr};
+  std::string left;
+  for (auto &kv : opts) {
+    const std::string &k = kv.first;
+    const bool solver_key = k.find("ksp_") != std::string::npos || k.find("pc_") != std::string::npos || k.rfind("fieldsplit_", 0) == 0 ||
+                            k.rfind("mg_", 0) == 0 || k.rfind("b200sp_", 0) == 0;
+    if (!solver_key || used.count(k)) continue;
+    bool exempt = false;
+    for (const char **c = caller_side; *c; ++c) exempt = exempt || k == *c;
+    if (!exempt) left += " -" + k;
+  }
+  if (!left.empty()) throw Error(B200SP_ERR_UNSUPPORTED, "options not used by any solver object (unknown or unsupported here):" + left);
 }
 
 static int ksp_type_from(const std::string &s) {
@@ -705,6 +728,16 @@ Ksp *Solver::make_ksp(const std::string &prefix, Op *A, Op *M, const char *defau
   const std::string nt = opt(prefix + "ksp_norm_type", "");
   // inner chebyshev / richardson solvers are fixed-sweep smoothers unless a norm type is requested
   if (nt == "none" || (nt.empty() && !prefix.empty() && (k->type == KSP_CHEBYSHEV || k->type == KSP_RICHARDSON))) k->norm_none = true;
+  { // -ksp_pc_side / -ksp_norm_type: each method is implemented with PETSc's DEFAULT side and norm only; anything else is rejected
+    const bool right = k->type == KSP_FGMRES;
+    const std::string side = opt(prefix + "ksp_pc_side", right ? "right" : "left");
+    if (side != (right ? "right" : "left"))
+      throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "ksp_pc_side " + side + ": " + tname + " is implemented with " + (right ? "right" : "left") + " preconditioning only");
+    const std::string natural = right ? "unpreconditioned" : "preconditioned";
+    const bool krylov = k->type == KSP_GMRES || k->type == KSP_FGMRES || k->type == KSP_MINRES;
+    if (!nt.empty() && nt != "default" && !(nt == natural) && !(nt == "none" && !krylov))
+      throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "ksp_norm_type " + nt + ": " + tname + " monitors the " + natural + " residual norm only");
+  }
   if (k->type == KSP_CHEBYSHEV) {
     const std::string ev = opt(prefix + "ksp_chebyshev_eigenvalues", "");
     if (!ev.empty()) {
@@ -722,6 +755,11 @@ Ksp *Solver::make_ksp(const std::string &prefix, Op *A, Op *M, const char *defau
 }
 
 Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, const char *default_type) {
+  // PETSc's default PC on an assembled AIJ matrix is ILU(0) (block Jacobi + ILU(0) on more than one rank), which is not
+  // on this library's kernel list: an unspecified -pc_type is an error, not a silent substitute
+  if (!has(prefix + "pc_type") && std::string(default_type) == "petsc-default")
+    throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "pc_type not given: PETSc would use ILU(0) here, which this library does not provide; "
+                                        "choose one of none, jacobi, mg, lu" + (prefix.empty() ? ", fieldsplit" : ""));
   const std::string t = opt(prefix + "pc_type", default_type);
   if (t == "none") return nullptr;
   if (t == "jacobi") return add_op<JacobiOp>(*mat);
@@ -737,7 +775,11 @@ Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, 
 // estimates must not be all-reduced.
 static void smoother_setup(Solver *S, Ksp *k, const std::string &sp, Op *Aop, Op *jac, bool local_only,
                            const std::map<std::string, std::string> &opts) {
-  auto opt = [&](const std::string &key, const std::string &def) { auto it = opts.find(key); return it == opts.end() ? def : it->second; };
+  auto opt = [&](const std::string &key, const std::string &def) { S->used[key] = true; auto it = opts.find(key); return it == opts.end() ? def : it->second; };
+  // PETSc's PCMG default smoother is Chebyshev + SOR; SOR is not on this library's kernel list, so the level PC is
+  // Jacobi and any other explicit choice is rejected
+  const std::string lpc = opt(sp + "pc_type", "jacobi");
+  if (lpc != "jacobi") throw Error(B200SP_ERR_UNSUPPORTED, "-" + sp + "pc_type " + lpc + ": the multigrid smoother preconditioner is jacobi only");
   k->set_operators(Aop, jac);
   const std::string t = opt(sp + "ksp_type", "chebyshev");
   k->type = t == "richardson" ? KSP_RICHARDSON : KSP_CHEBYSHEV;
@@ -917,7 +959,7 @@ Op *Solver::make_fieldsplit() {
   const double scale = std::stod(opt("pc_fieldsplit_schur_scale", "-1.0"));
   // K0: -fieldsplit_0_ KSP on A00
   Op *A00op = add_op<CsrOp>(A00);
-  Op *pc0 = make_simple_pc("fieldsplit_0_", A00, "jacobi");
+  Op *pc0 = make_simple_pc("fieldsplit_0_", A00, "petsc-default");
   Ksp *k0 = make_ksp("fieldsplit_0_", A00op, pc0, "preonly");
   Op *K0 = add_op<KspOp>(k0);
   // S with its own identically configured inner KSP (MatSchurComplementGetKSP)
@@ -936,7 +978,7 @@ Op *Solver::make_fieldsplit() {
     Sp = csr_add_scaled(*A11, -1.0, *prod);
     mats.push_back(Sp);
   } else if (pre != "self") throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -pc_fieldsplit_schur_precondition " + pre);
-  const std::string pt = opt("fieldsplit_1_pc_type", Sp ? "jacobi" : "none");
+  const std::string pt = opt("fieldsplit_1_pc_type", Sp ? "petsc-default" : "none");
   Op *pcS = nullptr;
   if (pt == "lsc") {
     const bool sd = has("fieldsplit_1_pc_lsc_scale_diag");
@@ -948,14 +990,14 @@ Op *Solver::make_fieldsplit() {
     } else Lm = csr_matmat(*A10, *A01);
     mats.push_back(Lm);
     Op *Lop = add_op<CsrOp>(Lm);
-    Op *pcl = make_simple_pc("fieldsplit_1_lsc_", Lm, "jacobi");
-    Ksp *kl = make_ksp("fieldsplit_1_lsc_", Lop, pcl, "preonly");
+    Op *pcl = make_simple_pc("fieldsplit_1_lsc_", Lm, "petsc-default");
+    Ksp *kl = make_ksp("fieldsplit_1_lsc_", Lop, pcl, "gmres"); // PCLSC creates a fresh KSP: GMRES unless told otherwise
     Op *Linv = add_op<KspOp>(kl);
     pcS = add_op<LscOp>(A00, A01, A10, Linv, sd);
   } else if (pt != "none" && Sp) {
-    pcS = make_simple_pc("fieldsplit_1_", Sp, "jacobi");
+    pcS = make_simple_pc("fieldsplit_1_", Sp, "petsc-default");
   }
-  Ksp *kS = make_ksp("fieldsplit_1_", S, pcS, "preonly");
+  Ksp *kS = make_ksp("fieldsplit_1_", S, pcS, "gmres"); // the Schur KSP is a fresh KSP in PETSc: GMRES unless told otherwise
   Op *KS = add_op<KspOp>(kS);
   Op *fsop = add_op<FieldSplitOp>(fact, scale, A01, A10, K0, KS);
   if (!strided_map.empty()) return add_op<StridedSplitOp>(fsop, strided_map);
@@ -964,21 +1006,27 @@ Op *Solver::make_fieldsplit() {
 
 void Solver::setup() {
   B2_REQUIRE(Amat && Pmat, "KSPSetUp: operators not set");
+  outer = nullptr; outer_pc = nullptr; is_setup = false; // a setup() that throws must not leave pointers into the cleared trees
   ops.clear(); ksps.clear(); mats.clear();
+  used.clear();
   Op *Aop = Amat->nest ? (Op *)add_op<NestOp>(Amat->blk[0][0], Amat->blk[0][1], Amat->blk[1][0], Amat->blk[1][1]) : (Op *)add_op<CsrOp>(Amat->csr);
-  const std::string pt = opt("pc_type", "none");
+  const std::string pt = opt("pc_type", "petsc-default");
+  if (pt == "petsc-default")
+    throw Error(B200SP_ERR_UNSUPPORTED, "-pc_type not given: PETSc would use ILU(0) (block Jacobi + ILU(0) in parallel), which this library does not "
+                                        "provide; choose one of none, jacobi, mg, lu, fieldsplit");
   Op *pc = nullptr;
   if (pt == "fieldsplit") {
     B2_REQUIRE(Pmat->nest || !ctx->dcomm, "pc fieldsplit on a monolithic matrix: single GPU only (use the nest layout when row-partitioned)");
     pc = make_fieldsplit();
   } else {
     B2_REQUIRE(!Pmat->nest, "pc " + pt + " on a nest matrix: use -pc_type fieldsplit");
-    pc = make_simple_pc("", Pmat->csr, "none");
+    pc = make_simple_pc("", Pmat->csr, "petsc-default");
   }
   outer_pc = pc;
   outer = make_ksp("", Aop, pc, "gmres");
   outer->keep_history = true;
   outer->use_pc_graph = pc && opt("b200sp_pc_graph", "1") != "0" && pc->capturable() && (!ctx->dcomm || ctx->dcomm->capturable());
+  check_options_left();
   ctx->sync();
   setup_state = Amat->state() + Pmat->state() + (schur_user ? schur_user->state : 0);
   is_setup = true;

@@ -195,7 +195,11 @@ double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits, bool local_only = fal
 struct Solver {
   Ctx *ctx;
   std::map<std::string, std::string> opts;
-  Mat *Amat = nullptr, *Pmat = nullptr;
+  // operators are held BY VALUE: a Mat is a handle on shared CSR blocks, so the caller may destroy its matrix handles
+  // before KSPSolve / KSPDestroy (PETSc reference-counts the operators of KSPSetOperators)
+  Mat Amat_, Pmat_;
+  Mat *Amat = nullptr, *Pmat = nullptr; // point at the copies above once the operators are set
+  void set_operators(const Mat &A, const Mat &P) { Amat_ = A; Pmat_ = P; Amat = &Amat_; Pmat = &Pmat_; is_setup = false; }
   std::shared_ptr<Csr> schur_user;
   bool have_grid = false;
   int grid_M = 0, grid_N = 0;
@@ -209,13 +213,17 @@ struct Solver {
   bool current() const { return is_setup && Amat && Pmat && Amat->state() + Pmat->state() + (schur_user ? schur_user->state : 0) == setup_state; }
   DevBuf<double> host_b, host_x; // device staging for b200sp_ksp_solve_host
   explicit Solver(Ctx *c) : ctx(c) {}
+  // every key a solver object reads is recorded; setup() then rejects solver options nobody consumed (PETSc's
+  // -options_left, promoted to an error: a mistyped or unsupported option must not silently select another solver)
+  mutable std::map<std::string, bool> used;
   void set_options(const char *text);
   void setup();
   std::string view() const;
 
 private:
   std::string opt(const std::string &key, const std::string &def) const;
-  bool has(const std::string &key) const { return opts.count(key) != 0; }
+  bool has(const std::string &key) const { used[key] = true; return opts.count(key) != 0; }
+  void check_options_left() const;
   template <class T, class... Args> T *add_op(Args &&...args) {
     ops.emplace_back(new T(std::forward<Args>(args)...));
     return static_cast<T *>(ops.back().get());

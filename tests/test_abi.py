@@ -174,8 +174,8 @@ def test_sass_shows_tma_staging_and_unfused_multiply_add():
         m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m and cur:
             ops[cur].add(m.group(1).split(".")[0])
-    tma = [k for k in ops if "k_spmv_tma" in k]
-    assert len(tma) >= 8, sorted(ops)[:5]                      # plain (2 unrolls) + block index (3) + dictionary (4)
+    tma = [k for k in ops if "k_spmv_tma" in k or "k_spmv_pd" in k]
+    assert len(tma) >= 9, sorted(ops)[:5]                      # plain (2 unrolls) + block index (3) + tile dictionaries (4)
     for k in tma:
         assert "UBLKCP" in ops[k] and "SYNCS" in ops[k], k
     for k in [k for k in ops if "k_spmv" in k]:

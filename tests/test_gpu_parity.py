@@ -189,7 +189,8 @@ def test_spmv_compressed_storage(ctx):
         Dr.mult(xd, yd)
         assert not Dr.spmv_format()["value_dict"]
         assert same_bits(yd.numpy(), Or.mult(x))
-    # few distinct values, some of them awkward (signed zero, denormal, huge, tiny): dictionary on a plain-CSR matrix
+    # few distinct values, some of them awkward (signed zero, denormal, huge, tiny): the random pattern above does not
+    # compress (every row has its own column pattern), so the values stay a plain stream there ...
     palette = np.array([-0.0, 0.0, 5e-324, -1.7976931348623157e308, 1e-300, 0.1, -0.1, 1.0 / 3.0])
     S = R.copy()
     S.data = palette[rng.integers(0, len(palette), size=S.nnz)]
@@ -197,10 +198,24 @@ def test_spmv_compressed_storage(ctx):
     Os = so.Csr.from_arrays(n, n, S.indptr, S.indices, S.data)
     x = rand_vec(n, 24) * 1e-3
     xd, yd = sp.Vec.from_numpy(ctx, x), sp.Vec(ctx, n)
-    if Ds.spmv_plan()["kernel"] == 3:
-        Ds.mult(xd, yd)
-        assert Ds.spmv_format()["value_dict"] and Ds.spmv_format()["block"] == (1, 1)
-        assert same_bits(yd.numpy(), Os.mult(x))
+    Ds.mult(xd, yd)
+    assert same_bits(yd.numpy(), Os.mult(x))
+    # ... while on a stencil pattern (fixed column offsets, clipped at the ends) the tile dictionaries take over: plain
+    # CSR matrix (no node blocks), 9 offsets, the same awkward palette
+    offs = [-70, -69, -68, -1, 0, 1, 68, 69, 70]
+    T = sps.diags([np.ones(n - abs(o)) for o in offs], offs, shape=(n, n), format="csr")
+    T.sort_indices()
+    T.data = palette[rng.integers(0, len(palette), size=T.nnz)]
+    Dt = sp.Mat.from_scipy(ctx, T)
+    Ot = so.Csr.from_arrays(n, n, T.indptr, T.indices, T.data)
+    if Dt.spmv_plan()["kernel"] == 3:
+        Dt.mult(xd, yd)
+        assert Dt.spmv_format()["value_dict"] and Dt.spmv_format()["block"] == (1, 1)
+        assert same_bits(yd.numpy(), Ot.mult(x))
+        Dt.set_spmv_format(block_index=False, value_dict=False)       # the same matrix through the plain stream
+        Dt.mult(xd, yd)
+        assert not Dt.spmv_format()["value_dict"]
+        assert same_bits(yd.numpy(), Ot.mult(x))
 
 
 def test_spmv_linearity_at_scale(ctx):
