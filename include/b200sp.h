@@ -167,6 +167,10 @@ int b200sp_mat_zero_columns(b200sp_mat A, int n, const int *cols);
 /* MATNEST 2x2 [A00 A01; A10 A11] acting on [x0; x1] stored contiguously (A11 may be NULL) */
 int b200sp_mat_create_nest(b200sp_mat A00, b200sp_mat A01, b200sp_mat A10, b200sp_mat A11, b200sp_mat *K);
 
+/* measurement hook (bench.py --config sweep): time the fused Gram-Schmidt kernels of the GMRES drivers (VecMDot against a
+ * strided basis of k vectors; VecMAXPY fused with VecNorm) over `reps` launches each, CUDA events, milliseconds per launch */
+int b200sp_bench_orthogonalization(b200sp_ctx ctx, int64_t n, int k, int reps, double *ms_mdot, double *ms_maxpy);
+
 /* ---- device assembly: replaces AssembleOperator_Laplace / AssembleRHS_Laplace / ApplyBC_Laplace and
  *      the stubbed AssembleOperator_Constraints (src/Discretization.c:130-290) ---- */
 /* A: DMCreateMatrix pattern + element stress matrices summed in the reference's element order */

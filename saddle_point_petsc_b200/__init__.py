@@ -73,6 +73,7 @@ _SIGS = {
     "b200sp_vec_norm": [_vp, c_dp],
     "b200sp_vec_mdot": [_vp, C.c_int, C.POINTER(_vp), c_dp],
     "b200sp_vec_maxpy": [_vp, C.c_int, c_dp, C.POINTER(_vp)],
+    "b200sp_bench_orthogonalization": [_vp, C.c_int64, C.c_int, C.c_int, c_dp, c_dp],
     "b200sp_mat_create_csr": [_vp, C.c_int, C.c_int, c_ip, c_ip, c_dp, C.POINTER(_vp)],
     "b200sp_mat_create_coo": [_vp, C.c_int, C.c_int, C.c_int64, c_ip, c_ip, c_dp, C.POINTER(_vp)],
     "b200sp_mat_destroy": [_vp],
@@ -260,6 +261,12 @@ class Context:
         buf = C.create_string_buffer(1 << 16)
         _chk(lib().b200sp_ctx_profile_report(self.h, buf, len(buf)))
         return json.loads(buf.value.decode())
+
+    def bench_orthogonalization(self, n, k, reps=10):
+        """(ms per VecMDot launch, ms per VecMAXPY+norm launch) of the fused GMRES kernels on k basis vectors"""
+        a, b = C.c_double(), C.c_double()
+        _chk(lib().b200sp_bench_orthogonalization(self.h, n, k, reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def destroy(self):
         if self.h:

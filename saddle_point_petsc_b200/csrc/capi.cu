@@ -389,6 +389,37 @@ int b200sp_vec_maxpy(b200sp_vec y, int k, const double *a, const b200sp_vec *x) 
   API_END
 }
 
+// measurement hook (bench.py --config sweep): the fused Gram-Schmidt kernels of the GMRES drivers -- VecMDot of w against a
+// strided basis of k vectors, and VecMAXPY fused with the norm -- timed with CUDA events over `reps` launches each
+int b200sp_bench_orthogonalization(b200sp_ctx ctx, int64_t n, int k, int reps, double *ms_mdot, double *ms_maxpy) {
+  API_BEGIN
+  B2_REQUIRE(ctx && n > 0 && k >= 1 && k <= 30 && reps >= 1, "bench_orthogonalization: bad arguments");
+  Ctx *c = &ctx->c;
+  use_device(c);
+  const int64_t ld = (n + 15) & ~(int64_t)15;
+  DevBuf<double> V((size_t)ld * k), w((size_t)ld);
+  vec_hash(c, ld * k, V.p);
+  vec_hash(c, n, w.p);
+  double *h = c->d_scalars;
+  auto timed = [&](auto fn) {
+    fn();
+    B2_CUDA(cudaEventRecord(c->tev0, c->stream));
+    for (int r = 0; r < reps; ++r) fn();
+    B2_CUDA(cudaEventRecord(c->tev1, c->stream));
+    B2_CUDA(cudaEventSynchronize(c->tev1));
+    float f = 0;
+    B2_CUDA(cudaEventElapsedTime(&f, c->tev0, c->tev1));
+    return (double)f / reps;
+  };
+  const double t1 = timed([&] { vec_mdot(c, n, k, w.p, V.p, ld, h); });
+  B2_CUDA(cudaMemsetAsync(h, 0, sizeof(double) * (size_t)(k + 1), c->stream)); // zero coefficients: w stays bounded over the repetitions
+  const double t2 = timed([&] { vec_maxpy_norm2(c, n, k, w.p, V.p, ld, h, h + k); });
+  if (ms_mdot) *ms_mdot = t1;
+  if (ms_maxpy) *ms_maxpy = t2;
+  c->sync();
+  API_END
+}
+
 // ---------------------------------------------------------------- Mat
 static b200sp_mat wrap(Ctx *c, std::shared_ptr<Csr> A) {
   auto *h = new b200sp_mat_s();

@@ -88,6 +88,10 @@ void exclusive_scan_i32(Ctx *c, const int *in, int *out, int64_t n, int *total_h
 }
 
 static std::shared_ptr<Csr> csr_alloc(Ctx *c, int nrows, int ncols, int64_t nnz) {
+  // row pointers and entry offsets are 32-bit (PetscInt in the reference's build): one rank holds < 2^31 entries;
+  // larger problems are row-partitioned (per-rank local indexing)
+  if (nnz < 0 || nnz >= (int64_t)2147483647 - CSR_PAD)
+    throw Error(B200SP_ERR_UNSUPPORTED, "matrix with " + std::to_string(nnz) + " stored entries on one rank: 32-bit row pointers hold < 2^31; use more ranks");
   auto A = std::make_shared<Csr>();
   A->ctx = c;
   A->nrows = nrows;

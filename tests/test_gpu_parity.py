@@ -351,6 +351,32 @@ def test_kkt_solve_parity(ctx, name, nx):
     assert np.allclose(rd["history"][:m - 1], ro["history"][:m - 1], rtol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["fgmres_schur_mg", "gmres_schur_mg", "minres_diag_mg"])
+def test_kkt_solve_parity_at_1m_dof(ctx, name):
+    """The benchmark configurations at nx = 576 (998,787 DOF, full multigrid depth, graph-replayed preconditioner, tile
+    dictionaries): iterations +-1, final relative residual within 1e-10, solution within rel 1e-8 of the oracle's."""
+    import bench
+    nx = 576
+    opts = bench.options_for(name, nx)
+    so.lib().or_set_threads(bench.host_threads())
+    dev, orc, ksp, rd, ro, x = run_pair(ctx, nx, nx, opts)
+    for rep in range(2):                     # the later solves replay the recorded CUDA graphs: same bits as the first
+        xr = sp.Vec(ctx, dev.n)
+        r2 = ksp.solve(dev.rhs, xr)
+        assert r2["its"] == rd["its"] and np.array_equal(xr.numpy(), x)
+    assert rd["reason"] == ro["reason"] == 2, (rd["reason"], ro["reason"])
+    assert abs(rd["its"] - ro["its"]) <= 1, (rd["its"], ro["its"])
+    rel_d, rel_o = rd["rnorm"] / rd["history"][0], ro["rnorm"] / ro["history"][0]
+    nu = dev.nu
+    if rd["its"] == ro["its"]:
+        assert abs(rel_d - rel_o) <= 1e-10, (rel_d, rel_o)
+        assert np.max(np.abs(x[:nu] - ro["x"][:nu])) <= 1e-8 * np.max(np.abs(ro["x"][:nu]))
+        dp = x[nu:] - ro["x"][nu:]
+        assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(ro["x"][nu:]))
+    m = min(len(rd["history"]), len(ro["history"]))
+    assert np.allclose(rd["history"][:m - 1], ro["history"][:m - 1], rtol=1e-6)
+
+
 @pytest.mark.parametrize("opts", ["-ksp_type gmres -pc_type jacobi", "-ksp_type fgmres -pc_type jacobi",
                                   "-ksp_type minres -pc_type jacobi", "-ksp_type gmres -pc_type none",
                                   "-ksp_type gmres -ksp_gmres_restart 5 -pc_type jacobi",

@@ -113,16 +113,23 @@ def test_distributed_kkt_solve_matches_single_rank_and_oracle(size, cfg):
         xs = x.numpy()
         eu = np.max(np.abs(xs[:2 * nl] - xu[2 * g0:2 * (g0 + nl)]))
         dp = xs[2 * nl:] - xp[g0:g0 + nl]
-        return r["its"], r["reason"], eu, dp
+        rr = sp.Vec(ctx, prob.n)
+        prob.K.residual(prob.rhs, x, rr)
+        return r["its"], r["reason"], eu, dp, rr.norm() / prob.rhs.norm()
 
     res = sp.run_ranks(size, rank_fn)
     its = {r[0] for r in res}
     assert len(its) == 1 and all(r[1] == 2 for r in res)
     assert abs(res[0][0] - ro["its"]) <= 1, (res[0][0], ro["its"])
+    # the distributed solve's own true residual meets the tolerance whatever the iteration count ...
+    assert res[0][4] < 5e-7, res[0][4]
     if res[0][0] == ro["its"]:
-        # both runs stop at rtol 1e-8; the partition changes the summation order of MatMult (diagonal block, then
-        # off-diagonal block) and of the reductions, so the iterates agree to solver tolerance x conditioning,
-        # not to 1e-8 of the solution
-        assert max(r[2] for r in res) <= 1e-6 * np.max(np.abs(xu))
+        # ... and with the same number of iterations the iterates agree with the single-rank oracle to north_star's
+        # 1e-8 (the partition only changes summation orders: measured differences are 1e-10 ... 1e-13)
+        assert max(r[2] for r in res) <= 1e-8 * np.max(np.abs(xu))
         dp = np.concatenate([r[3] for r in res])
-        assert np.max(np.abs(dp - dp.mean())) <= 1e-6 * np.max(np.abs(xp))
+        assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(xp))
+    else:
+        # one iteration more or less at rtol 1e-8: both are solutions to the tolerance, they differ by about the
+        # last correction (measured: a few 1e-7 of the solution)
+        assert max(r[2] for r in res) <= 5e-6 * np.max(np.abs(xu))
