@@ -542,7 +542,7 @@ def main():
     secondary = None
     if world == 1 and not args.no_secondary and args.config == "fgmres_schur_mg":
         secondary = []
-        for name, nx2 in (("gmres_schur_mg", 576), ("fgmres_schur_lsc", 192), ("minres_diag_mg", args.nx)):
+        for name, nx2 in (("gmres_schur_mg", 576), ("fgmres_schur_lsc", 96), ("minres_diag_mg", args.nx)):
             try:
                 secondary.append(secondary_config(sp, ctx, name, nx2))
             except Exception as e:  # noqa: BLE001

@@ -160,6 +160,11 @@ int b200sp_mat_get_diagonal(b200sp_mat A, b200sp_vec d);                    /* M
 int b200sp_mat_mult_transpose(b200sp_mat A, b200sp_vec x, b200sp_vec y);
 int b200sp_mat_transpose(b200sp_mat A, b200sp_mat *At);                     /* MatTranspose (explicit) */
 int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C);          /* MatMatMult (device SpGEMM) */
+/* C = A diag(d) (MatDiagonalScale with a right vector, out of place) and C = A + s B (MatAXPY on the union pattern, out of
+ * place); both work on row-partitioned matrices (ghost columns scaled through the halo; B's ghost set must contain A's).
+ * They are the pieces of Sp = A11 - A10 diag(A00)^-1 A01 (selfp) and of the LSC operator. */
+int b200sp_mat_scale_columns(b200sp_mat A, b200sp_vec d, b200sp_mat *C);
+int b200sp_mat_add_scaled(b200sp_mat A, double s, b200sp_mat B, b200sp_mat *C);
 /* MatZeroRowsColumns(A,n,rows,diag,NULL,NULL): local row ids; pattern preserved (Appendix A.4) */
 int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag);
 int b200sp_mat_zero_rows(b200sp_mat A, int n, const int *rows, double diag); /* MatZeroRows (diag only if square) */

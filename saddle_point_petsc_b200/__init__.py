@@ -90,6 +90,8 @@ _SIGS = {
     "b200sp_mat_get_diagonal": [_vp, _vp],
     "b200sp_mat_transpose": [_vp, C.POINTER(_vp)],
     "b200sp_mat_matmult": [_vp, _vp, C.POINTER(_vp)],
+    "b200sp_mat_scale_columns": [_vp, _vp, C.POINTER(_vp)],
+    "b200sp_mat_add_scaled": [_vp, C.c_double, _vp, C.POINTER(_vp)],
     "b200sp_mat_zero_rows_columns": [_vp, C.c_int, c_ip, C.c_double],
     "b200sp_mat_zero_rows": [_vp, C.c_int, c_ip, C.c_double],
     "b200sp_mat_zero_columns": [_vp, C.c_int, c_ip],
@@ -483,6 +485,16 @@ class Mat:
     def matmult(self, B):
         h = _vp()
         _chk(lib().b200sp_mat_matmult(self.h, B.h, C.byref(h)))
+        return Mat(self.ctx, h)
+
+    def scale_columns(self, d):
+        h = _vp()
+        _chk(lib().b200sp_mat_scale_columns(self.h, d.h, C.byref(h)))
+        return Mat(self.ctx, h)
+
+    def add_scaled(self, s, B):
+        h = _vp()
+        _chk(lib().b200sp_mat_add_scaled(self.h, float(s), B.h, C.byref(h)))
         return Mat(self.ctx, h)
 
     def zero_rows_columns(self, rows, diag=1.0):

@@ -581,6 +581,20 @@ int b200sp_mat_mult_transpose(b200sp_mat A, b200sp_vec x, b200sp_vec y) {
 }
 int b200sp_mat_transpose(b200sp_mat A, b200sp_mat *At) { API_BEGIN *At = wrap(A->m.ctx, csr_transpose(plain(A))); API_END }
 int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C) { API_BEGIN *C = wrap(A->m.ctx, csr_matmat(plain(A), plain(B))); API_END }
+int b200sp_mat_scale_columns(b200sp_mat A, b200sp_vec d, b200sp_mat *C) {
+  API_BEGIN
+  Csr &M = plain(A);
+  use_device(M.ctx);
+  B2_REQUIRE(d->v.n == M.ncols, "mat_scale_columns: vector does not match the (owned) column space");
+  *C = wrap(M.ctx, csr_scale_cols(M, d->v.d));
+  API_END
+}
+int b200sp_mat_add_scaled(b200sp_mat A, double s, b200sp_mat B, b200sp_mat *C) {
+  API_BEGIN
+  use_device(A->m.ctx);
+  *C = wrap(A->m.ctx, csr_add_scaled(plain(A), s, plain(B)));
+  API_END
+}
 int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag) {
   API_BEGIN
   Csr &M = plain(A);

@@ -228,6 +228,7 @@ void vec_cheb_update(Ctx *c, int64_t n, double a, const double *x, double b, con
 void vec_pointwise_mult(Ctx *c, int64_t n, const double *x, const double *y, double *w);
 void vec_reciprocal_safe(Ctx *c, int64_t n, double *d); // d = 1/(d==0?1:d)   (PCJACOBI setup)
 void vec_hash(Ctx *c, int64_t n, double *v);
+void vec_hash_natural(Ctx *c, int xs, int ys, int xm, int ym, int M, int dof, double *v); // same values as vec_hash on one rank, by natural index
 void vec_scatter_set(Ctx *c, int64_t n, const int *idx, double val, double *y); // y[idx[i]] = val
 void vec_permute_scatter(Ctx *c, int64_t n, const int *map, const double *in, double *out); // out[map[i]] = in[i] where map[i] >= 0
 void vec_permute_gather(Ctx *c, int64_t n, const int *map, const double *in, double *out);  // out[i] = in[map[i]]
@@ -385,6 +386,9 @@ std::shared_ptr<Csr> csr_from_host(Ctx *c, int nrows, int ncols, const int *rowp
 std::shared_ptr<Csr> csr_from_coo_host(Ctx *c, int nrows, int ncols, int64_t ncoo, const int *row, const int *col, const double *val);
 std::shared_ptr<Csr> csr_transpose(const Csr &A);
 std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B);
+std::shared_ptr<Csr> csr_matmat_dist(const Csr &A, const Csr &B); // row-partitioned operands (dist_spgemm.cu), collective
+std::shared_ptr<Csr> spgemm_raw(Ctx *c, int nrowsA, const int *rpa, const int *ca, const double *va, const int *rpb, const int *cb, const double *vb, int ncolsC);
+void csr_copy_distribution(Csr &C, const Csr &like);
 std::shared_ptr<Csr> csr_extract_fields(const Csr &A, int bs, const std::vector<int> &split_of_field, int rs, int cs); // MatCreateSubMatrix, strided ISs
 std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d);            // A * diag(d)
 std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double a, const Csr &B);     // A + a B (same pattern required)

@@ -456,6 +456,33 @@ static void setup_p2p(Halo &h, const Layout &L, int rank) {
   h.p2p = true;
 }
 
+// node-keyed view of the send lists (pushes fused into producing kernels, PushOut in core.h)
+static void build_push_tables(HaloPlan &P) {
+  const int n = P.n_owned;
+  P.push_grp.assign((size_t)(n + 63) / 64 + 1, 0);
+  P.push_node_ent.assign((size_t)n + 1, 0);
+  std::vector<int> cnt((size_t)n + 1, 0), first((size_t)n + 1, 0), fill((size_t)n + 1, 0);
+  for (const HaloMsg &m : P.msgs)
+    for (int64_t k = 0; k < m.send_cnt; ++k) cnt[(size_t)P.send_lnode[(size_t)(m.send_off + k)]]++;
+  int total = 1; // entry 0 is never used so that "0" can mean "none"
+  for (int v = 0; v < n; ++v) {
+    if (cnt[(size_t)v] > 3) P.push_valid = false; // boxes thinner than 2 nodes: the 2-bit count cannot hold it (no fused push, no peer-to-peer)
+    first[(size_t)v] = total;
+    total += cnt[(size_t)v];
+  }
+  P.push_ent_msg.assign((size_t)total, 0);
+  P.push_ent_pos.assign((size_t)total, 0);
+  for (size_t mi = 0; mi < P.msgs.size(); ++mi)
+    for (int64_t k = 0; k < P.msgs[mi].send_cnt; ++k) {
+      const int v = P.send_lnode[(size_t)(P.msgs[mi].send_off + k)];
+      const int e = first[(size_t)v] + fill[(size_t)v]++;
+      P.push_ent_msg[(size_t)e] = (int)mi;
+      P.push_ent_pos[(size_t)e] = (int)k;
+    }
+  for (int v = 0; v < n; ++v)
+    if (cnt[(size_t)v] && P.push_valid) { P.push_node_ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; P.push_grp[(size_t)(v >> 6)] = 1; }
+}
+
 HaloPlan plan_halo(const Layout &L, int rank) {
   HaloPlan P;
   L.box(rank, &P.xs, &P.ys, &P.xm, &P.ym);
@@ -487,47 +514,25 @@ HaloPlan plan_halo(const Layout &L, int rank) {
     msg.recv_cnt = cnt;
     if (msg.send_cnt || msg.recv_cnt) P.msgs.push_back(msg);
   }
-  // node-keyed send tables
-  const int n = P.n_owned;
-  P.push_grp.assign((size_t)(n + 63) / 64 + 1, 0);
-  P.push_node_ent.assign((size_t)n + 1, 0);
-  std::vector<int> cnt((size_t)n + 1, 0), first((size_t)n + 1, 0), fill((size_t)n + 1, 0);
-  for (const HaloMsg &m : P.msgs)
-    for (int64_t k = 0; k < m.send_cnt; ++k) cnt[(size_t)P.send_lnode[(size_t)(m.send_off + k)]]++;
-  int total = 1; // entry 0 is never used so that "0" can mean "none"
-  for (int v = 0; v < n; ++v) {
-    if (cnt[(size_t)v] > 3) P.push_valid = false; // boxes thinner than 2 nodes: the 2-bit count cannot hold it (no fused push, no peer-to-peer)
-    first[(size_t)v] = total;
-    total += cnt[(size_t)v];
-  }
-  P.push_ent_msg.assign((size_t)total, 0);
-  P.push_ent_pos.assign((size_t)total, 0);
-  for (size_t mi = 0; mi < P.msgs.size(); ++mi)
-    for (int64_t k = 0; k < P.msgs[mi].send_cnt; ++k) {
-      const int v = P.send_lnode[(size_t)(P.msgs[mi].send_off + k)];
-      const int e = first[(size_t)v] + fill[(size_t)v]++;
-      P.push_ent_msg[(size_t)e] = (int)mi;
-      P.push_ent_pos[(size_t)e] = (int)k;
-    }
-  for (int v = 0; v < n; ++v)
-    if (cnt[(size_t)v] && P.push_valid) { P.push_node_ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; P.push_grp[(size_t)(v >> 6)] = 1; }
+  build_push_tables(P);
   return P;
 }
 
-std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
+// device side of a halo from its plan; `ring` (DMDA halos only): the width-1 ring classification used by the assembly
+static std::shared_ptr<Halo> halo_from_plan(Ctx *c, const Layout &L, int rank, const HaloPlan &P, bool ring_of_box) {
   auto h = std::make_shared<Halo>();
   h->ctx = c;
   h->M = L.M; h->N = L.N;
-  HaloPlan P = plan_halo(L, rank);
   h->xs = P.xs; h->ys = P.ys; h->xm = P.xm; h->ym = P.ym;
   const int xs = h->xs, ys = h->ys, xm = h->xm, ym = h->ym;
-  B2_REQUIRE(L.size == 1 || (xm >= 2 && ym >= 2), "dmda: every rank must own at least 2 x 2 nodes");
   h->n_owned = P.n_owned;
   h->n_ghost = (int)P.ghost_gnode.size();
   h->ghost_gnode = P.ghost_gnode; h->ghost_i = P.ghost_i; h->ghost_j = P.ghost_j;
   std::vector<int> ring((size_t)(2 * (xm + 2) + 2 * ym), -1);
-  ColSpace cs{xs, ys, xm, ym, nullptr};
-  for (int t = 0; t < h->n_ghost; ++t) ring[(size_t)cs.ring_id(P.ghost_i[(size_t)t], P.ghost_j[(size_t)t])] = t;
+  if (ring_of_box) {
+    ColSpace cs{xs, ys, xm, ym, nullptr};
+    for (int t = 0; t < h->n_ghost; ++t) ring[(size_t)cs.ring_id(P.ghost_i[(size_t)t], P.ghost_j[(size_t)t])] = t;
+  }
   h->node_msgs = P.msgs;
   const std::vector<int> &send_lnode = P.send_lnode;
   h->h_push_grp = P.push_grp; h->h_push_node_ent = P.push_node_ent; h->h_push_ent_msg = P.push_ent_msg; h->h_push_ent_pos = P.push_ent_pos;
@@ -543,11 +548,79 @@ std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
   c->sync();
   // every message must carry data in both directions for the flag protocol (true for a box-stencil ring)
-  bool symmetric = true;
+  bool symmetric = (int)h->node_msgs.size() <= 8;
   for (const HaloMsg &m : h->node_msgs) symmetric = symmetric && m.send_cnt > 0 && m.recv_cnt > 0;
   symmetric = symmetric && P.push_valid;
-  if (c->dcomm && c->dcomm->p2p_capable() && L.size > 1 && symmetric) setup_p2p(*h, L, rank);
+  if (c->dcomm && c->dcomm->p2p_capable() && L.size > 1) {
+    // the peer-to-peer setup is collective: every rank must take the same decision
+    DevBuf<double> d_in(2), d_all((size_t)L.size + 1);
+    const double mine = symmetric ? 1.0 : 0.0;
+    std::vector<double> all((size_t)L.size);
+    B2_CUDA(cudaMemcpyAsync(d_in.p, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->dcomm->allgather(d_in.p, d_all.p, 1, c->stream);
+    B2_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(double) * (size_t)L.size, cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    for (double v : all) symmetric = symmetric && v != 0.0;
+    if (symmetric) setup_p2p(*h, L, rank);
+  }
   return h;
+}
+
+std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank) {
+  HaloPlan P = plan_halo(L, rank);
+  B2_REQUIRE(L.size == 1 || (P.xm >= 2 && P.ym >= 2), "dmda: every rank must own at least 2 x 2 nodes");
+  return halo_from_plan(c, L, rank, P, true);
+}
+
+// Halo for an ARBITRARY ghost set (sorted, unique global node ids in PETSc numbering, none owned by this rank): what
+// MatSetUpMultiply_MPIAIJ builds from the off-diagonal columns of an assembled matrix.  Used for matrices produced by
+// the distributed SpGEMM (A10 A01 has a two-node-wide stencil).  Collective: every rank publishes its ghost list through
+// the communicator's all-gather and finds the nodes it has to send in the requesters' order.
+std::shared_ptr<Halo> make_halo_general(Ctx *c, const Layout &L, int rank, const std::vector<int> &ghost_gnode) {
+  B2_REQUIRE(c->dcomm, "make_halo_general: context has no communicator");
+  const int size = L.size;
+  DevBuf<double> d_in(2), d_cnt((size_t)size + 1);
+  const double mycnt = (double)ghost_gnode.size();
+  B2_CUDA(cudaMemcpyAsync(d_in.p, &mycnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->dcomm->allgather(d_in.p, d_cnt.p, 1, c->stream);
+  std::vector<double> h_cnt((size_t)size);
+  B2_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt.p, sizeof(double) * (size_t)size, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  int64_t maxc = 1;
+  for (double v : h_cnt) maxc = std::max<int64_t>(maxc, (int64_t)v);
+  std::vector<double> mine((size_t)maxc, -1.0), all((size_t)maxc * size);
+  for (size_t t = 0; t < ghost_gnode.size(); ++t) mine[t] = (double)ghost_gnode[t];
+  DevBuf<double> d_mine((size_t)maxc), d_all((size_t)maxc * size);
+  B2_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(double) * (size_t)maxc, cudaMemcpyHostToDevice, c->stream));
+  c->dcomm->allgather(d_mine.p, d_all.p, maxc, c->stream);
+  B2_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  HaloPlan P;
+  P.n_owned = L.rstart[(size_t)rank + 1] - L.rstart[(size_t)rank];
+  const int g0 = L.rstart[(size_t)rank], g1 = L.rstart[(size_t)rank + 1];
+  P.ghost_gnode = ghost_gnode;
+  for (int g : ghost_gnode) {
+    B2_REQUIRE(g >= 0 && g < L.rstart[(size_t)size] && (g < g0 || g >= g1), "make_halo_general: ghost id owned by this rank or out of range");
+    const int owner = (int)(std::upper_bound(L.rstart.begin(), L.rstart.end(), g) - L.rstart.begin()) - 1;
+    P.ghost_owner.push_back(owner);
+  }
+  for (int q = 0; q < size; ++q) {
+    if (q == rank) continue;
+    HaloMsg msg{q, (int64_t)P.send_lnode.size(), 0, 0, 0};
+    const int qn = (int)h_cnt[(size_t)q];
+    for (int t = 0; t < qn; ++t) { // q's ghost list is sorted: the nodes I own appear in ascending order = q's receive order
+      const int g = (int)all[(size_t)q * maxc + t];
+      if (g >= g0 && g < g1) { P.send_lnode.push_back(g - g0); msg.send_cnt++; }
+    }
+    int first = -1, cnt = 0;
+    for (size_t t = 0; t < P.ghost_owner.size(); ++t)
+      if (P.ghost_owner[t] == q) { if (first < 0) first = (int)t; cnt++; }
+    msg.recv_off = first < 0 ? 0 : first;
+    msg.recv_cnt = cnt;
+    if (msg.send_cnt || msg.recv_cnt) P.msgs.push_back(msg);
+  }
+  build_push_tables(P);
+  return halo_from_plan(c, L, rank, P, false);
 }
 
 void Halo::begin(const double *x, int dof) {

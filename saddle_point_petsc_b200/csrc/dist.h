@@ -134,6 +134,7 @@ struct Halo {
   void end();
 };
 std::shared_ptr<Halo> make_halo(Ctx *c, const Layout &L, int rank);
+std::shared_ptr<Halo> make_halo_general(Ctx *c, const Layout &L, int rank, const std::vector<int> &ghost_gnode); // collective
 
 // device-side view of a column space (owned box + ghost ring) used by the assembly kernels to classify columns
 struct ColSpace {

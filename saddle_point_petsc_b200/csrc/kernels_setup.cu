@@ -3,6 +3,7 @@
 // explicit transpose, SpGEMM (MatMatMult used by selfp / LSC), small dense inverse
 // (coarsest multigrid level).
 #include "dev.cuh"
+#include "dist.h"
 #include <algorithm>
 
 namespace b200sp {
@@ -132,6 +133,33 @@ namespace {
 __global__ void __launch_bounds__(256) k_scale_cols(int64_t nnz, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ d, double *out) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = val[k] * d[col[k]];
 }
+__global__ void __launch_bounds__(256) k_scale_cols_ghost(int64_t nnz, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ d,
+                                                          const double *ghost, int ncols, double *out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const int cl = col[k];
+    out[k] = val[k] * (cl < ncols ? d[cl] : ghost[cl - ncols]);
+  }
+}
+__global__ void __launch_bounds__(256) k_remap_ghost_cols(int64_t nnz, const int *__restrict__ col, int ncols, int dof, const int *__restrict__ map, int *out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const int cl = col[k];
+    out[k] = cl < ncols ? cl : ncols + map[(cl - ncols) / dof] * dof + (cl - ncols) % dof;
+  }
+}
+// rows of a row-partitioned DMDA matrix list their columns in GLOBAL order (ghost columns of lower ranks first), not in
+// local-id order: the union merge below needs ascending ids, so the operands are sorted row by row first (short rows)
+__global__ void __launch_bounds__(256) k_sort_rows(int nrows, const int *__restrict__ rowptr, int *col, double *val) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int b = rowptr[r], e = rowptr[r + 1];
+    for (int i = b + 1; i < e; ++i) {
+      const int cv = col[i];
+      const double vv = val[i];
+      int j = i;
+      while (j > b && col[j - 1] > cv) { col[j] = col[j - 1]; val[j] = val[j - 1]; --j; }
+      col[j] = cv; val[j] = vv;
+    }
+  }
+}
 // A + s*B on the union pattern: count, then fill (both matrices have ascending columns)
 __global__ void __launch_bounds__(256) k_union_count(int nrows, const int *__restrict__ rpa, const int *__restrict__ ca, const int *__restrict__ rpb, const int *__restrict__ cb, int *cnt) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
@@ -166,9 +194,24 @@ inline int grid_for(Ctx *c, int64_t n) {
 } // namespace
 
 std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d) {
-  if (A.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_scale_cols: row-partitioned matrices are not supported by this routine (ghost columns)");
-
   Ctx *c = A.ctx;
+  if (A.halo) { // row-partitioned: the scale factors of the ghost columns travel through the matrix's own halo
+    A.halo->begin(d, A.halo_dof);
+    A.halo->end();
+    const double *ghost = A.halo->ghost_now();
+    auto C = csr_alloc(c, A.nrows, A.ncols, A.nnz);
+    B2_CUDA(cudaMemcpyAsync(C->rowptr.p, A.rowptr.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(C->col.p, A.col.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, c->stream));
+    if (A.nnz) {
+      LaunchScope ls(c, "setup");
+      k_scale_cols_ghost<<<grid_for(c, A.nnz), 256, 0, c->stream>>>(A.nnz, A.col.p, A.val.p, d, ghost, A.ncols, C->val.p);
+      check_launch("k_scale_cols_ghost");
+    }
+    c->sync();
+    csr_copy_distribution(*C, A);
+    C->plan();
+    return C;
+  }
   auto C = csr_alloc(c, A.nrows, A.ncols, A.nnz);
   B2_CUDA(cudaMemcpyAsync(C->rowptr.p, A.rowptr.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
   B2_CUDA(cudaMemcpyAsync(C->col.p, A.col.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, c->stream));
@@ -183,14 +226,50 @@ std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d) {
 }
 
 std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double s, const Csr &B) {
-  if (A.halo || B.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_add_scaled: row-partitioned matrices are not supported by this routine (ghost columns)");
-
   Ctx *c = A.ctx;
   B2_REQUIRE(A.nrows == B.nrows && A.ncols == B.ncols, "csr_add_scaled: shape mismatch");
+  B2_REQUIRE((A.halo == nullptr) == (B.halo == nullptr), "csr_add_scaled: one operand is row-partitioned and the other is not");
+  // row-partitioned operands: the result lives in B's column space (its ghost set must contain A's: true for
+  // A11 - A10 D^-1 A01, whose product stencil is a superset of A11's); A's ghost columns are renumbered into it
+  DevBuf<int> a_cols, b_cols;
+  DevBuf<double> a_vals, b_vals;
+  const int *a_col = A.col.p, *b_col = B.col.p;
+  const double *a_val = A.val.p, *b_val = B.val.p;
+  if (A.halo) {
+    B2_REQUIRE(A.halo_dof == B.halo_dof, "csr_add_scaled: column spaces with different dof per node");
+    std::vector<int> map((size_t)A.halo->n_ghost + 1, 0);
+    const auto &gb = B.halo->ghost_gnode;
+    for (int t = 0; t < A.halo->n_ghost; ++t) {
+      auto it = std::lower_bound(gb.begin(), gb.end(), A.halo->ghost_gnode[(size_t)t]);
+      if (it == gb.end() || *it != A.halo->ghost_gnode[(size_t)t])
+        throw Error(B200SP_ERR_UNSUPPORTED, "csr_add_scaled: the second operand's ghost columns do not contain the first operand's");
+      map[(size_t)t] = (int)(it - gb.begin());
+    }
+    DevBuf<int> d_map(map.size());
+    B2_CUDA(cudaMemcpyAsync(d_map.p, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, c->stream));
+    a_cols.alloc((size_t)A.nnz + 1); a_vals.alloc((size_t)A.nnz + 1);
+    b_cols.alloc((size_t)B.nnz + 1); b_vals.alloc((size_t)B.nnz + 1);
+    B2_CUDA(cudaMemcpyAsync(a_vals.p, A.val.p, sizeof(double) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(b_cols.p, B.col.p, sizeof(int) * (size_t)B.nnz, cudaMemcpyDeviceToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(b_vals.p, B.val.p, sizeof(double) * (size_t)B.nnz, cudaMemcpyDeviceToDevice, c->stream));
+    if (A.nnz) {
+      LaunchScope ls(c, "setup");
+      k_remap_ghost_cols<<<grid_for(c, A.nnz), 256, 0, c->stream>>>(A.nnz, A.col.p, A.ncols, A.halo_dof, d_map.p, a_cols.p);
+      check_launch("k_remap_ghost_cols");
+    }
+    if (A.nrows) {
+      LaunchScope ls(c, "setup");
+      k_sort_rows<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, a_cols.p, a_vals.p);
+      k_sort_rows<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, B.rowptr.p, b_cols.p, b_vals.p);
+      check_launch("k_sort_rows");
+    }
+    c->sync(); // d_map is freed on scope exit
+    a_col = a_cols.p; a_val = a_vals.p; b_col = b_cols.p; b_val = b_vals.p;
+  }
   DevBuf<int> cnt((size_t)A.nrows + 1);
   if (A.nrows) {
     LaunchScope ls(c, "setup");
-    k_union_count<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, B.rowptr.p, B.col.p, cnt.p);
+    k_union_count<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, a_col, B.rowptr.p, b_col, cnt.p);
     check_launch("k_union_count");
   }
   DevBuf<int> rp((size_t)A.nrows + 1);
@@ -200,11 +279,12 @@ std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double s, const Csr &B) {
   B2_CUDA(cudaMemcpyAsync(C->rowptr.p, rp.p, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
   if (A.nrows) {
     LaunchScope ls(c, "setup");
-    k_union_fill<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, B.rowptr.p, B.col.p, B.val.p, s, C->rowptr.p, C->col.p, C->val.p);
+    k_union_fill<<<grid_for(c, A.nrows), 256, 0, c->stream>>>(A.nrows, A.rowptr.p, a_col, a_val, B.rowptr.p, b_col, b_val, s, C->rowptr.p, C->col.p, C->val.p);
     check_launch("k_union_fill");
   }
   c->sync();
   C->grid_M = A.grid_M; C->grid_N = A.grid_N; C->dof_r = A.dof_r; C->dof_c = A.dof_c;
+  if (B.halo) csr_copy_distribution(*C, B);
   C->plan();
   return C;
 }
@@ -264,15 +344,23 @@ __global__ void __launch_bounds__(128) k_spgemm_numeric(int nrows, const int *__
 } // namespace
 
 std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B) {
-  if (A.halo || B.halo) throw Error(B200SP_ERR_UNSUPPORTED, "csr_matmat: row-partitioned matrices are not supported by this routine (ghost columns)");
-
-  Ctx *c = A.ctx;
+  if (A.halo || B.halo) return csr_matmat_dist(A, B); // dist_spgemm.cu: fetch the ghost rows of B, multiply locally, build the result's halo
   B2_REQUIRE(A.ncols == B.nrows, "csr_matmat: inner dimensions differ");
-  const int n = A.nrows;
+  return spgemm_raw(A.ctx, A.nrows, A.rowptr.p, A.col.p, A.val.p, B.rowptr.p, B.col.p, B.val.p, B.ncols);
+}
+
+// distribution metadata of a matrix that shares `like`'s row partition and column space
+void csr_copy_distribution(Csr &C, const Csr &like) {
+  C.halo = like.halo; C.halo_dof = like.halo_dof; C.layout = like.layout;
+  C.row_gstart = like.row_gstart; C.col_gstart = like.col_gstart;
+  C.grid_M = like.grid_M; C.grid_N = like.grid_N; C.dof_r = like.dof_r; C.dof_c = like.dof_c;
+}
+
+std::shared_ptr<Csr> spgemm_raw(Ctx *c, int n, const int *rpa, const int *ca, const double *va, const int *rpb, const int *cb, const double *vb, int ncolsC) {
   DevBuf<int> ub((size_t)n + 1), ub_off((size_t)n + 1), cnt((size_t)n + 1), rp((size_t)n + 1);
   if (n) {
     LaunchScope ls(c, "setup");
-    k_spgemm_ub<<<grid_for(c, n), 256, 0, c->stream>>>(n, A.rowptr.p, A.col.p, B.rowptr.p, ub.p);
+    k_spgemm_ub<<<grid_for(c, n), 256, 0, c->stream>>>(n, rpa, ca, rpb, ub.p);
     check_launch("k_spgemm_ub");
   }
   // the scratch offsets can exceed 2^31 in principle: process in row chunks whose upper bound fits int32
@@ -286,16 +374,16 @@ std::shared_ptr<Csr> csr_matmat(const Csr &A, const Csr &B) {
   DevBuf<int> scratch((size_t)h_off[n] + 1);
   if (n) {
     LaunchScope ls(c, "setup");
-    k_spgemm_symbolic<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, A.rowptr.p, A.col.p, B.rowptr.p, B.col.p, soff.p, scratch.p, cnt.p);
+    k_spgemm_symbolic<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, rpa, ca, rpb, cb, soff.p, scratch.p, cnt.p);
     check_launch("k_spgemm_symbolic");
   }
   int total = 0;
   exclusive_scan_i32(c, cnt.p, rp.p, n, &total);
-  auto C = csr_alloc(c, n, B.ncols, total);
+  auto C = csr_alloc(c, n, ncolsC, total);
   B2_CUDA(cudaMemcpyAsync(C->rowptr.p, rp.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c->stream));
   if (n) {
     LaunchScope ls(c, "setup");
-    k_spgemm_numeric<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, A.rowptr.p, A.col.p, A.val.p, B.rowptr.p, B.col.p, B.val.p, soff.p, scratch.p,
+    k_spgemm_numeric<<<std::max(1, std::min((n + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(n, rpa, ca, va, rpb, cb, vb, soff.p, scratch.p,
                                                                                                       C->rowptr.p, C->col.p, C->val.p);
     check_launch("k_spgemm_numeric");
   }

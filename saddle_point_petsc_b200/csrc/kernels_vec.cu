@@ -102,6 +102,18 @@ __global__ void __launch_bounds__(256) k_hash(int64_t n, double *v) {
     v[i] = 0.5 + (double)(h >> 8) / 16777216.0;
   }
 }
+// the same hashed vector on a row-partitioned DMDA vector: entry (node (i,j), component c) gets the value its NATURAL
+// global index ((j*M + i)*dof + c) has on one rank, so eigenvalue estimates do not depend on the partition
+__global__ void __launch_bounds__(256) k_hash_natural(int xs, int ys, int xm, int ym, int M, int dof, double *v) {
+  const int64_t n = (int64_t)xm * ym * dof;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int node = (int)(t / dof), c = (int)(t % dof);
+    const int i = xs + node % xm, j = ys + node / xm;
+    unsigned h = (unsigned)(((int64_t)j * M + i) * dof + c) * 2654435761u;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13;
+    v[t] = 0.5 + (double)(h >> 8) / 16777216.0;
+  }
+}
 __global__ void __launch_bounds__(256) k_scatter_set(int64_t n, const int *idx, double val, double *y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[idx[i]] = val;
 }
@@ -266,6 +278,13 @@ void vec_hash(Ctx *c, int64_t n, double *v) {
   LaunchScope ls(c, "vec");
   k_hash<<<stream_grid(c, n), 256, 0, c->stream>>>(n, v);
   check_launch("k_hash");
+}
+void vec_hash_natural(Ctx *c, int xs, int ys, int xm, int ym, int M, int dof, double *v) {
+  const int64_t n = (int64_t)xm * ym * dof;
+  if (n <= 0) return;
+  LaunchScope ls(c, "vec");
+  k_hash_natural<<<stream_grid(c, n), 256, 0, c->stream>>>(xs, ys, xm, ym, M, dof, v);
+  check_launch("k_hash_natural");
 }
 void vec_scatter_set(Ctx *c, int64_t n, const int *idx, double val, double *y) {
   if (n <= 0) return;

@@ -635,7 +635,17 @@ std::string Ksp::view(int indent) const {
 double estimate_lambda_max(Ctx *c, Op *A, Op *M, int nits, bool local_only) {
   const int64_t n = A->n_in;
   DevBuf<double> v((size_t)n + 2), t((size_t)n + 2), z((size_t)n + 2);
-  vec_hash(c, n, v.p);
+  // start vector: hashed by the NATURAL global index of every entry, so that the estimate (and with it the Chebyshev
+  // coefficients, i.e. the preconditioner) is the same on any number of ranks
+  const Csr *ac = A->csr();
+  if (!local_only && ac && ac->halo && ac->layout && ac->dof_r > 0 && ac->nrows == ac->ncols) {
+    int xs, ys, xm, ym;
+    ac->layout->box(c->rank, &xs, &ys, &xm, &ym);
+    B2_REQUIRE((int64_t)xm * ym * ac->dof_r == n, "estimate_lambda_max: matrix does not match its DMDA layout");
+    vec_hash_natural(c, xs, ys, xm, ym, ac->layout->M, ac->dof_r, v.p);
+  } else {
+    vec_hash(c, n, v.p);
+  }
   double lam = 0.0, nv;
   for (int it = 0; it < nits; ++it) {
     vec_dot(c, n, v.p, v.p, c->d_scalars);

@@ -125,11 +125,110 @@ def test_distributed_kkt_solve_matches_single_rank_and_oracle(size, cfg):
     assert res[0][4] < 5e-7, res[0][4]
     if res[0][0] == ro["its"]:
         # ... and with the same number of iterations the iterates agree with the single-rank oracle to north_star's
-        # 1e-8 (the partition only changes summation orders: measured differences are 1e-10 ... 1e-13)
-        assert max(r[2] for r in res) <= 1e-8 * np.max(np.abs(xu))
+        # 1e-8 (the partition only changes summation orders: measured differences are 1e-10 ... 1e-13).  The weakly
+        # preconditioned configuration (Chebyshev(6)/Jacobi instead of multigrid: ~10x the iterations) is more
+        # sensitive to rounding than that: its tolerance is the ORACLE'S OWN measured sensitivity to a mathematically
+        # neutral change (modified instead of classical Gram-Schmidt), as for the LSC configuration in test_gpu_parity.
+        tol_u = tol_p = 1e-8
+        if cfg == "cheb":
+            # measured: 1e-8 ... 6e-8 between two valid rtol-1e-8 iterates here.  Bound: the distributed iterate may not be
+            # farther from the oracle's iterate than the oracle's iterate is from the converged solution (rtol 1e-13).
+            rt = so.Solver(orc, opts.replace("-ksp_rtol 1e-8", "-ksp_rtol 1e-13")).solve()
+            nu_ = 2 * M * N
+            d2 = rt["x"][nu_:] - ro["x"][nu_:]
+            tol_u = max(tol_u, np.max(np.abs(rt["x"][:nu_] - ro["x"][:nu_])) / np.max(np.abs(xu)))
+            tol_p = max(tol_p, np.max(np.abs(d2 - d2.mean())) / np.max(np.abs(xp)))
+        assert max(r[2] for r in res) <= tol_u * np.max(np.abs(xu)), (max(r[2] for r in res) / np.max(np.abs(xu)), tol_u)
         dp = np.concatenate([r[3] for r in res])
-        assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(xp))
+        assert np.max(np.abs(dp - dp.mean())) <= tol_p * np.max(np.abs(xp)), (np.max(np.abs(dp - dp.mean())) / np.max(np.abs(xp)), tol_p)
     else:
         # one iteration more or less at rtol 1e-8: both are solutions to the tolerance, they differ by about the
         # last correction (measured: a few 1e-7 of the solution)
         assert max(r[2] for r in res) <= 5e-6 * np.max(np.abs(xu))
+
+
+# ------------------------------------------------------------------ distributed SpGEMM: selfp and LSC on a row-partitioned nest
+@pytest.mark.parametrize("size,nx,ny", [(2, 12, 9), (4, 14, 12), (8, 24, 20)])
+def test_distributed_matmatmult_matches_the_oracle(size, nx, ny):
+    """L = B * Bt and Sp-style products on row-partitioned operands: the rows each rank holds equal the oracle's product
+    (structure exactly, in PETSc numbering; values to rounding -- the products of an entry are added in local column order)."""
+    import saddle_point_petsc_b200 as sp
+    M, N = nx + 1, ny + 1
+    orc = so.Problem(nx, ny, kkt=True, rhs_kind=1)
+    Lref = to_petsc_order(orc.B.matmat(orc.Bt), M, N, size, 1, 1)
+    Lref.eliminate_zeros()                                            # structural zeros may differ between the two orders of construction
+    pp, nm, ow = petsc_perm(M, N, size, 1)
+    rng = np.random.default_rng(9)
+    xg = rng.uniform(-1, 1, M * N)
+
+    def rank_fn(ctx):
+        prob = sp.SaddlePointProblem(ctx, nx, ny, kkt=True, rhs_kind=1)
+        nl = prob.da.n_nodes_local
+        g0 = int(np.sum(ow < ctx.rank))
+        Lm = prob.B.matmult(prob.Bt)
+        rp, col, val = Lm.csr()                                       # local rows, global PETSc columns
+        mine = sps.csr_matrix((val, col, rp), shape=(nl, M * N))
+        mine.eliminate_zeros()
+        R = Lref[g0:g0 + nl]
+        d = abs(mine - R)
+        err = d.max() / abs(Lref).max() if d.nnz else 0.0
+        same_pattern = np.array_equal(mine.indptr, R.indptr) and np.array_equal(mine.indices, R.indices)
+        x = sp.Vec.from_numpy(ctx, xg[g0:g0 + nl])
+        y = sp.Vec(ctx, nl)
+        for rep in range(2):                                           # the product's own (two-node-wide) halo, both parities
+            Lm.mult(x, y)
+        yr = Lref @ xg
+        return err, same_pattern, np.max(np.abs(y.numpy() - yr[g0:g0 + nl])) / np.max(np.abs(yr))
+
+    for err, same_pattern, merr in sp.run_ranks(size, rank_fn):
+        assert same_pattern
+        assert err < 1e-14 and merr < 1e-13, (err, merr)
+
+
+@pytest.mark.parametrize("size", [2, 4])
+@pytest.mark.parametrize("name", ["gmres_lower_selfp", "fgmres_lsc"])
+def test_distributed_selfp_and_lsc_match_the_oracle(size, name):
+    """-pc_fieldsplit_schur_precondition selfp and -fieldsplit_1_pc_type lsc on a row-partitioned nest (the BASELINE
+    'FGMRES + Schur/LSC on 1/2/4/8 GPUs' configuration): one preconditioner application and the solve against the oracle."""
+    import saddle_point_petsc_b200 as sp
+    from test_oracle import CONFIGS
+    nx = ny = 16
+    opts = CONFIGS[name]
+    M, N = nx + 1, ny + 1
+    orc = so.Problem(nx, ny, kkt=True, rhs_kind=1)
+    s = so.Solver(orc, opts)
+    ro = s.solve()
+    pu, nm, ow = petsc_perm(M, N, size, 2)
+    pp, _, _ = petsc_perm(M, N, size, 1)
+    rng = np.random.default_rng(4)
+    v = rng.uniform(-1, 1, 3 * M * N)
+    yo = np.empty_like(v)
+    so.lib().or_op_apply(s.ksp.contents.M, so.dptr(v), so.dptr(yo))
+    vu, vp, you, yop = (np.zeros(2 * M * N), np.zeros(M * N), np.zeros(2 * M * N), np.zeros(M * N))
+    vu[pu] = v[:2 * M * N]; vp[pp] = v[2 * M * N:]
+    you[pu] = yo[:2 * M * N]; yop[pp] = yo[2 * M * N:]
+
+    def rank_fn(ctx):
+        prob = sp.SaddlePointProblem(ctx, nx, ny, kkt=True, rhs_kind=1)
+        nl = prob.da.n_nodes_local
+        g0 = int(np.sum(ow < ctx.rank))
+        ksp = prob.make_ksp(opts)
+        ksp.setup()
+        xin = sp.Vec.from_numpy(ctx, np.concatenate([vu[2 * g0:2 * (g0 + nl)], vp[g0:g0 + nl]]))
+        y = sp.Vec(ctx, prob.n)
+        ksp.pc_apply(xin, y)
+        yl = y.numpy()
+        e = max(np.max(np.abs(yl[:2 * nl] - you[2 * g0:2 * (g0 + nl)])), np.max(np.abs(yl[2 * nl:] - yop[g0:g0 + nl])))
+        x = sp.Vec(ctx, prob.n)
+        r = ksp.solve(prob.rhs, x)
+        rr = sp.Vec(ctx, prob.n)
+        prob.K.residual(prob.rhs, x, rr)
+        return e, r["its"], r["reason"], rr.norm() / prob.rhs.norm()
+
+    res = sp.run_ranks(size, rank_fn)
+    assert max(r[0] for r in res) <= 1e-10 * np.max(np.abs(yo)), [r[0] for r in res]
+    assert all(r[2] == 2 for r in res)
+    # LSC with unrefined CGS-GMRES is rounding-chaotic after ~20 steps (see test_gpu_parity): a few percent on the count
+    tol_its = 1 if name != "fgmres_lsc" else max(1, ro["its"] // 20)
+    assert abs(res[0][1] - ro["its"]) <= tol_its, (res[0][1], ro["its"])
+    assert res[0][3] < 5e-7
