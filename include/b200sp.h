@@ -185,6 +185,10 @@ int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec
 /* KKT blocks on the same nodal grid: Bt (gradient), B = Bt^T (divergence), C (stabilisation, the (2,2)
  * block), Q (= -pressure mass matrix, the "user" Schur preconditioning matrix) */
 int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q);
+/* AssembleOperator_Constraints (an empty stub in the reference, src/Discretization.c:277-283; B is 4 x nCols,
+ * src/SaddlePointProblem.c:48-49): the four dense constraint rows "barycentre and volume" (src/main.c:1) -- barycentre
+ * x / y, dilation moment, rotation moment of the displacement field about the domain centre -- and B^T.  One rank only. */
+int b200sp_assemble_constraints(b200sp_dmda da, b200sp_mat *B, b200sp_mat *Bt);
 /* ApplyBC_Laplace id list (local row ids of this rank, ascending); ids may be NULL to query the count */
 int b200sp_dmda_bc_ids(b200sp_dmda da, int dof, int *n, int *ids);
 /* Q1 interpolation coarse->fine (DMCreateInterpolation on a DMDA); bc!=0 zeroes Dirichlet rows/cols */

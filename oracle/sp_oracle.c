@@ -506,6 +506,68 @@ void or_assemble_kkt(int M, int N, OrCsr **pBt, OrCsr **pB, OrCsr **pC, OrCsr **
 /* Q1 interpolation, coarse Mc x Nc nodes -> fine (2Mc-1) x (2Nc-1) nodes (DMCreateInterpolation_DA_2D_Q1
  * weights 1, 1/2, 1/4), dof-interleaved.  bc: zero rows of fine boundary dofs and cols of coarse
  * boundary dofs (pattern kept) so the coarse correction never touches Dirichlet values. */
+/* The reference's own constraint block: "barycentre and volume constraints" (main.c:1), B is 4 x nCols
+ * (SaddlePointProblem.c:48-49), g has 4 entries (:51-52); AssembleOperator_Constraints / AssembleRHS_Constraints are
+ * empty stubs (Discretization.c:277-290), so the rows are DEFINED here, with the reference's quadrature, node order
+ * and fac = w*detJ, as the four lowest moments of the displacement field u = (Ux,Uy) about the domain centre c:
+ *   row 0:  int Ux                      (barycentre, x)
+ *   row 1:  int Uy                      (barycentre, y)
+ *   row 2:  int (x-cx) Ux + (y-cy) Uy   (dilation moment: the first-order volume change of the material about c;
+ *                                        the plain  int div u  vanishes identically under the reference's all-round
+ *                                        Dirichlet condition and would make the row redundant)
+ *   row 3:  int (x-cx) Uy - (y-cy) Ux   (rotation moment)
+ * Element vector Be[r*8 + 2a+d] (node a, component d), summed over the Gauss points from +0.0. */
+void or_element_constraints(const double ec[8], double Be[32]) {
+  for (int p = 0; p < 4; ++p) {
+    double Ni[4], GNi[2][4], GNx[2][4], detJ, fac, xp = 0.0, yp = 0.0, rx, ry;
+    q1_Ni(GP_XI[p], Ni);
+    q1_GNi(GP_XI[p], GNi);
+    q1_GNx(GNi, ec, GNx, &detJ);
+    fac = GP_W[p] * detJ;
+    for (int i = 0; i < 4; ++i) { xp += Ni[i] * ec[2 * i]; yp += Ni[i] * ec[2 * i + 1]; }
+    rx = xp - 0.5; ry = yp - 0.5;
+    for (int a = 0; a < 4; ++a) {
+      const double w = fac * Ni[a];
+      Be[0 * 8 + 2 * a] += w;
+      Be[1 * 8 + 2 * a + 1] += w;
+      Be[2 * 8 + 2 * a] += w * rx;
+      Be[2 * 8 + 2 * a + 1] += w * ry;
+      Be[3 * 8 + 2 * a] -= w * ry;
+      Be[3 * 8 + 2 * a + 1] += w * rx;
+    }
+  }
+}
+/* AssembleOperator_Constraints: B (4 x 2MN, rows 0/1 hold only their own component's columns, rows 2/3 all columns,
+ * ascending) assembled with ADD_VALUES in the reference's element order; Bt is its transpose (2MN x 4, 3 entries
+ * per row).  Columns of Dirichlet dofs are zeroed by the caller like MatZeroRowsColumns would on the KKT matrix. */
+void or_assemble_constraints(int M, int N, OrCsr **pB, OrCsr **pBt) {
+  const int n = 2 * M * N, nn = M * N;
+  OrCsr *B = or_csr_alloc(4, n, 2L * nn + 2L * n);
+  B->rowptr[0] = 0; B->rowptr[1] = nn; B->rowptr[2] = 2 * nn; B->rowptr[3] = 2 * nn + n; B->rowptr[4] = 2 * nn + 2 * n;
+  for (int i = 0; i < nn; ++i) { B->col[i] = 2 * i; B->col[nn + i] = 2 * i + 1; }
+  for (int i = 0; i < n; ++i) { B->col[2 * nn + i] = i; B->col[2 * nn + n + i] = i; }
+  for (long k = 0; k < B->rowptr[4]; ++k) B->val[k] = 0.0;
+  for (int ej = 0; ej < N - 1; ++ej)
+    for (int ei = 0; ei < M - 1; ++ei) {
+      double ec[8], Be[32];
+      int nd[4];
+      or_element_coords(M, N, ei, ej, 0, ec);
+      memset(Be, 0, sizeof(Be));
+      or_element_constraints(ec, Be);
+      element_nodes(M, ei, ej, nd);
+      for (int a = 0; a < 4; ++a) {
+        B->val[nd[a]] += Be[0 * 8 + 2 * a];
+        B->val[nn + nd[a]] += Be[1 * 8 + 2 * a + 1];
+        for (int d = 0; d < 2; ++d) {
+          B->val[2 * nn + 2 * nd[a] + d] += Be[2 * 8 + 2 * a + d];
+          B->val[2 * nn + n + 2 * nd[a] + d] += Be[3 * 8 + 2 * a + d];
+        }
+      }
+    }
+  *pB = B;
+  if (pBt) *pBt = or_csr_transpose(B);
+}
+
 OrCsr *or_interp_q1(int Mc, int Nc, int dof, int bc) {
   int Mf = 2 * Mc - 1, Nf = 2 * Nc - 1;
   long nnz = 0;

@@ -68,6 +68,8 @@ void or_apply_bc(OrCsr *A, double *f, int nbc, const int *ids);      /* MatZeroR
  * Bt (2MN x MN) gradient, B = Bt^T, C (MN x MN) stabilisation (the (2,2) block, sign included),
  * Q (MN x MN) = -pressure mass matrix (the "user" Schur preconditioning matrix). */
 void or_assemble_kkt(int M, int N, OrCsr **Bt, OrCsr **B, OrCsr **C, OrCsr **Q);
+void or_element_constraints(const double ec[8], double Be[32]);               /* += ; the reference's 4 constraint rows (ours) */
+void or_assemble_constraints(int M, int N, OrCsr **B, OrCsr **Bt);            /* B: 4 x 2MN, Bt = B^T */
 void or_zero_rows(OrCsr *A, int n, const int *rows);
 void or_zero_cols(OrCsr *A, int n, const int *cols);
 /* bilinear interpolation coarse(Mc x Nc) -> fine(2Mc-1 x 2Nc-1), dof-interleaved; bc!=0 zeroes boundary rows/cols */

@@ -76,6 +76,8 @@ def lib():
     sig("or_bc_ids", C.c_int, C.c_int, C.c_int, C.c_int, c_ip)
     sig("or_apply_bc", None, CsrP, c_dp, C.c_int, c_ip)
     sig("or_assemble_kkt", None, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP))
+    sig("or_assemble_constraints", None, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP))
+    sig("or_element_constraints", None, c_dp, c_dp)
     sig("or_zero_rows", None, CsrP, C.c_int, c_ip)
     sig("or_zero_cols", None, CsrP, C.c_int, c_ip)
     sig("or_interp_q1", CsrP, C.c_int, C.c_int, C.c_int, C.c_int)
@@ -220,7 +222,7 @@ def bc_ids(M, N, dof=2):
 class Problem:
     """The reference's A u = f (velocity block) and, with kkt=True, the [A Bt; B C] extension."""
 
-    def __init__(self, nx, ny, kkt=False, rhs_kind=0, as_written=False, bc=True):
+    def __init__(self, nx, ny, kkt=False, rhs_kind=0, as_written=False, bc=True, constraints=False, g=(0.0, 0.0, 0.0, 0.0)):
         L = lib()
         self.M, self.N = nx + 1, ny + 1
         M, N = self.M, self.N
@@ -240,19 +242,32 @@ class Problem:
                 L.or_zero_rows(self.Bt.ptr, len(self.bc), iptr(self.bc))
                 L.or_zero_cols(self.B.ptr, len(self.bc), iptr(self.bc))
             self.rhs = np.concatenate([self.f, np.zeros(self.np_)])
+        elif constraints:
+            # the reference's own saddle-point problem (src/SaddlePointProblem.c:45-60, commented out there):
+            # [A Bt; B 0] [u; lambda] = [f; g] with the 4 dense barycentre / moment rows of or_assemble_constraints
+            ps = [CsrP(), CsrP()]
+            L.or_assemble_constraints(M, N, C.byref(ps[0]), C.byref(ps[1]))
+            self.B, self.Bt = Csr(ps[0]), Csr(ps[1])
+            if bc:
+                L.or_zero_rows(self.Bt.ptr, len(self.bc), iptr(self.bc))
+                L.or_zero_cols(self.B.ptr, len(self.bc), iptr(self.bc))
+            self.C = self.Q = None
+            self.np_ = 4
+            self.kkt = True
+            self.rhs = np.concatenate([self.f, np.asarray(g, dtype=np.float64)])
         else:
             self.rhs = self.f
 
     def operator(self):
         if self.kkt:
-            return lib().or_op_nest(self.A.ptr, self.Bt.ptr, self.B.ptr, self.C.ptr)
+            return lib().or_op_nest(self.A.ptr, self.Bt.ptr, self.B.ptr, self.C.ptr if self.C is not None else None)
         return lib().or_op_csr(self.A.ptr)
 
     def scipy_K(self):
         import scipy.sparse as sp
         if not self.kkt:
             return self.A.scipy()
-        return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy()]], format="csr")
+        return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy() if self.C is not None else None]], format="csr")
 
 
 # ------------------------------------------------------------- option wiring
@@ -423,7 +438,8 @@ class Solver:
         k0s = self._make_ksp("fieldsplit_0_", A00op, pc0, default_type="preonly")
         self.ksps["schur_inner_"] = k0s
         K0s = self._ksp_op(k0s)
-        S = L.or_op_schur(prob.C.ptr, prob.B.ptr, K0s, prob.Bt.ptr)
+        Cptr = prob.C.ptr if prob.C is not None else None
+        S = L.or_op_schur(Cptr, prob.B.ptr, K0s, prob.Bt.ptr)
         self.keep.append(S)
         # preconditioning matrix for the S solve
         if pre == "a11":
@@ -434,7 +450,10 @@ class Solver:
             d = prob.A.diagonal()
             BtD = Csr(L.or_csr_scale_cols(prob.B.ptr, dptr(np.ascontiguousarray(1.0 / d))))  # A10 * D^-1
             prod = BtD.matmat(prob.Bt)
-            Sp = Csr(L.or_csr_add_scaled(prob.C.ptr, -1.0, prod.ptr))
+            if prob.C is not None:
+                Sp = Csr(L.or_csr_add_scaled(prob.C.ptr, -1.0, prod.ptr))
+            else:   # no (1,1) block: Sp = -A10 D^-1 A01 = prod + (-2) prod, exact in floating point
+                Sp = Csr(L.or_csr_add_scaled(prod.ptr, -2.0, prod.ptr))
             self.keep += [BtD, prod]
         elif pre == "self":
             Sp = None

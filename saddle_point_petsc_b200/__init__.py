@@ -99,6 +99,7 @@ _SIGS = {
     "b200sp_assemble_stress": [_vp, C.c_int, C.POINTER(_vp)],
     "b200sp_assemble_rhs": [_vp, C.c_int, C.c_int, _vp],
     "b200sp_assemble_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "b200sp_assemble_constraints": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_interp_q1": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
     "b200sp_mat_mult_transpose": [_vp, _vp, _vp],
     "b200sp_pc_create": [_vp, C.POINTER(_vp)],
@@ -548,6 +549,12 @@ class DMDA:
         _chk(lib().b200sp_assemble_kkt(self.h, *[C.byref(h) for h in hs]))
         return tuple(Mat(self.ctx, h) for h in hs)
 
+    def assemble_constraints(self):
+        """AssembleOperator_Constraints (stub in the reference): the 4 dense constraint rows B and B^T"""
+        hb, hbt = _vp(), _vp()
+        _chk(lib().b200sp_assemble_constraints(self.h, C.byref(hb), C.byref(hbt)))
+        return Mat(self.ctx, hb), Mat(self.ctx, hbt)
+
     def destroy(self):
         if self.h:
             _chk(lib().b200sp_dmda_destroy(self.h))
@@ -657,14 +664,17 @@ class SaddlePointProblem:
     """Device-side equivalent of SolveConstraintLaplaceProblem (src/SaddlePointProblem.c:34-76): DMDA ->
     assemble A, f -> Dirichlet BC -> (kkt=True: B^T, B, C, Q blocks and the 2x2 nest) -> KSP."""
 
-    def __init__(self, ctx, nx, ny, kkt=False, rhs_kind=0, as_written=False):
+    def __init__(self, ctx, nx, ny, kkt=False, rhs_kind=0, as_written=False, constraints=False, g=(0.0, 0.0, 0.0, 0.0)):
         self.ctx = ctx
         self.da = DMDA(ctx, nx, ny)
         da = self.da
         self.nu, self.np_ = 2 * da.n_nodes_local, da.n_nodes_local
         self.kkt = kkt
         self.A = da.assemble_stress(as_written)
-        n = self.nu + (self.np_ if kkt else 0)
+        self.constraints = constraints
+        if constraints:   # the reference's own [A Bt; B 0] with 4 constraint rows (src/SaddlePointProblem.c:45-60)
+            self.np_ = 4
+        n = self.nu + (self.np_ if (kkt or constraints) else 0)
         self.rhs = Vec(ctx, n)
         da.assemble_rhs(self.rhs, rhs_kind, as_written)   # fills the velocity part, pressure part stays 0 (g = 0)
         self.bc = da.bc_ids(2)
@@ -675,6 +685,15 @@ class SaddlePointProblem:
             self.Bt.zero_rows(self.bc, 0.0)
             self.B.zero_columns(self.bc)
             self.K = Mat.nest(self.A, self.Bt, self.B, self.C)
+        elif constraints:
+            self.B, self.Bt = da.assemble_constraints()
+            self.Bt.zero_rows(self.bc, 0.0)
+            self.B.zero_columns(self.bc)
+            self.C = self.Q = None
+            self.K = Mat.nest(self.A, self.Bt, self.B, None)
+            gi = np.arange(self.nu, self.nu + 4, dtype=np.int32)       # AssembleRHS_Constraints: g
+            self.rhs.set_values(gi, np.asarray(g, dtype=np.float64))
+            self.kkt = True
         else:
             self.K = self.A
         self.n = n
@@ -682,7 +701,7 @@ class SaddlePointProblem:
     def make_ksp(self, options):
         ksp = KSP(self.ctx)
         ksp.set_operators(self.K, self.K)
-        if self.kkt:
+        if self.kkt and self.Q is not None:
             ksp.set_schur_user_mat(self.Q)
         ksp.set_dmda(self.da)
         ksp.set_options(options)

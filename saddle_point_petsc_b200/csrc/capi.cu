@@ -650,6 +650,16 @@ int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_ma
   if (Q) *Q = wrap(da->d.ctx, q);
   API_END
 }
+int b200sp_assemble_constraints(b200sp_dmda da, b200sp_mat *B, b200sp_mat *Bt) {
+  API_BEGIN
+  B2_REQUIRE(da && B, "assemble_constraints: bad arguments");
+  use_device(da->d.ctx);
+  std::shared_ptr<Csr> b, bt;
+  assemble_constraints(da->d, &b, Bt ? &bt : nullptr);
+  *B = wrap(da->d.ctx, b);
+  if (Bt) *Bt = wrap(da->d.ctx, bt);
+  API_END
+}
 int b200sp_interp_q1(b200sp_ctx ctx, int Mc, int Nc, int dof, int bc, b200sp_mat *P) { API_BEGIN *P = wrap(&ctx->c, interp_q1(&ctx->c, Mc, Nc, dof, bc)); API_END }
 
 // ---------------------------------------------------------------- KSP

@@ -399,6 +399,7 @@ void dense_matvec(Ctx *c, int n, const double *Ainv, const double *x, double *y)
 std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written);
 void assemble_rhs(const Dmda &da, int as_written, int kind, double *f);
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
+void assemble_constraints(const Dmda &da, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *Bt); // the reference's 4 dense constraint rows
 std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc);
 std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc); // = interp_q1^T, built directly
 std::shared_ptr<Csr> interp_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc);

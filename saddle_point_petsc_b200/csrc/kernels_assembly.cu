@@ -420,6 +420,52 @@ __global__ void __launch_bounds__(256) k_rhs_gather(GridBox g, ElemBox eb, const
   }
 }
 
+// AssembleOperator_Constraints (a stub in the reference, Discretization.c:277-283; B is 4 x nCols, SaddlePointProblem.c:48-49):
+// the four dense rows defined in oracle/sp_oracle.c or_element_constraints (barycentre x / y, dilation moment, rotation
+// moment about the domain centre).  One thread per node: for each of its <= 4 elements, in the reference's element order,
+// the element's contribution to this node's six entries is summed over the Gauss points from +0.0 and then added -- the
+// same operations in the same order as the element-vector + ADD_VALUES loop of the oracle.
+__global__ void __launch_bounds__(128) k_constraint_rows(int M, int N, int *__restrict__ col, double *__restrict__ val) {
+  const int nn = M * N, n = 2 * nn;
+  for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < nn; node += gridDim.x * blockDim.x) {
+    const int i = node % M, j = node / M;
+    double t0 = 0.0, t1 = 0.0, t2x = 0.0, t2y = 0.0, t3x = 0.0, t3y = 0.0;
+    for (int ej = max(j - 1, 0); ej <= min(j, N - 2); ++ej)
+      for (int ei = max(i - 1, 0); ei <= min(i, M - 2); ++ei) {
+        double ec[8];
+        element_coords(M, N, ei, ej, 0, ec);
+        const int a = local_node(i, j, ei, ej);
+        double c0 = 0.0, c1 = 0.0, c2x = 0.0, c2y = 0.0, c3x = 0.0, c3y = 0.0;
+        for (int p = 0; p < 4; ++p) {
+          double xi[2], Ni[4], GNi[2][4], GNx[2][4], detJ;
+          gauss_point(p, xi);
+          q1_Ni(xi, Ni);
+          q1_GNi(xi, GNi);
+          q1_GNx(GNi, ec, GNx, &detJ);
+          const double fac = 1.0 * detJ;
+          double xp = 0.0, yp = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { xp += Ni[q] * ec[2 * q]; yp += Ni[q] * ec[2 * q + 1]; }
+          const double rx = xp - 0.5, ry = yp - 0.5;
+          const double w = fac * Ni[a];
+          c0 += w;
+          c1 += w;
+          c2x += w * rx;
+          c2y += w * ry;
+          c3x -= w * ry;
+          c3y += w * rx;
+        }
+        t0 += c0; t1 += c1; t2x += c2x; t2y += c2y; t3x += c3x; t3y += c3y;
+      }
+    col[node] = 2 * node;                 val[node] = t0;
+    col[nn + node] = 2 * node + 1;        val[nn + node] = t1;
+    col[2 * nn + 2 * node] = 2 * node;    val[2 * nn + 2 * node] = t2x;
+    col[2 * nn + 2 * node + 1] = 2 * node + 1; val[2 * nn + 2 * node + 1] = t2y;
+    col[2 * nn + n + 2 * node] = 2 * node;     val[2 * nn + n + 2 * node] = t3x;
+    col[2 * nn + n + 2 * node + 1] = 2 * node + 1; val[2 * nn + n + 2 * node + 1] = t3y;
+  }
+}
+
 // Q1 interpolation (DMCreateInterpolation_DA_2D_Q1 weights), see oracle or_interp_q1
 __global__ void __launch_bounds__(256) k_interp_len(int Mc, int Nc, int dof, int *len) {
   const int Mf = 2 * Mc - 1, Nf = 2 * Nc - 1, nrows = Mf * Nf * dof;
@@ -585,6 +631,26 @@ void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr>
   }
   if (C) { *C = build_box_matrix(da, ea, 1, 1, 0, ea.Ce.p); (*C)->tag = "spmv:C"; }
   if (Q) { *Q = build_box_matrix(da, ea, 1, 1, 0, ea.Qe.p); (*Q)->tag = "spmv:Q"; }
+}
+
+void assemble_constraints(const Dmda &da, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *Bt) {
+  Ctx *c = da.ctx;
+  if (da.halo) throw Error(B200SP_ERR_UNSUPPORTED, "assemble_constraints: the 4 dense constraint rows are assembled on one rank only");
+  const int nn = da.M * da.N, n = 2 * nn;
+  const int64_t nnz = 2LL * nn + 2LL * n;
+  auto Bm = csr_alloc_public(c, 4, n, nnz);
+  const int rp[5] = {0, nn, 2 * nn, 2 * nn + n, 2 * nn + 2 * n};
+  B2_CUDA(cudaMemcpyAsync(Bm->rowptr.p, rp, sizeof(rp), cudaMemcpyHostToDevice, c->stream));
+  {
+    LaunchScope ls(c, "assembly");
+    k_constraint_rows<<<std::max(1, std::min((nn + 127) / 128, c->num_sms * 16)), 128, 0, c->stream>>>(da.M, da.N, Bm->col.p, Bm->val.p);
+    check_launch("k_constraint_rows");
+  }
+  c->sync();
+  Bm->tag = "spmv:Bcon";
+  Bm->plan();
+  if (Bt) { *Bt = csr_transpose(*Bm); (*Bt)->tag = "spmv:Bcon_t"; }
+  if (B) *B = Bm;
 }
 
 std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc) {

@@ -984,8 +984,8 @@ Op *Solver::make_fieldsplit() {
     JacobiOp dj(*A00);
     auto A10D = csr_scale_cols(*A10, dj.dinv.p);
     auto prod = csr_matmat(*A10D, *A01);
-    B2_REQUIRE(A11 != nullptr, "selfp: needs a (1,1) block (may be zero-valued)");
-    Sp = csr_add_scaled(*A11, -1.0, *prod);
+    // no (1,1) block (the reference's [A Bt; B 0]): Sp = -A10 D^-1 A01 = prod + (-2) prod, exact in floating point
+    Sp = A11 ? csr_add_scaled(*A11, -1.0, *prod) : csr_add_scaled(*prod, -2.0, *prod);
     mats.push_back(Sp);
   } else if (pre != "self") throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -pc_fieldsplit_schur_precondition " + pre);
   const std::string pt = opt("fieldsplit_1_pc_type", Sp ? "petsc-default" : "none");

@@ -146,3 +146,44 @@ def test_velocity_only_problem_all_krylov_types():
         else:
             r = so.Solver(p, opts + " -ksp_rtol 1e-10").solve()
             assert r["reason"] == 2 and np.abs(r["x"] - u).max() < 1e-8, opts
+
+
+# ------------------------------------------------------------------ the reference's own constraint block (4 dense rows)
+G_CON = (0.01, -0.02, 0.005, 0.003)
+CON_OPTS = ("-ksp_rtol 1e-10 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_precondition selfp "
+            "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels 3 -fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type lu ")
+CON_CONFIGS = {"fgmres_upper": "-ksp_type fgmres -pc_fieldsplit_schur_fact_type upper " + CON_OPTS,
+               "minres_diag": "-ksp_type minres -pc_fieldsplit_schur_fact_type diag " + CON_OPTS,
+               "gmres_full": "-ksp_type gmres -pc_fieldsplit_schur_fact_type full " + CON_OPTS}
+
+
+def test_constraint_rows_are_the_moments_they_claim_to_be():
+    """B is 4 x nCols (src/SaddlePointProblem.c:48-49): barycentre x / y, dilation and rotation moments about the centre."""
+    nx, ny = 12, 9
+    p = so.Problem(nx, ny, constraints=True, bc=False)
+    B = p.B.scipy()
+    M, N = nx + 1, ny + 1
+    assert B.shape == (4, 2 * M * N) and abs(p.Bt.scipy() - B.T).max() == 0.0
+    X, Y = np.meshgrid(np.linspace(0, 1, M), np.linspace(0, 1, N))
+    def field(ux, uy):
+        u = np.zeros(2 * M * N)
+        u[0::2], u[1::2] = ux.ravel(), uy.ravel()
+        return u
+    one, zero = np.ones_like(X), np.zeros_like(X)
+    assert np.allclose(B @ field(one, zero), [1.0, 0.0, 0.0, 0.0], atol=1e-12)          # int 1 = area
+    assert np.allclose(B @ field(zero, one), [0.0, 1.0, 0.0, 0.0], atol=1e-12)
+    assert np.allclose(B @ field(X - 0.5, Y - 0.5), [0.0, 0.0, 1.0 / 6.0, 0.0], atol=1e-9)   # int |x-c|^2 = 2/12 (Gauss literal: 1e-11)
+    assert np.allclose(B @ field(-(Y - 0.5), X - 0.5), [0.0, 0.0, 0.0, 1.0 / 6.0], atol=1e-9)  # rigid rotation
+
+
+@pytest.mark.parametrize("name", sorted(CON_CONFIGS))
+def test_constrained_problem_solves_to_the_direct_solution(name):
+    """[A Bt; B 0][u; lambda] = [f; g] (the commented-out wiring of src/SaddlePointProblem.c:45-60): Schur complement is the
+    dense 4 x 4 -B A^-1 Bt, preconditioned by selfp (-B diag(A)^-1 Bt) solved exactly."""
+    import scipy.sparse.linalg as spla
+    p = so.Problem(16, 16, constraints=True, g=G_CON)
+    x = spla.spsolve(p.scipy_K().tocsc(), p.rhs)
+    assert np.allclose(p.B.scipy() @ x[:-4], G_CON, atol=1e-13)
+    r = so.Solver(p, CON_CONFIGS[name]).solve()
+    assert r["reason"] == 2 and r["its"] <= 25, (r["reason"], r["its"])
+    assert np.max(np.abs(r["x"] - x)) <= 1e-8 * np.max(np.abs(x))
