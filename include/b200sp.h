@@ -26,6 +26,7 @@ typedef struct b200sp_vec_s *b200sp_vec;
 typedef struct b200sp_mat_s *b200sp_mat;
 typedef struct b200sp_ksp_s *b200sp_ksp;
 typedef struct b200sp_dmda_s *b200sp_dmda;
+typedef struct b200sp_dmda3d_s *b200sp_dmda3d;
 typedef struct b200sp_pc_s *b200sp_pc;
 
 enum {
@@ -185,6 +186,18 @@ int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec
 /* KKT blocks on the same nodal grid: Bt (gradient), B = Bt^T (divergence), C (stabilisation, the (2,2)
  * block), Q (= -pressure mass matrix, the "user" Schur preconditioning matrix) */
 int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q);
+/* ---- 3-D (BASELINE config 4; the reference is 2-D only, include/Discretization.h:8): DMDACreate3d-style grid of M x N x P
+ *      nodes, box stencil, PETSC_DECIDE process grid, and the Q1-hexahedron analogue of the 2-D assembly (definition:
+ *      oracle/sp_oracle3d.c).  Velocity 3 dof per node, pressure 1; rows are local, columns local (ghosts after the owned). ---- */
+int b200sp_dmda3d_proc_grid(int M, int N, int P, int size, int *m, int *n, int *p);
+int b200sp_dmda3d_create(b200sp_ctx ctx, int M, int N, int P, b200sp_dmda3d *da);
+int b200sp_dmda3d_destroy(b200sp_dmda3d da);
+int b200sp_dmda3d_get_info(b200sp_dmda3d da, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm, int64_t *first_global_node);
+int b200sp_dmda3d_bc_ids(b200sp_dmda3d da, int dof, int *n, int *ids); /* local row ids of the owned boundary nodes */
+int b200sp_assemble3d_stress(b200sp_dmda3d da, b200sp_mat *A);
+int b200sp_assemble3d_rhs(b200sp_dmda3d da, int rhs_kind, b200sp_vec f); /* 0: (1,2,3); 1: rotational force about z */
+int b200sp_assemble3d_kkt(b200sp_dmda3d da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q);
+
 /* AssembleOperator_Constraints (an empty stub in the reference, src/Discretization.c:277-283; B is 4 x nCols,
  * src/SaddlePointProblem.c:48-49): the four dense constraint rows "barycentre and volume" (src/main.c:1) -- barycentre
  * x / y, dilation moment, rotation moment of the displacement field about the domain centre -- and B^T.  One rank only. */

@@ -68,6 +68,15 @@ void or_apply_bc(OrCsr *A, double *f, int nbc, const int *ids);      /* MatZeroR
  * Bt (2MN x MN) gradient, B = Bt^T, C (MN x MN) stabilisation (the (2,2) block, sign included),
  * Q (MN x MN) = -pressure mass matrix (the "user" Schur preconditioning matrix). */
 void or_assemble_kkt(int M, int N, OrCsr **Bt, OrCsr **B, OrCsr **C, OrCsr **Q);
+/* ---- 3-D Q1 hexahedron analogue (sp_oracle3d.c; BASELINE config 4 -- no reference code exists: DIM 2 is a #define) ---- */
+void or3_element_coords(int M, int N, int P, int ei, int ej, int ek, double ec[24]);
+void or3_element_stress(const double ec[24], double Ke[576]);                           /* += */
+void or3_element_rhs(const double ec[24], int kind, double Fe[24]);                     /* += */
+void or3_element_kkt(const double ec[24], double Ge[192], double Ce[64], double Qe[64]); /* += */
+OrCsr *or3_assemble_A(int M, int N, int P);
+void or3_assemble_rhs(int M, int N, int P, int kind, double *f);
+void or3_assemble_kkt(int M, int N, int P, OrCsr **Bt, OrCsr **B, OrCsr **C, OrCsr **Q);
+int or3_bc_ids(int M, int N, int P, int dof, int *ids); /* ids may be NULL to query the count */
 void or_element_constraints(const double ec[8], double Be[32]);               /* += ; the reference's 4 constraint rows (ours) */
 void or_assemble_constraints(int M, int N, OrCsr **B, OrCsr **Bt);            /* B: 4 x 2MN, Bt = B^T */
 void or_zero_rows(OrCsr *A, int n, const int *rows);

@@ -76,6 +76,14 @@ def lib():
     sig("or_bc_ids", C.c_int, C.c_int, C.c_int, C.c_int, c_ip)
     sig("or_apply_bc", None, CsrP, c_dp, C.c_int, c_ip)
     sig("or_assemble_kkt", None, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP))
+    sig("or3_assemble_A", CsrP, C.c_int, C.c_int, C.c_int)
+    sig("or3_assemble_rhs", None, C.c_int, C.c_int, C.c_int, C.c_int, c_dp)
+    sig("or3_assemble_kkt", None, C.c_int, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP))
+    sig("or3_bc_ids", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip)
+    sig("or3_element_coords", None, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp)
+    sig("or3_element_stress", None, c_dp, c_dp)
+    sig("or3_element_rhs", None, c_dp, C.c_int, c_dp)
+    sig("or3_element_kkt", None, c_dp, c_dp, c_dp, c_dp)
     sig("or_assemble_constraints", None, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP))
     sig("or_element_constraints", None, c_dp, c_dp)
     sig("or_zero_rows", None, CsrP, C.c_int, c_ip)
@@ -268,6 +276,40 @@ class Problem:
         if not self.kkt:
             return self.A.scipy()
         return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy() if self.C is not None else None]], format="csr")
+
+
+class Problem3D:
+    """3-D Q1-hexahedron KKT problem [A Bt; B C] on (nx+1)(ny+1)(nz+1) nodes (BASELINE config 4; sp_oracle3d.c)."""
+
+    def __init__(self, nx, ny, nz, rhs_kind=1, bc=True):
+        L = lib()
+        self.M, self.N, self.P = nx + 1, ny + 1, nz + 1
+        M, N, P = self.M, self.N, self.P
+        nn = M * N * P
+        self.nu, self.np_ = 3 * nn, nn
+        self.A = Csr(L.or3_assemble_A(M, N, P))
+        self.f = np.zeros(self.nu)
+        L.or3_assemble_rhs(M, N, P, rhs_kind, dptr(self.f))
+        nbc = L.or3_bc_ids(M, N, P, 3, None)
+        self.bc = np.zeros(nbc, dtype=np.int32)
+        L.or3_bc_ids(M, N, P, 3, iptr(self.bc))
+        if bc:
+            L.or_apply_bc(self.A.ptr, dptr(self.f), len(self.bc), iptr(self.bc))
+        ps = [CsrP() for _ in range(4)]
+        L.or3_assemble_kkt(M, N, P, *[C.byref(p) for p in ps])
+        self.Bt, self.B, self.C, self.Q = [Csr(p) for p in ps]
+        if bc:
+            L.or_zero_rows(self.Bt.ptr, len(self.bc), iptr(self.bc))
+            L.or_zero_cols(self.B.ptr, len(self.bc), iptr(self.bc))
+        self.kkt = True
+        self.rhs = np.concatenate([self.f, np.zeros(self.np_)])
+
+    def operator(self):
+        return lib().or_op_nest(self.A.ptr, self.Bt.ptr, self.B.ptr, self.C.ptr)
+
+    def scipy_K(self):
+        import scipy.sparse as sp
+        return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy()]], format="csr")
 
 
 # ------------------------------------------------------------- option wiring

@@ -99,6 +99,14 @@ _SIGS = {
     "b200sp_assemble_stress": [_vp, C.c_int, C.POINTER(_vp)],
     "b200sp_assemble_rhs": [_vp, C.c_int, C.c_int, _vp],
     "b200sp_assemble_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "b200sp_dmda3d_proc_grid": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip],
+    "b200sp_dmda3d_create": [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
+    "b200sp_dmda3d_destroy": [_vp],
+    "b200sp_dmda3d_get_info": [_vp, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)],
+    "b200sp_dmda3d_bc_ids": [_vp, C.c_int, c_ip, c_ip],
+    "b200sp_assemble3d_stress": [_vp, C.POINTER(_vp)],
+    "b200sp_assemble3d_rhs": [_vp, C.c_int, _vp],
+    "b200sp_assemble3d_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_assemble_constraints": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_interp_q1": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
     "b200sp_mat_mult_transpose": [_vp, _vp, _vp],
@@ -561,6 +569,47 @@ class DMDA:
             self.h = _vp()
 
 
+class DMDA3D:
+    """DMDACreate3d(..., nx+1, ny+1, nz+1, box stencil width 1): the 3-D grid of BASELINE config 4."""
+
+    def __init__(self, ctx, nx, ny, nz):
+        self.ctx = ctx
+        self.M, self.N, self.P = nx + 1, ny + 1, nz + 1
+        self.h = _vp()
+        _chk(lib().b200sp_dmda3d_create(ctx.h, self.M, self.N, self.P, C.byref(self.h)))
+        v = [C.c_int() for _ in range(6)]
+        g0 = C.c_int64()
+        _chk(lib().b200sp_dmda3d_get_info(self.h, *[C.byref(x) for x in v], C.byref(g0)))
+        self.xs, self.ys, self.zs, self.xm, self.ym, self.zm = [x.value for x in v]
+        self.gstart = g0.value
+        self.n_nodes_local = self.xm * self.ym * self.zm
+
+    def bc_ids(self, dof=3):
+        n = C.c_int()
+        _chk(lib().b200sp_dmda3d_bc_ids(self.h, dof, C.byref(n), None))
+        ids = np.zeros(n.value, dtype=np.int32)
+        _chk(lib().b200sp_dmda3d_bc_ids(self.h, dof, C.byref(n), _iptr(ids)))
+        return ids
+
+    def assemble_stress(self):
+        h = _vp()
+        _chk(lib().b200sp_assemble3d_stress(self.h, C.byref(h)))
+        return Mat(self.ctx, h)
+
+    def assemble_rhs(self, f, rhs_kind=1):
+        _chk(lib().b200sp_assemble3d_rhs(self.h, rhs_kind, f.h))
+
+    def assemble_kkt(self):
+        hs = [_vp() for _ in range(4)]
+        _chk(lib().b200sp_assemble3d_kkt(self.h, *[C.byref(h) for h in hs]))
+        return tuple(Mat(self.ctx, h) for h in hs)
+
+    def destroy(self):
+        if self.h:
+            _chk(lib().b200sp_dmda3d_destroy(self.h))
+            self.h = _vp()
+
+
 class PC:
     """PCCreate / PCSetOperators / PCSetFromOptions / PCSetUp / PCApply as an object of its own."""
 
@@ -704,5 +753,35 @@ class SaddlePointProblem:
         if self.kkt and self.Q is not None:
             ksp.set_schur_user_mat(self.Q)
         ksp.set_dmda(self.da)
+        ksp.set_options(options)
+        return ksp
+
+
+class SaddlePointProblem3D:
+    """The 3-D Stokes-type KKT problem of BASELINE config 4: [A Bt; B C] on a Q1-hexahedron grid, velocity Dirichlet on the
+    whole boundary, rotational body force; Q (= -pressure mass) is the `user` Schur preconditioning matrix."""
+
+    def __init__(self, ctx, nx, ny, nz, rhs_kind=1):
+        self.ctx = ctx
+        self.da = DMDA3D(ctx, nx, ny, nz)
+        da = self.da
+        self.nu, self.np_ = 3 * da.n_nodes_local, da.n_nodes_local
+        self.n = self.nu + self.np_
+        self.A = da.assemble_stress()
+        self.rhs = Vec(ctx, self.n)
+        da.assemble_rhs(self.rhs, rhs_kind)
+        self.bc = da.bc_ids(3)
+        self.rhs.set_values(self.bc, np.zeros(len(self.bc)))
+        self.A.zero_rows_columns(self.bc, 1.0)
+        self.Bt, self.B, self.C, self.Q = da.assemble_kkt()
+        self.Bt.zero_rows(self.bc, 0.0)
+        self.B.zero_columns(self.bc)
+        self.K = Mat.nest(self.A, self.Bt, self.B, self.C)
+        self.kkt = True
+
+    def make_ksp(self, options):
+        ksp = KSP(self.ctx)
+        ksp.set_operators(self.K, self.K)
+        ksp.set_schur_user_mat(self.Q)
         ksp.set_options(options)
         return ksp

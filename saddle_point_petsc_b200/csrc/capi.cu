@@ -19,6 +19,7 @@ struct b200sp_mat_s {
 struct b200sp_ksp_s { Solver s; explicit b200sp_ksp_s(Ctx *c) : s(c) {} };
 struct b200sp_pc_s { Solver s; explicit b200sp_pc_s(Ctx *c) : s(c) {} }; // a PC is the preconditioner half of the same solver object
 struct b200sp_dmda_s { Dmda d; };
+struct b200sp_dmda3d_s { Dmda3 d; };
 
 static thread_local std::string g_last_error;
 
@@ -661,6 +662,115 @@ int b200sp_assemble_constraints(b200sp_dmda da, b200sp_mat *B, b200sp_mat *Bt) {
   API_END
 }
 int b200sp_interp_q1(b200sp_ctx ctx, int Mc, int Nc, int dof, int bc, b200sp_mat *P) { API_BEGIN *P = wrap(&ctx->c, interp_q1(&ctx->c, Mc, Nc, dof, bc)); API_END }
+
+// ---------------------------------------------------------------- 3-D DMDA + assembly (BASELINE config 4)
+// DMDACreate3d(PETSC_DECIDE x3) process grid (PETSc da3.c: squarish factorisation), ownership M/m + (M%m > i) per direction
+static void dmda3_proc_grid(int M, int N, int P, int size, int *pm, int *pn, int *pp) {
+  int n = (int)(0.5 + std::pow(((double)N * N) * ((double)size) / ((double)P * M), 1.0 / 3.0)), m, p = 1;
+  if (!n) n = 1;
+  while (n > 0) { const int pmn = size / n; if (n * pmn == size) break; n--; }
+  if (!n) n = 1;
+  m = (int)(0.5 + std::sqrt(((double)M) * ((double)size) / ((double)P * n)));
+  if (!m) m = 1;
+  while (m > 0) { p = size / (m * n); if (m * n * p == size) break; m--; }
+  if (M > P && m < p) std::swap(m, p);
+  *pm = m; *pn = n; *pp = p;
+}
+int b200sp_dmda3d_proc_grid(int M, int N, int P, int size, int *m, int *n, int *p) {
+  API_BEGIN B2_REQUIRE(M > 0 && N > 0 && P > 0 && size > 0, "bad args"); dmda3_proc_grid(M, N, P, size, m, n, p); API_END
+}
+int b200sp_dmda3d_create(b200sp_ctx ctx, int M, int N, int P, b200sp_dmda3d *da) {
+  API_BEGIN
+  B2_REQUIRE(ctx && da && M >= 2 && N >= 2 && P >= 2, "dmda3d_create: bad arguments");
+  Ctx *c = &ctx->c;
+  use_device(c);
+  auto *h = new b200sp_dmda3d_s();
+  try {
+    Dmda3 &d = h->d;
+    d.ctx = c; d.M = M; d.N = N; d.P = P;
+    const int size = c->size, rank = c->rank;
+    dmda3_proc_grid(M, N, P, size, &d.pm, &d.pn, &d.pp);
+    B2_REQUIRE(d.pm * d.pn * d.pp == size && d.pm <= M && d.pn <= N && d.pp <= P, "dmda3d: size does not factor into a process grid for this mesh");
+    std::vector<int> lx((size_t)d.pm), ly((size_t)d.pn), lz((size_t)d.pp), xo((size_t)d.pm + 1, 0), yo((size_t)d.pn + 1, 0), zo((size_t)d.pp + 1, 0);
+    dmda_ownership(M, d.pm, lx.data()); dmda_ownership(N, d.pn, ly.data()); dmda_ownership(P, d.pp, lz.data());
+    for (int i = 0; i < d.pm; ++i) xo[(size_t)i + 1] = xo[(size_t)i] + lx[(size_t)i];
+    for (int i = 0; i < d.pn; ++i) yo[(size_t)i + 1] = yo[(size_t)i] + ly[(size_t)i];
+    for (int i = 0; i < d.pp; ++i) zo[(size_t)i + 1] = zo[(size_t)i] + lz[(size_t)i];
+    auto box = [&](int r, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm) {
+      const int pi = r % d.pm, pj = (r / d.pm) % d.pn, pk = r / (d.pm * d.pn);
+      *xs = xo[(size_t)pi]; *ys = yo[(size_t)pj]; *zs = zo[(size_t)pk]; *xm = lx[(size_t)pi]; *ym = ly[(size_t)pj]; *zm = lz[(size_t)pk];
+    };
+    std::vector<int> rstart((size_t)size + 1, 0);
+    for (int r = 0; r < size; ++r) { int a, b, e, xm, ym, zm; box(r, &a, &b, &e, &xm, &ym, &zm); rstart[(size_t)r + 1] = rstart[(size_t)r] + xm * ym * zm; }
+    box(rank, &d.xs, &d.ys, &d.zs, &d.xm, &d.ym, &d.zm);
+    B2_REQUIRE(size == 1 || (d.xm >= 2 && d.ym >= 2 && d.zm >= 2), "dmda3d: every rank must own at least 2 x 2 x 2 nodes");
+    d.g0 = rstart[(size_t)rank];
+    auto owner_of = [&](const std::vector<int> &off, int v) { return (int)(std::upper_bound(off.begin(), off.end(), v) - off.begin()) - 1; };
+    auto gnode = [&](int i, int j, int k) {
+      const int pi = owner_of(xo, i), pj = owner_of(yo, j), pk = owner_of(zo, k), r = (pk * d.pn + pj) * d.pm + pi;
+      return rstart[(size_t)r] + ((k - zo[(size_t)pk]) * ly[(size_t)pj] + (j - yo[(size_t)pj])) * lx[(size_t)pi] + (i - xo[(size_t)pi]);
+    };
+    // ghost nodes: the one-node layer around the owned box, clipped to the domain, sorted by global id (MPIAIJ garray order)
+    const int ex = d.xm + 2, ey = d.ym + 2, ez = d.zm + 2;
+    std::vector<std::pair<int, int>> gh; // (global node id, ext index)
+    std::vector<int> lut((size_t)ex * ey * ez, -1);
+    for (int k = d.zs - 1; k <= d.zs + d.zm; ++k)
+      for (int j = d.ys - 1; j <= d.ys + d.ym; ++j)
+        for (int i = d.xs - 1; i <= d.xs + d.xm; ++i) {
+          if (i < 0 || i >= M || j < 0 || j >= N || k < 0 || k >= P) continue;
+          const int e = ((k - d.zs + 1) * ey + (j - d.ys + 1)) * ex + (i - d.xs + 1);
+          const bool owned = i >= d.xs && i < d.xs + d.xm && j >= d.ys && j < d.ys + d.ym && k >= d.zs && k < d.zs + d.zm;
+          if (owned) lut[(size_t)e] = ((k - d.zs) * d.ym + (j - d.ys)) * d.xm + (i - d.xs);
+          else gh.push_back({gnode(i, j, k), e});
+        }
+    std::sort(gh.begin(), gh.end());
+    const int nown = d.xm * d.ym * d.zm;
+    std::vector<int> ghost_gnode;
+    for (size_t t = 0; t < gh.size(); ++t) { lut[(size_t)gh[t].second] = nown + (int)t; ghost_gnode.push_back(gh[t].first); }
+    dmda3_build_lut(d, lut);
+    if (size > 1) {
+      d.layout = std::make_shared<Layout>();
+      d.layout->M = M; d.layout->N = N; d.layout->size = size; d.layout->rstart = rstart;
+      d.halo = make_halo_general(c, *d.layout, rank, ghost_gnode);
+    }
+  } catch (...) { delete h; throw; }
+  *da = h;
+  API_END
+}
+int b200sp_dmda3d_destroy(b200sp_dmda3d da) { API_BEGIN delete da; API_END }
+int b200sp_dmda3d_get_info(b200sp_dmda3d da, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm, int64_t *gstart) {
+  API_BEGIN
+  const Dmda3 &d = da->d;
+  if (xs) *xs = d.xs; if (ys) *ys = d.ys; if (zs) *zs = d.zs; if (xm) *xm = d.xm; if (ym) *ym = d.ym; if (zm) *zm = d.zm;
+  if (gstart) *gstart = d.g0;
+  API_END
+}
+int b200sp_dmda3d_bc_ids(b200sp_dmda3d da, int dof, int *n, int *ids) {
+  API_BEGIN
+  std::vector<int> v = dmda3_bc_ids(da->d, dof);
+  if (n) *n = (int)v.size();
+  if (ids) std::copy(v.begin(), v.end(), ids);
+  API_END
+}
+int b200sp_assemble3d_stress(b200sp_dmda3d da, b200sp_mat *A) { API_BEGIN use_device(da->d.ctx); *A = wrap(da->d.ctx, assemble3_stress(da->d)); API_END }
+int b200sp_assemble3d_rhs(b200sp_dmda3d da, int rhs_kind, b200sp_vec f) {
+  API_BEGIN
+  B2_REQUIRE(f->v.n >= (int64_t)da->d.xm * da->d.ym * da->d.zm * 3, "assemble3d_rhs: vector too short");
+  use_device(da->d.ctx);
+  assemble3_rhs(da->d, rhs_kind, f->v.d);
+  API_END
+}
+int b200sp_assemble3d_kkt(b200sp_dmda3d da, b200sp_mat *Bt, b200sp_mat *B, b200sp_mat *C, b200sp_mat *Q) {
+  API_BEGIN
+  std::shared_ptr<Csr> bt, b, c, q;
+  use_device(da->d.ctx);
+  assemble3_kkt(da->d, Bt ? &bt : nullptr, B ? &b : nullptr, C ? &c : nullptr, Q ? &q : nullptr);
+  if (Bt) *Bt = wrap(da->d.ctx, bt);
+  if (B) *B = wrap(da->d.ctx, b);
+  if (C) *C = wrap(da->d.ctx, c);
+  if (Q) *Q = wrap(da->d.ctx, q);
+  API_END
+}
 
 // ---------------------------------------------------------------- KSP
 int b200sp_ksp_create(b200sp_ctx ctx, b200sp_ksp *ksp) { API_BEGIN B2_REQUIRE(ctx && ksp, "ksp_create: bad arguments"); *ksp = new b200sp_ksp_s(&ctx->c); API_END }

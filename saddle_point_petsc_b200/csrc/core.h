@@ -145,6 +145,18 @@ struct Dmda {
   std::shared_ptr<Halo> halo;             // ghost ring of this rank (null on one rank)
 };
 
+// 3-D DMDA (BASELINE config 4): owned node box of this rank, ext-box column lookup table, ghost halo (null on one rank)
+struct Dmda3 {
+  Ctx *ctx = nullptr;
+  int M = 0, N = 0, P = 0;
+  int pm = 1, pn = 1, pp = 1;
+  int xs = 0, ys = 0, zs = 0, xm = 0, ym = 0, zm = 0;
+  int64_t g0 = 0;                   // first global (PETSc numbering) node id of this rank
+  DevBuf<int> lut;                  // (xm+2)(ym+2)(zm+2): local column node id (owned: local index, ghost: n_owned + ghost index, -1 outside)
+  std::shared_ptr<Halo> halo;
+  std::shared_ptr<Layout> layout;   // carries size and rstart for the general halo
+};
+
 // ------------------------------------------------------------------ Mat
 enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3 };
 struct XSrc;
@@ -400,6 +412,12 @@ std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written);
 void assemble_rhs(const Dmda &da, int as_written, int kind, double *f);
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
 void assemble_constraints(const Dmda &da, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *Bt); // the reference's 4 dense constraint rows
+// 3-D assembly (kernels_assembly3d.cu)
+void dmda3_build_lut(Dmda3 &da, const std::vector<int> &host_lut);
+std::shared_ptr<Csr> assemble3_stress(const Dmda3 &da);
+void assemble3_rhs(const Dmda3 &da, int kind, double *f);
+void assemble3_kkt(const Dmda3 &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
+std::vector<int> dmda3_bc_ids(const Dmda3 &da, int dof);
 std::shared_ptr<Csr> interp_q1(Ctx *c, int Mc, int Nc, int dof, int bc);
 std::shared_ptr<Csr> restrict_q1(Ctx *c, int Mc, int Nc, int dof, int bc); // = interp_q1^T, built directly
 std::shared_ptr<Csr> interp_q1_dist(const Dmda &fine, const Dmda &coarse, int dof, int bc);

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -q) > gpurun_out/r02_pytest8.log 2>&1
-grep -E "^E   |^FAILED|passed|failed" gpurun_out/r02_pytest8.log | cut -c1-300 | head -30
+(time python -m pytest tests/test_3d.py -m gpu -q) > gpurun_out/r02_pytest9.log 2>&1
+grep -E "^E   |^FAILED|passed|failed|rror" gpurun_out/r02_pytest9.log | cut -c1-300 | head -30
