@@ -62,6 +62,14 @@ CONFIGS = {
                            "-pc_fieldsplit_schur_fact_type full -pc_fieldsplit_schur_precondition user "
                            "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type jacobi -fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
 }
+# BASELINE config 4: 3-D Stokes-type KKT (Q1 hexahedra, 4 dof per node), MINRES + block-diagonal preconditioner with a
+# Chebyshev/Jacobi A00 solve and the pressure-mass-matrix Schur approximation.  --nx = elements per side of the cube.
+CONFIGS_3D = {
+    "minres3d_diag_cheb": ("-ksp_type minres -ksp_rtol 1e-8 -ksp_max_it 20000 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type diag "
+                           "-pc_fieldsplit_schur_precondition user -fieldsplit_0_ksp_type chebyshev -fieldsplit_0_ksp_max_it 4 -fieldsplit_0_pc_type jacobi "
+                           "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
+}
+CONFIGS.update(CONFIGS_3D)
 # north_star tolerances (BASELINE.json): iterations +-1, final relative residual 1e-10, solution rel 1e-8
 TOL_ITS, TOL_RES, TOL_X = 1, 1e-10, 1e-8
 
@@ -141,16 +149,23 @@ def oracle():
     return so
 
 
-def oracle_solve_setup(nx, opts):
+def make_problem(sp, ctx, config, nx):
+    if config in CONFIGS_3D:
+        return sp.SaddlePointProblem3D(ctx, nx, nx, nx, rhs_kind=1)
+    return sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
+
+
+def oracle_solve_setup(nx, opts, config="fgmres_schur_mg"):
     so = oracle()
     t0 = time.perf_counter()
-    prob = so.Problem(nx, nx, kkt=True, rhs_kind=1)
+    prob = so.Problem3D(nx, nx, nx, rhs_kind=1) if config in CONFIGS_3D else so.Problem(nx, nx, kkt=True, rhs_kind=1)
     solver = so.Solver(prob, opts)
     return so, prob, solver, time.perf_counter() - t0
 
 
 def workload(args, dof, opts):
-    return {"workload": "kkt2d_%s" % args.config, "grid_elements": [args.nx, args.nx], "dof": int(dof), "solver_options": opts,
+    is3d = args.config in CONFIGS_3D
+    return {"workload": ("kkt3d_%s" if is3d else "kkt2d_%s") % args.config, "grid_elements": [args.nx] * (3 if is3d else 2), "dof": int(dof), "solver_options": opts,
             "rtol": 1e-8, "l2_policy": "inputs (5 GB of matrices, 128 MB vectors) far larger than the 126 MB L2; no explicit flush",
             "parallelism": "dmda_row_partition_x%d" % args.gpus}
 
@@ -161,7 +176,7 @@ def run_reference(args, opts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    so, prob, solver, t_setup = oracle_solve_setup(args.nx, opts)
+    so, prob, solver, t_setup = oracle_solve_setup(args.nx, opts, args.config)
     cores = so.lib().or_get_threads()
     steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
     for _ in range(warmup):
@@ -386,11 +401,11 @@ def main():
 
     ctx = sp.Context(device=local_rank, rank=rank, size=world, nccl_id=nccl_id)
     dcheck = None
-    if world > 1 and not args.no_dist_check:
+    if world > 1 and not args.no_dist_check and args.config not in CONFIGS_3D:
         dcheck = dist_check(sp, ctx, dist)
         barrier()
     t0 = time.perf_counter()
-    prob = sp.SaddlePointProblem(ctx, args.nx, args.nx, kkt=True, rhs_kind=1)
+    prob = make_problem(sp, ctx, args.config, args.nx)
     ctx.synchronize()
     t_assembly = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -516,7 +531,7 @@ def main():
     # ---- N=1: the same system through the CPU oracle -> cpu_baseline + parity at the benchmarked size
     cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
-        so, oprob, osolver, t_osetup = oracle_solve_setup(args.nx, opts)
+        so, oprob, osolver, t_osetup = oracle_solve_setup(args.nx, opts, args.config)
         t0 = time.perf_counter()
         orr = osolver.solve(history=True)
         t_cpu = time.perf_counter() - t0

@@ -158,7 +158,7 @@ struct Dmda3 {
 };
 
 // ------------------------------------------------------------------ Mat
-enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3 };
+enum SpmvKernel { SPMV_STREAM = 0, SPMV_VECTOR = 1, SPMV_BLOCK = 2, SPMV_TMA = 3, SPMV_NODE = 4 }; // NODE: warp per node-block row (3-D blocks)
 struct XSrc;
 struct SpmvEpi;
 constexpr int TMA_TILE_ROWS = 128; // rows per tile of the TMA SpMV kernel (profiles/r01_tma_tile_sweep.txt)
@@ -296,7 +296,7 @@ struct PushOut {
   int nmsg = 0, dof = 1;
 #ifdef __CUDACC__
   __device__ __forceinline__ void row(int r, double v) const { // row r of the produced vector has the value v
-    const int node = dof == 2 ? r >> 1 : r, c = dof == 2 ? r & 1 : 0;
+    const int node = dof == 2 ? r >> 1 : (dof == 1 ? r : r / dof), c = r - node * dof;
     if (!grp[node >> 6]) return;
     const int e = node_ent[node];
     if (!e) return;

@@ -397,7 +397,7 @@ static void setup_p2p(Halo &h, const Layout &L, int rank) {
   static_assert(sizeof(Rec) <= REC * sizeof(double), "record too large");
   h.n_msgs = (int)h.node_msgs.size();
   B2_REQUIRE(h.n_msgs <= 8, "halo: more than 8 neighbours");
-  h.ghost_stride = ((int64_t)h.n_ghost * 2 + 2 + 15) & ~15LL;
+  h.ghost_stride = ((int64_t)h.n_ghost * HALO_MAX_DOF + 2 + 15) & ~15LL;
   h.ghost.alloc((size_t)h.ghost_stride * 2);
   h.ghost.zero(c->stream);
   h.seq.alloc(1); h.seq.zero(c->stream);
@@ -541,8 +541,8 @@ static std::shared_ptr<Halo> halo_from_plan(Ctx *c, const Layout &L, int rank, c
   h->d_ring2ghost.alloc(ring.size() + 1);
   if (h->n_send) B2_CUDA(cudaMemcpyAsync(h->d_send_lnode.p, send_lnode.data(), sizeof(int) * send_lnode.size(), cudaMemcpyHostToDevice, c->stream));
   B2_CUDA(cudaMemcpyAsync(h->d_ring2ghost.p, ring.data(), sizeof(int) * ring.size(), cudaMemcpyHostToDevice, c->stream));
-  h->sendbuf.alloc((size_t)h->n_send * 2 + 2);
-  h->ghost.alloc((size_t)h->n_ghost * 2 + 2);
+  h->sendbuf.alloc((size_t)h->n_send * HALO_MAX_DOF + 2);
+  h->ghost.alloc((size_t)h->n_ghost * HALO_MAX_DOF + 2);
   h->ghost.zero(c->stream);
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming));
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_arrived, cudaEventDisableTiming));
@@ -624,7 +624,7 @@ std::shared_ptr<Halo> make_halo_general(Ctx *c, const Layout &L, int rank, const
 }
 
 void Halo::begin(const double *x, int dof) {
-  B2_REQUIRE(dof == 1 || dof == 2, "halo: dof must be 1 or 2");
+  B2_REQUIRE(dof >= 1 && dof <= HALO_MAX_DOF, "halo: dof must be 1, 2 or 3");
   Ctx *c = ctx;
   if (!c->dcomm || (n_send == 0 && n_ghost == 0)) return;
   if (p2p && pushed_vec) { // the kernel that produced x already pushed it (csr_spmv_epi push_to)

@@ -14,6 +14,7 @@ namespace b200sp {
 //   LocalComm all ranks are threads of ONE process (one or several GPUs): host barrier + cudaMemcpyPeerAsync.
 //             Used by the tests (the whole distributed algorithm runs on a 1-GPU box, ranks never wait on each
 //             other inside a kernel) and usable as a single-process multi-GPU mode.
+constexpr int HALO_MAX_DOF = 3; // values per node a halo exchange can carry (2-D velocity 2, 3-D velocity 3, pressure 1)
 struct HaloMsg { int peer; int64_t send_off, send_cnt, recv_off, recv_cnt; }; // in doubles
 
 struct Comm {
@@ -104,7 +105,7 @@ struct Halo {
   DevBuf<int> d_send_lnode;                       // owned local node ids to pack, grouped by neighbour
   int n_send = 0;
   DevBuf<int> d_ring2ghost;                       // ring position -> ghost index (-1 outside the domain)
-  DevBuf<double> sendbuf, ghost;                  // sized for dof <= 2 (ghost holds two parities in peer-to-peer mode)
+  DevBuf<double> sendbuf, ghost;                  // sized for dof <= HALO_MAX_DOF (ghost holds two parities in peer-to-peer mode)
   cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
   // ---- peer-to-peer mode (NVLink): the "pack" kernel stores every outgoing value DIRECTLY into the neighbour's ghost
   // buffer (CUDA IPC mapping) and then raises a sequence flag in the neighbour's memory; the receiver polls its own

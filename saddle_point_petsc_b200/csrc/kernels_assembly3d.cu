@@ -364,6 +364,7 @@ std::shared_ptr<Csr> build_box_matrix3(const Dmda3 &da, const ElemBox3 &eb, int 
   A->tag = tag;
   if (da.halo) { A->halo = da.halo; A->halo_dof = dofc; A->row_gstart = da.g0 * dofr; A->col_gstart = da.g0 * dofc; }
   A->plan();
+  if (dofr * dofc > 1) csr_try_block_index(*A, dofr, dofc); // 3 x 3 / 3 x 1 / 1 x 3 node blocks -> warp-per-node SpMV
   return A;
 }
 

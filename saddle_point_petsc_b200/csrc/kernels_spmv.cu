@@ -81,6 +81,46 @@ __global__ void __launch_bounds__(256) k_spmv_vector(int nrows, const int *__res
   }
 }
 
+// One WARP per block row (node) of a matrix with dense BR x BC node blocks and long rows (3-D: 27 blocks, 81 nonzeros per
+// row of A): lane b owns block b, loads its BC entries of x ONCE for the BR rows of the node and one block-column id
+// instead of BR*BC column ids (8 + 4/(BR*BC) bytes per nonzero instead of 12), keeps BR*BC + BC independent loads in
+// flight, and the BR row sums are reduced with a fixed shuffle tree.
+template <int BR, int BC>
+__global__ void __launch_bounds__(256) k_spmv_nodeblk(int nbrows, const int *__restrict__ rowptr, const int *__restrict__ bptr, const int *__restrict__ bcol,
+                                                      const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi) {
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  for (int I = blockIdx.x * wpc + (threadIdx.x >> 5); I < nbrows; I += gridDim.x * wpc) {
+    const int b0 = bptr[I], nb = bptr[I + 1] - b0;
+    int rs[BR];
+    double sum[BR];
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr) { rs[rr] = rowptr[I * BR + rr]; sum[rr] = 0.0; }
+    for (int b = lane; b < nb; b += 32) {
+      const int c0 = ld_stream_s32(bcol + b0 + b) * BC;
+      double xv[BC], av[BR][BC];
+#pragma unroll
+      for (int cc = 0; cc < BC; ++cc) xv[cc] = xs.load(c0 + cc);
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < BC; ++cc) av[rr][cc] = ld_stream_f64(val + rs[rr] + b * BC + cc);
+#pragma unroll
+      for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < BC; ++cc) sum[rr] += av[rr][cc] * xv[cc];
+    }
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr) sum[rr] = warp_sum(sum[rr]);
+    if (lane < BR) {
+      double s = sum[0];
+#pragma unroll
+      for (int rr = 1; rr < BR; ++rr)
+        if (lane == rr) s = sum[rr];
+      y[I * BR + lane] = epi.apply(s, I * BR + lane);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_spmv_block(int nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
                                                     const double *__restrict__ val, XSrc xs, double *y, SpmvEpi epi) {
   __shared__ double s_w[8];
@@ -265,6 +305,15 @@ static bool csr_spmv_launch(const Csr &A, const double *x, double *y, SpmvEpi &e
     if (grid > c->num_sms * per_sm) grid = c->num_sms * per_sm;
     k_spmv_stream<<<grid, 256, smem, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, xs, y, epi, tile);
     check_launch("k_spmv_stream");
+  } else if (A.kernel == SPMV_NODE && A.bcol.p) {
+    const int nb = A.nrows / A.blk_r;
+    int grid = (nb + 7) / 8;
+    if (grid > c->num_sms * 8) grid = c->num_sms * 8;
+    if (A.blk_r == 3 && A.blk_c == 3) k_spmv_nodeblk<3, 3><<<grid, 256, 0, c->stream>>>(nb, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi);
+    else if (A.blk_r == 3 && A.blk_c == 1) k_spmv_nodeblk<3, 1><<<grid, 256, 0, c->stream>>>(nb, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi);
+    else if (A.blk_r == 1 && A.blk_c == 3) k_spmv_nodeblk<1, 3><<<grid, 256, 0, c->stream>>>(nb, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi);
+    else throw Error(B200SP_ERR_UNSUPPORTED, "node-block SpMV: unsupported block shape");
+    check_launch("k_spmv_nodeblk");
   } else if (A.kernel == SPMV_BLOCK) {
     int grid = A.nrows < c->num_sms * 8 ? A.nrows : c->num_sms * 8;
     k_spmv_block<<<grid, 256, 0, c->stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, xs, y, epi);

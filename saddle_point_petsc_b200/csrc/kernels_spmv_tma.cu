@@ -585,7 +585,17 @@ bool build_block_index(Csr &A) {
 
 bool csr_try_block_index(Csr &A, int br, int bc) {
   static const bool off = getenv("B200SP_NO_BLOCK_INDEX") && atoi(getenv("B200SP_NO_BLOCK_INDEX"));
-  if (off || A.kernel != SPMV_TMA) return false;
+  if (off) return false;
+  if (br * bc >= 3 && (br == 3 || bc == 3) && br * bc != 6) { // 3-D node blocks: warp-per-node kernel (kernels_spmv.cu k_spmv_nodeblk)
+    if (A.kernel == SPMV_TMA) return false; // short rows (B^T: 27 per row): the TMA thread-per-row kernel is faster (0.62 vs 0.70 ms at 8.6M DOF)
+    bool ok = false;
+    if (br == 3 && bc == 3) ok = build_block_index<3, 3>(A);
+    else if (br == 3 && bc == 1) ok = build_block_index<3, 1>(A);
+    else if (br == 1 && bc == 3) ok = build_block_index<1, 3>(A);
+    if (ok) A.kernel = SPMV_NODE;
+    return ok;
+  }
+  if (A.kernel != SPMV_TMA) return false;
   if (br == 2 && bc == 2) return build_block_index<2, 2>(A);
   if (br == 1 && bc == 2) return build_block_index<1, 2>(A);
   if (br == 2 && bc == 1) return build_block_index<2, 1>(A);

@@ -110,3 +110,69 @@ def test_3d_kkt_solve_parity(ctx, name, opts):
         assert np.max(np.abs(dp - dp.mean())) <= 1e-8 * np.max(np.abs(ro["x"][nu:]))
     K = orc.scipy_K()
     assert np.linalg.norm(orc.rhs - K @ xs) / np.linalg.norm(orc.rhs) < 5e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,n", [(2, (8, 7, 9)), (4, (10, 9, 8)), (8, (11, 10, 9))])
+def test_3d_row_partitioned_assembly_spmv_and_solve(size, n):
+    """3-D DMDA partition (PETSC_DECIDE process grid, rank-contiguous numbering, ghost layer through the general halo): every
+    rank's rows equal the oracle's rows (values bit for bit), distributed MatMult, and the MINRES solve of config 4."""
+    import scipy.sparse as sps
+    import saddle_point_petsc_b200 as sp
+    orc = so.Problem3D(*n)
+    M, N, P = orc.M, orc.N, orc.P
+    ro = so.Solver(orc, OPTS_MINRES).solve()
+    rng = np.random.default_rng(7)
+    xg = {1: rng.uniform(-1, 1, M * N * P), 3: rng.uniform(-1, 1, 3 * M * N * P)}
+    blocks = {"A": (3, 3), "Bt": (3, 1), "B": (1, 3), "C": (1, 1)}
+
+    def rank_fn(ctx):
+        prob = sp.SaddlePointProblem3D(ctx, *n)
+        da = prob.da
+        # natural ids of my owned nodes, in local order (x fastest, then y, then z)
+        kk, jj, ii = np.meshgrid(np.arange(da.zs, da.zs + da.zm), np.arange(da.ys, da.ys + da.ym), np.arange(da.xs, da.xs + da.xm), indexing="ij")
+        nat = ((kk * N + jj) * M + ii).ravel()
+        out = {"nat": nat, "g0": da.gstart}
+        for name, (dr, dc) in blocks.items():
+            m = getattr(prob, name)
+            x = sp.Vec.from_numpy(ctx, xg[dc].reshape(-1, dc)[nat].ravel())
+            y = sp.Vec(ctx, len(nat) * dr)
+            m.mult(x, y)
+            out["y" + name] = y.numpy()
+            out["csr" + name] = m.csr()          # local rows, GLOBAL (PETSc numbering) columns
+        ksp = prob.make_ksp(OPTS_MINRES)
+        x = sp.Vec(ctx, prob.n)
+        r = ksp.solve(prob.rhs, x)
+        out["its"], out["reason"], out["x"] = r["its"], r["reason"], x.numpy()
+        out["rhs"] = prob.rhs.numpy()
+        return out
+
+    res = sp.run_ranks(size, rank_fn)
+    petsc_of_nat = np.zeros(M * N * P, dtype=np.int64)                     # natural node -> PETSc global node
+    for o in res:
+        petsc_of_nat[o["nat"]] = o["g0"] + np.arange(len(o["nat"]))
+    nat_of_petsc = np.argsort(petsc_of_nat)
+    for o in res:
+        nat = o["nat"]
+        for name, (dr, dc) in blocks.items():
+            ref = getattr(orc, name).scipy()
+            rows = (nat[:, None] * dr + np.arange(dr)).ravel()
+            yr = (ref @ xg[dc])[rows]
+            assert np.max(np.abs(o["y" + name] - yr)) <= 1e-14 * max(1.0, np.max(np.abs(yr))), name
+            rp, col, val = o["csr" + name]
+            mine = sps.csr_matrix((val, col, rp), shape=(len(rows), dc * M * N * P)).tocoo()
+            natcol = nat_of_petsc[mine.col // dc] * dc + mine.col % dc     # back to natural columns
+            got = sps.csr_matrix((mine.data, (mine.row, natcol)), shape=mine.shape)
+            got.sort_indices()
+            R = ref[rows]
+            assert np.array_equal(got.indptr, R.indptr) and np.array_equal(got.indices, R.indices), name
+            assert same_bits(got.data, R.data), name
+        assert same_bits(o["rhs"][:3 * len(nat)], orc.f.reshape(-1, 3)[nat].ravel())
+    assert len({o["its"] for o in res}) == 1 and all(o["reason"] == 2 for o in res)
+    assert abs(res[0]["its"] - ro["its"]) <= 1, (res[0]["its"], ro["its"])
+    if res[0]["its"] == ro["its"]:
+        umax = np.max(np.abs(ro["x"][:orc.nu]))
+        for o in res:
+            nat = o["nat"]
+            xu = ro["x"][:orc.nu].reshape(-1, 3)[nat].ravel()
+            assert np.max(np.abs(o["x"][:3 * len(nat)] - xu)) <= 1e-8 * umax
