@@ -97,7 +97,7 @@ int b200sp_dmda_global_node(int M, int N, int size, int i, int j, int *gnode, in
 int b200sp_dmda_halo_plan(int M, int N, int size, int rank, int *nghost, int *ghost_gnode, int *ghost_owner,
                           int *nsend_total, int *send_rank, int *send_lnode);
 /* [host-only] the node-keyed view of the same send lists, used when the kernel that PRODUCES a vector pushes its
- * boundary values to the neighbours itself: node_ent[v] = (first entry << 2) | count for owned local node v (0 = not
+ * boundary values to the neighbours itself: node_ent[v] = (first entry << 3) | count (<= 7) for owned local node v (0 = not
  * sent, count <= 3); entry e goes to rank entry_rank[e] at position entry_pos[e] of that neighbour's receive range
  * (entry 0 is unused).  Call with NULL arrays to query n_owned / n_entries. */
 int b200sp_dmda_halo_push_table(int M, int N, int size, int rank, int *n_owned, int *node_ent, int *n_entries, int *entry_rank, int *entry_pos);

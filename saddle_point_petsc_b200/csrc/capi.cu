@@ -259,7 +259,7 @@ int b200sp_dmda_halo_push_table(int M, int N, int size, int rank, int *n_owned, 
   Layout L(M, N, size);
   B2_REQUIRE(rank >= 0 && rank < size, "bad rank");
   const HaloPlan P = plan_halo(L, rank);
-  B2_REQUIRE(P.push_valid, "halo push table: a node goes to more than 3 neighbours (boxes thinner than 2 nodes)");
+  B2_REQUIRE(P.push_valid, "halo push table: a node goes to more than 7 neighbours (boxes thinner than 2 nodes)");
   if (n_owned) *n_owned = P.n_owned;
   if (node_ent) std::copy(P.push_node_ent.begin(), P.push_node_ent.begin() + P.n_owned, node_ent);
   if (n_entries) *n_entries = (int)P.push_ent_msg.size();

@@ -288,7 +288,7 @@ struct XSrc {
 struct HaloP2PMsg { double *peer_ghost; unsigned long long *peer_flag; long long peer_stride; int send_off, send_cnt, peer_recv_off, pad; };
 struct PushOut {
   const unsigned char *grp = nullptr; // per 64 owned nodes: does any of them go to a neighbour?  (null: no push)
-  const int *node_ent = nullptr;      // per owned node: (first entry << 2) | number of entries (<= 3), 0 = none
+  const int *node_ent = nullptr;      // per owned node: (first entry << 3) | number of entries (<= 7: a corner node of a 3-D box has 7 neighbours), 0 = none
   const int2 *ents = nullptr;         // {message, position of the node inside that message}
   const HaloP2PMsg *msgs = nullptr;
   unsigned long long *seq = nullptr;
@@ -301,8 +301,8 @@ struct PushOut {
     const int e = node_ent[node];
     if (!e) return;
     const unsigned long long par = *seq & 1ull;
-    for (int k = 0; k < (e & 3); ++k) {
-      const int2 t = ents[(e >> 2) + k];
+    for (int k = 0; k < (e & 7); ++k) {
+      const int2 t = ents[(e >> 3) + k];
       const HaloP2PMsg &g = msgs[t.x];
       g.peer_ghost[par * g.peer_stride + (long long)(g.peer_recv_off + t.y) * dof + c] = v;
     }
@@ -312,8 +312,8 @@ struct PushOut {
     const int e = node_ent[node];
     if (!e) return;
     const unsigned long long par = *seq & 1ull;
-    for (int k = 0; k < (e & 3); ++k) {
-      const int2 t = ents[(e >> 2) + k];
+    for (int k = 0; k < (e & 7); ++k) {
+      const int2 t = ents[(e >> 3) + k];
       const HaloP2PMsg &g = msgs[t.x];
       *reinterpret_cast<double2 *>(g.peer_ghost + par * g.peer_stride + (long long)(g.peer_recv_off + t.y) * 2) = make_double2(v0, v1);
     }

@@ -466,7 +466,7 @@ static void build_push_tables(HaloPlan &P) {
     for (int64_t k = 0; k < m.send_cnt; ++k) cnt[(size_t)P.send_lnode[(size_t)(m.send_off + k)]]++;
   int total = 1; // entry 0 is never used so that "0" can mean "none"
   for (int v = 0; v < n; ++v) {
-    if (cnt[(size_t)v] > 3) P.push_valid = false; // boxes thinner than 2 nodes: the 2-bit count cannot hold it (no fused push, no peer-to-peer)
+    if (cnt[(size_t)v] > 7) P.push_valid = false; // more destinations than the 3-bit count holds (boxes thinner than 2 nodes): no fused push, no peer-to-peer
     first[(size_t)v] = total;
     total += cnt[(size_t)v];
   }
@@ -480,7 +480,7 @@ static void build_push_tables(HaloPlan &P) {
       P.push_ent_pos[(size_t)e] = (int)k;
     }
   for (int v = 0; v < n; ++v)
-    if (cnt[(size_t)v] && P.push_valid) { P.push_node_ent[(size_t)v] = (first[(size_t)v] << 2) | cnt[(size_t)v]; P.push_grp[(size_t)(v >> 6)] = 1; }
+    if (cnt[(size_t)v] && P.push_valid) { P.push_node_ent[(size_t)v] = (first[(size_t)v] << 3) | cnt[(size_t)v]; P.push_grp[(size_t)(v >> 6)] = 1; }
 }
 
 HaloPlan plan_halo(const Layout &L, int rank) {

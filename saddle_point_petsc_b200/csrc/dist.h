@@ -89,7 +89,7 @@ struct HaloPlan {
   std::vector<int> send_lnode;    // owned local node ids to send, grouped by message, in the receiver's ghost order
   // node-keyed view of the send lists (pushes fused into producing kernels, PushOut in core.h)
   std::vector<unsigned char> push_grp; // per 64 owned nodes: any of them sent?
-  std::vector<int> push_node_ent;      // per owned node: (first entry << 2) | count (<= 3); 0 = not sent
+  std::vector<int> push_node_ent;      // per owned node: (first entry << 3) | count (<= 7); 0 = not sent
   std::vector<int> push_ent_msg, push_ent_pos; // entry -> message index, position inside that message; entry 0 unused
   bool push_valid = true;              // false when some node has more than 3 destinations (boxes thinner than 2 nodes)
 };

@@ -93,7 +93,7 @@ def test_halo_push_table_is_the_send_list_keyed_by_node(M, N, size):
                 want[(int(v), int(q))] = pos
         got = {}
         for v, e in enumerate(tab["node_ent"]):
-            first, cnt = int(e) >> 2, int(e) & 3
+            first, cnt = int(e) >> 3, int(e) & 7
             assert (e == 0) == (cnt == 0)
             for k in range(cnt):
                 key = (v, int(tab["entry_rank"][first + k]))

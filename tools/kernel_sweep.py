@@ -43,7 +43,8 @@ def time_ms(ctx, fn, reps=20, warm=3):
     return ctx.timer_stop() / reps
 
 
-def sweep_point(sp, ctx, nx, pk, reduce_max, reduce_sum):
+def sweep_point(sp, ctx, nx, pk1, reduce_max, reduce_sum):
+    pk = pk1 * max(ctx.size, 1)          # whole-job figures against the aggregate peak of the N GPUs
     prob = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
     row = {"nx": nx, "dof": int(reduce_sum(prob.n)), "spmv": {}, "vec": {}}
     for name in ("A", "Bt", "B", "C"):
