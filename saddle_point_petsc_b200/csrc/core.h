@@ -194,7 +194,9 @@ struct Csr {
   // by the first SpMV (state 0 = not tried, 1 = in use, -1 = declined), dropped when values change
   mutable DevBuf<unsigned char> pd_blob;
   mutable DevBuf<int> pd_off;                 // blob offsets per tile, in 16-byte units
-  mutable int dict_state = 0, pd_cap = 0, dict_rows = 0; // pd_cap: largest blob (bytes); dict_rows: rows per tile
+  mutable DevBuf<int> pd_gstart, pd_goff;     // first tile / blob offset (16-byte units) of every group of consecutive tiles (one group per pipeline stage)
+  mutable std::vector<int> h_pd_gstart;
+  mutable int dict_state = 0, pd_cap = 0, pd_ngroups = 0, dict_rows = 0; // pd_cap: largest group (bytes); dict_rows: rows per tile
   mutable int64_t dict_bytes = 0;
   bool no_value_dict = false;                 // b200sp_mat_set_spmv_format: keep the plain value stream
   // tile order for kernels that wait for the halo themselves: tiles (of wait_order_rows rows) without ghost columns first

@@ -258,16 +258,21 @@ constexpr int PD_MAX_K = 16;       // blocks per block row
 constexpr int PD_MAX_DICT = 2048;  // (position, value) pairs per tile
 
 __host__ __device__ inline int pd_pad16(int bytes) { return (bytes + 15) & ~15; }
-struct PdLayout { int nbmax, npat, ndict, o_dict, o_pat, o_pos, o_pid, o_codes, bytes; };
+// rel: what the pattern's block-column offsets are relative to.  0: the block row index itself (square stencil matrices:
+// one pattern per tile); 1: the row's FIRST block column, stored explicitly per row (+4 bytes per row) -- for rectangular
+// operators whose columns move at another rate than the rows (interpolation / restriction: 4 resp. 1 patterns per tile
+// instead of 128).
+struct PdLayout { int nbmax, npat, ndict, rel, o_dict, o_pat, o_pos, o_pid, o_base, o_codes, bytes; };
 template <int BR, int BC>
-__host__ __device__ inline PdLayout pd_layout(int nbmax, int npat, int ndict) {
+__host__ __device__ inline PdLayout pd_layout(int nbmax, int npat, int ndict, int rel) {
   PdLayout L;
-  L.nbmax = nbmax; L.npat = npat; L.ndict = ndict;
+  L.nbmax = nbmax; L.npat = npat; L.ndict = ndict; L.rel = rel;
   L.o_dict = 16;
   L.o_pat = L.o_dict + pd_pad16(ndict * 8);
   L.o_pos = L.o_pat + pd_pad16(npat * (nbmax + 1) * 4);
   L.o_pid = L.o_pos + pd_pad16(nbmax * BR * BC * 2);
-  L.o_codes = L.o_pid + PD_NB;
+  L.o_base = L.o_pid + PD_NB;
+  L.o_codes = L.o_base + (rel ? PD_NB * 4 : 0);
   L.bytes = L.o_codes + nbmax * PD_NB * BR * BC;
   return L;
 }
@@ -275,16 +280,20 @@ __host__ __device__ inline PdLayout pd_layout(int nbmax, int npat, int ndict) {
 // One thread per BLOCK ROW (node): one x load (16 bytes when BC = 2) serves BR x BC nonzeros; each row accumulates its
 // own entries in CSR order (block k ascending, then column).  One bulk copy per tile, two stages per CTA.
 template <int BR, int BC, int UB>
-__global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const int *__restrict__ order, const int *__restrict__ toff,
+__global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, const int *__restrict__ gstart, int ntiles, const int *__restrict__ order, const int *__restrict__ toff,
                                                    const unsigned char *__restrict__ blob, XSrc xs, double *y, SpmvEpi epi, int cap, int stages,
                                                    int n_nowait) {
+  // A stage holds a GROUP of G consecutive tiles (their blobs are contiguous in memory: one bulk copy): matrices with short
+  // rows have blobs of 1-4 KB, and one tile per stage left the kernel bound by the turn-around latency of the copies.
+  // `ntiles` counts groups; group g covers tiles [gstart[g], gstart[g+1]) -- formed on the host by bytes (~8 KB), so that one
+  // unusually large tile (domain boundary, ghost columns) does not inflate the stage size of every CTA.
   extern __shared__ __align__(128) unsigned char s_raw[];
   constexpr int BRBC = BR * BC;
   uint64_t *full = reinterpret_cast<uint64_t *>(s_raw + (size_t)cap * stages);
   const int tid = threadIdx.x;
   auto issue = [&](int idx, int stage) { // one thread
-    const int tile = order ? order[idx] : idx;
-    const long long o0 = toff[tile], o1 = toff[tile + 1];
+    const int grp = order ? order[idx] : idx;
+    const long long o0 = toff[grp], o1 = toff[grp + 1]; // toff: blob offset of every GROUP (16-byte units)
     const unsigned bytes = (unsigned)(o1 - o0) * 16u;
     mbar_expect_tx(&full[stage], bytes);
     if (bytes) bulk_g2s(s_raw + (size_t)cap * stage, blob + o0 * 16, bytes, &full[stage]);
@@ -303,16 +312,19 @@ __global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const
   bool waited = xs.wait_flags == nullptr; // tiles before n_nowait read no ghost column: the wait is deferred until the first one that does
   int it = 0;
   for (int idx = blockIdx.x; idx < ntiles; idx += gridDim.x, ++it) {
-    const int tile = order ? order[idx] : idx;
+    const int grp = order ? order[idx] : idx;
     if (!waited && idx >= n_nowait) { halo_wait_cta(xs); waited = true; }
     const int stage = it % stages;
     const unsigned parity = (unsigned)(it / stages) & 1u;
-    const int I = tile * PD_NB + tid;
     mbar_wait(&full[stage], parity);
     const unsigned char *base = s_raw + (size_t)cap * stage;
-    if (I < nbrows) {
-      const int4 hdr = *reinterpret_cast<const int4 *>(base);
-      const PdLayout L = pd_layout<BR, BC>(hdr.x, hdr.y, hdr.z);
+    const int t_end = gstart[grp + 1];
+    for (int tile = gstart[grp]; tile < t_end; ++tile) {
+     const int I = tile * PD_NB + tid;
+     const int4 hdr = *reinterpret_cast<const int4 *>(base);
+     if (I < nbrows) {
+      const PdLayout L = pd_layout<BR, BC>(hdr.x, hdr.y, hdr.z, hdr.w);
+      const int cbase = hdr.w ? reinterpret_cast<const int *>(base + L.o_base)[tid] : I; // what the pattern offsets are relative to
       const double *sd = reinterpret_cast<const double *>(base + L.o_dict);
       const int *sp = reinterpret_cast<const int *>(base + L.o_pat) + (int)base[L.o_pid + tid] * (L.nbmax + 1);
       const unsigned short *spos = reinterpret_cast<const unsigned short *>(base + L.o_pos);
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const
       const int nb = sp[0];
       // values of block k of this thread's rows and the x entries they multiply
       auto fetch = [&](int k, double (&av)[BR][BC], double (&xv)[BC]) {
-        const int c0 = (I + sp[1 + k]) * BC;
+        const int c0 = (cbase + sp[1 + k]) * BC;
         if (BC == 2) {
           const double2 x2 = xs.load2(c0);
           xv[0] = x2.x; xv[BC - 1] = x2.y;
@@ -387,6 +399,8 @@ __global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const
           if (epi.push.grp) epi.push.row(I * BR + rr, v);
         }
       }
+     }
+     base += pd_layout<BR, BC>(hdr.x, hdr.y, hdr.z, hdr.w).bytes; // the next tile of the group follows immediately
     }
     __syncthreads();
     if (tid == 0) {
@@ -403,14 +417,14 @@ __global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, int ntiles, const
 // k_blk_check when BR*BC > 1.
 template <int BR, int BC>
 __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-                                                  int write, int *tsize16, const int *__restrict__ toff, unsigned char *blob, int *stat) {
+                                                  int write, int rel, int *tsize16, const int *__restrict__ toff, unsigned char *blob, int *stat) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr int BRBC = BR * BC, PMAX = PD_MAX_K * BRBC;
   int *s_delta = reinterpret_cast<int *>(s_raw);                                                   // [PD_NB][PD_MAX_K + 1]: nb, offsets
   unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_delta + PD_NB * (PD_MAX_K + 1)); // [PMAX][PD_NB] value bits
   unsigned char *s_first = reinterpret_cast<unsigned char *>(s_val + (size_t)PMAX * PD_NB);         // [PMAX][PD_NB] first row with this value
   unsigned char *s_rank = s_first + (size_t)PMAX * PD_NB;                                          // [PMAX][PD_NB] rank of a first occurrence
-  __shared__ int s_pfirst[PD_NB], s_prank[PD_NB], s_cnt[PMAX], s_posoff[PMAX + 1], s_w[4];
+  __shared__ int s_pfirst[PD_NB], s_prank[PD_NB], s_cnt[PMAX], s_posoff[PMAX + 1], s_w[4], s_base[PD_NB];
   __shared__ int s_nbmax, s_bad, s_npat;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
   const int I0 = tile * PD_NB;
@@ -423,7 +437,11 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
       const int rs = rowptr[I * BR];
       nb = (rowptr[I * BR + 1] - rs) / BC;
       if (nb > PD_MAX_K) { s_bad = 1; nb = 0; }
-      for (int k = 0; k < nb; ++k) s_delta[tid * (PD_MAX_K + 1) + 1 + k] = col[rs + k * BC] / BC - I;
+      const int ref = rel ? (nb > 0 ? col[rs] / BC : 0) : I;
+      s_base[tid] = ref;
+      for (int k = 0; k < nb; ++k) s_delta[tid * (PD_MAX_K + 1) + 1 + k] = col[rs + k * BC] / BC - ref;
+    } else {
+      s_base[tid] = 0;
     }
     s_delta[tid * (PD_MAX_K + 1)] = nb;
     atomicMax(&s_nbmax, nb);
@@ -504,13 +522,14 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
     if (tid == 0) { stat[0] = 1; if (!write) tsize16[tile] = 0; }
     return;
   }
-  const PdLayout L = pd_layout<BR, BC>(nbmax, npat, ndict);
+  const PdLayout L = pd_layout<BR, BC>(nbmax, npat, ndict, rel);
   if (!write) {
     if (tid == 0) { tsize16[tile] = L.bytes / 16; atomicMax(&stat[1], L.bytes); }
     return;
   }
   unsigned char *out = blob + (size_t)toff[tile] * 16; // zero-filled by the caller: padding stays zero
-  if (tid == 0) { int *h = reinterpret_cast<int *>(out); h[0] = nbmax; h[1] = npat; h[2] = ndict; h[3] = 0; }
+  if (tid == 0) { int *h = reinterpret_cast<int *>(out); h[0] = nbmax; h[1] = npat; h[2] = ndict; h[3] = rel; }
+  if (rel && tid < PD_NB) reinterpret_cast<int *>(out + L.o_base)[tid] = s_base[tid];
   double *dict = reinterpret_cast<double *>(out + L.o_dict);
   int *pat = reinterpret_cast<int *>(out + L.o_pat);
   unsigned short *pos = reinterpret_cast<unsigned short *>(out + L.o_pos);
@@ -639,9 +658,42 @@ static void ensure_wait_order(const Csr &A, int T) {
   A.wait_order_rows = T;
 }
 
+// the same ordering for the pd kernel's GROUPS of tiles (variable size): a group waits if any of its tiles has a ghost column.
+// Cached as wait_order_rows = -T so that it is not confused with the fixed-size tile order of the other kernels.
+static void ensure_wait_order_groups(const Csr &A, int T) {
+  static const bool off = getenv("B200SP_NO_DEFER_WAIT") && atoi(getenv("B200SP_NO_DEFER_WAIT"));
+  if (off || A.wait_order_rows == -T || A.nrows <= 0 || A.h_pd_gstart.empty()) return;
+  Ctx *c = A.ctx;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  B2_CUDA(cudaStreamIsCapturing(c->stream, &st));
+  if (st != cudaStreamCaptureStatusNone) return;
+  const int ntiles = (A.nrows + T - 1) / T, ng = (int)A.h_pd_gstart.size() - 1;
+  DevBuf<int> flag((size_t)ntiles + 1);
+  flag.zero(c->stream);
+  {
+    LaunchScope ls(c, "setup");
+    k_tile_ghost_flag<<<std::max(1, std::min((A.nrows + 255) / 256, c->num_sms * 16)), 256, 0, c->stream>>>(A.nrows, T, A.ncols, A.rowptr.p, A.col.p, flag.p);
+    check_launch("k_tile_ghost_flag");
+  }
+  std::vector<int> hf((size_t)ntiles), order;
+  B2_CUDA(cudaMemcpyAsync(hf.data(), flag.p, sizeof(int) * (size_t)ntiles, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  std::vector<char> gf((size_t)ng, 0);
+  for (int g = 0; g < ng; ++g)
+    for (int t = A.h_pd_gstart[(size_t)g]; t < A.h_pd_gstart[(size_t)g + 1] && t < ntiles; ++t) gf[(size_t)g] |= (char)(hf[(size_t)t] != 0);
+  order.reserve((size_t)ng);
+  for (int g = 0; g < ng; ++g) if (!gf[(size_t)g]) order.push_back(g);
+  A.wait_n_nowait = (int)order.size();
+  for (int g = 0; g < ng; ++g) if (gf[(size_t)g]) order.push_back(g);
+  A.wait_order.alloc((size_t)ng + 1);
+  B2_CUDA(cudaMemcpyAsync(A.wait_order.p, order.data(), sizeof(int) * (size_t)ng, cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  A.wait_order_rows = -T;
+}
+
 // build (or decline) the tile-local pattern/value dictionaries of A; called lazily from the first un-captured TMA SpMV
 template <int BR, int BC>
-static void build_pd(const Csr &A, int force) {
+static bool build_pd_mode(const Csr &A, int force, int rel, bool only_if_small) {
   Ctx *c = A.ctx;
   const int nbrows = A.nrows / BR, ntiles = (nbrows + PD_NB - 1) / PD_NB;
   DevBuf<int> tsize((size_t)ntiles + 1), stat(2);
@@ -650,26 +702,66 @@ static void build_pd(const Csr &A, int force) {
   const size_t smem = (size_t)PD_NB * (PD_MAX_K + 1) * 4 + (size_t)PMAX * PD_NB * 10;
   // (the attribute is per device and this kernel has four instantiations: set it on every build, setup path only)
   B2_CUDA(cudaFuncSetAttribute(k_pd_build<BR, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 0, tsize.p, nullptr, nullptr, stat.p); check_launch("k_pd_build"); }
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 0, rel, tsize.p, nullptr, nullptr, stat.p); check_launch("k_pd_build"); }
   int h_stat[2] = {0, 0};
   B2_CUDA(cudaMemcpyAsync(h_stat, stat.p, sizeof(h_stat), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
-  if (h_stat[0]) return; // a row with more than PD_MAX_K blocks, or a tile with too many distinct values
-  A.pd_off.alloc((size_t)ntiles + 1);
+  if (h_stat[0]) return false; // a row with more than PD_MAX_K blocks, or a tile with too many distinct values
+  DevBuf<int> off((size_t)ntiles + 1);
   int total16 = 0;
-  exclusive_scan_i32(c, tsize.p, A.pd_off.p, ntiles, &total16);
+  exclusive_scan_i32(c, tsize.p, off.p, ntiles, &total16);
   const double total = 16.0 * (double)total16;
   // worth it only if the blobs are clearly smaller than what the plain kernels stream (values + (block) column index)
   const double alt = 8.0 * (double)A.nnz + 4.0 * (double)A.nnz / (double)(BR * BC);
-  if (force < 2 && total > 0.6 * alt) { A.pd_off.release(); return; }
+  if (force < 2 && total > 0.6 * alt) return false;
+  if (only_if_small && total > 0.25 * alt) return false; // the caller has a second mode to try: accept only a clear win
+  A.pd_off = std::move(off);
   A.pd_blob.alloc((size_t)total16 * 16 + 256);
   A.pd_blob.zero(c->stream);
-  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 1, nullptr, A.pd_off.p, A.pd_blob.p, stat.p); check_launch("k_pd_build"); }
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 1, rel, nullptr, A.pd_off.p, A.pd_blob.p, stat.p); check_launch("k_pd_build"); }
   c->sync();
-  A.pd_cap = (h_stat[1] + 127) & ~127;
+  { // groups of consecutive tiles, ~8 KB of blobs and at most 8 tiles each (measured: profiles/r02_pd_group_sweep.txt);
+    // the stage capacity is the largest group
+    std::vector<int> h_off((size_t)ntiles + 1), gs;
+    B2_CUDA(cudaMemcpyAsync(h_off.data(), A.pd_off.p, sizeof(int) * ((size_t)ntiles + 1), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    static const int env_g = getenv("B200SP_PD_GROUP") ? atoi(getenv("B200SP_PD_GROUP")) : 0;       // fixed tiles per group
+    static const int env_kb = getenv("B200SP_PD_GROUP_KB") ? atoi(getenv("B200SP_PD_GROUP_KB")) : 0; // byte target
+    const int64_t target = env_kb > 0 ? (int64_t)env_kb * 1024 : 12288;
+    int64_t capg = 0;
+    for (int t = 0; t < ntiles;) {
+      gs.push_back(t);
+      int e = t + 1;
+      if (env_g > 0) e = std::min(t + env_g, ntiles);
+      else while (e < ntiles && e - t < 8 && 16LL * (h_off[(size_t)e + 1] - h_off[(size_t)t]) <= target) ++e;
+      capg = std::max<int64_t>(capg, 16LL * (h_off[(size_t)e] - h_off[(size_t)t]));
+      t = e;
+    }
+    gs.push_back(ntiles);
+    A.pd_ngroups = (int)gs.size() - 1;
+    A.pd_gstart.alloc(gs.size() + 1);
+    A.pd_goff.alloc(gs.size() + 1);
+    std::vector<int> go(gs.size());
+    for (size_t g = 0; g < gs.size(); ++g) go[g] = h_off[(size_t)gs[g]];
+    B2_CUDA(cudaMemcpyAsync(A.pd_gstart.p, gs.data(), sizeof(int) * gs.size(), cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(A.pd_goff.p, go.data(), sizeof(int) * go.size(), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+    A.h_pd_gstart = gs;
+    A.pd_cap = (int)((capg + 127) & ~127LL);
+  }
   A.dict_rows = PD_NB * BR;
   A.dict_bytes = (int64_t)total16 * 16 + 4 * (int64_t)(ntiles + 1);
   A.dict_state = 1;
+  return true;
+}
+// build (or decline) the tile-local pattern/value dictionaries of A; called lazily from the first un-captured TMA SpMV.
+// Column patterns relative to the block row (square stencil operators) are tried first; rectangular operators whose
+// patterns do not repeat that way (interpolation, restriction) get the explicit-first-column mode.
+template <int BR, int BC>
+static void build_pd(const Csr &A, int force) {
+  if (A.nrows == A.ncols * BR / BC && build_pd_mode<BR, BC>(A, force, 0, false)) return; // same node space for rows and columns
+  if (build_pd_mode<BR, BC>(A, force, 1, false)) return;
+  if (A.nrows != A.ncols * BR / BC) build_pd_mode<BR, BC>(A, force, 0, false);
 }
 static void build_value_dict(const Csr &A) {
   static const bool off = getenv("B200SP_NO_VALUE_DICT") && atoi(getenv("B200SP_NO_VALUE_DICT"));
@@ -684,7 +776,9 @@ static void build_value_dict(const Csr &A) {
 }
 void csr_drop_value_dict(Csr &A) {
   A.pd_blob.release(); A.pd_off.release();
+  A.pd_gstart.release(); A.pd_goff.release(); A.h_pd_gstart.clear(); A.pd_ngroups = 0;
   A.dict_state = 0; A.pd_cap = 0; A.dict_rows = 0; A.dict_bytes = 0;
+  if (A.wait_order_rows < 0) A.wait_order_rows = 0; // the group order belongs to the dropped format
 }
 
 // returns false when the matrix does not fit the shared-memory tiling (caller falls back)
@@ -741,7 +835,9 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   }
   const int dbr = A.bcol.p ? A.blk_r : 1, dbc = A.bcol.p ? A.blk_c : 1;
   if (A.dict_state == 1 && !tile_list && (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // tile-local dictionaries, one thread per block row
-    const size_t smem_d = (size_t)A.pd_cap * 2 + 8 * TMA_MAX_STAGES;
+    static const int env_st = getenv("B200SP_PD_STAGES") ? atoi(getenv("B200SP_PD_STAGES")) : 0;
+    const int pd_stages = env_st >= 2 && env_st <= TMA_MAX_STAGES ? env_st : 2;
+    const size_t smem_d = (size_t)A.pd_cap * pd_stages + 8 * TMA_MAX_STAGES;
     if (!(c->attr_mask & 8u)) {
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -753,16 +849,16 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     static const int env_psm = getenv("B200SP_TMA_CTAS") ? atoi(getenv("B200SP_TMA_CTAS")) : 0;
     if (env_psm && env_psm < psm) psm = env_psm;
     const int nbrows = A.nrows / dbr;
-    const int ntd = (nbrows + PD_NB - 1) / PD_NB;
+    const int ntd = A.pd_ngroups; // groups of consecutive tiles
     const int gridd = ntd < c->num_sms * psm ? ntd : c->num_sms * psm;
     const int *order = nullptr;
     int n_nowait = 0;
-    if (xs.wait_flags) { ensure_wait_order(A, PD_NB * dbr); if (A.wait_order_rows == PD_NB * dbr) { order = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
+    if (xs.wait_flags) { ensure_wait_order_groups(A, PD_NB * dbr); if (A.wait_order_rows == -(PD_NB * dbr)) { order = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
     auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     SpmvEpi e2 = epi;
     e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
 #define B200SP_PD_LAUNCH(BR_, BC_, UB_) \
-  k_spmv_pd<BR_, BC_, UB_><<<gridd, PD_NB, smem_d, c->stream>>>(nbrows, ntd, order, A.pd_off.p, A.pd_blob.p, xs, y, e2, A.pd_cap, 2, n_nowait)
+  k_spmv_pd<BR_, BC_, UB_><<<gridd, PD_NB, smem_d, c->stream>>>(nbrows, A.pd_gstart.p, ntd, order, A.pd_goff.p, A.pd_blob.p, xs, y, e2, A.pd_cap, pd_stages, n_nowait)
     if (dbr == 2 && dbc == 2) B200SP_PD_LAUNCH(2, 2, 3);
     else if (dbr == 2 && dbc == 1) B200SP_PD_LAUNCH(2, 1, 3);
     else if (dbr == 1 && dbc == 2) B200SP_PD_LAUNCH(1, 2, 3);
