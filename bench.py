@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 FS = ("-pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type {fact} -pc_fieldsplit_schur_precondition user "
       "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels {{levels}} "
+      "-fieldsplit_0_mg_levels_ksp_type chebyshev -fieldsplit_0_mg_levels_ksp_max_it 3 -fieldsplit_0_mg_levels_pc_type jacobi "
       "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
 CONFIGS = {
     # BASELINE config 3: FGMRES(30), right PC, Schur factorisation with a multigrid A00 solve and the
@@ -85,7 +86,7 @@ def mg_levels(nx):
 
 def options_for(config, nx):
     lev = int(os.environ.get("B200SP_BENCH_MG_LEVELS", "0")) or mg_levels(nx)
-    return CONFIGS[config].format(levels=lev)
+    return CONFIGS[config].format(levels=lev) + (" " + os.environ["B200SP_BENCH_EXTRA_OPTS"] if os.environ.get("B200SP_BENCH_EXTRA_OPTS") else "")
 
 
 def peak_hbm():
