@@ -480,7 +480,7 @@ def main():
     moved_avg = tot_moved / max(tot_n, 1)
     total_prof = sum(v["ms"] for v in prof.values())
     traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the plain-epilogue launch of this kernel on this matrix (ncu --set full)
-    for tf in ("r02_spmv_traffic.json", "r01_spmv_traffic.json"):
+    for tf in ("r02_spmv_traffic.json",):
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
             if tr["nx"] == args.nx and tr["n_gpus"] == world and tr.get("format") == fmt.get("format", tr.get("format")) and \
@@ -489,7 +489,7 @@ def main():
                 break
         except Exception:
             pass
-    kname = fmt.get("kernel") or (("k_spmv_tma_dict<%d,%d>" % fmt["block"]) if fmt["value_dict"] else
+    kname = fmt.get("kernel") or (("k_spmv_pd<%d,%d,3> (tile-local pattern/value dictionaries)" % fmt["block"]) if fmt["value_dict"] else
                                   ("k_spmv_tma_blk<%d,%d>" % fmt["block"]) if fmt["block"] != (1, 1) else "k_spmv_tma")
     achieved = moved_avg / avg_ms / 1e6 if avg_ms > 0 else 0.0
     roofline = {"kernel": "%s on the A block (%d x %d, %d nnz per GPU)" % (kname, rA, cA, nnzA), "bound": "hbm",

@@ -82,3 +82,39 @@ def test_pc_none_is_the_identity(ctx):
     pc.apply(vd, yd)                                          # sets up on first use
     assert same_bits(yd.numpy(), v)
     pc.destroy()
+
+
+def test_ksp_shares_ownership_of_its_operators(ctx):
+    """PETSc reference-counts the operators of KSPSetOperators: MatDestroy before KSPSolve is legal."""
+    import numpy as np
+    import saddle_point_petsc_b200 as sp
+    opts = ("-ksp_type fgmres -ksp_rtol 1e-8 -pc_type fieldsplit -pc_fieldsplit_type schur -pc_fieldsplit_schur_fact_type upper "
+            "-pc_fieldsplit_schur_precondition user -fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type mg -fieldsplit_0_pc_mg_levels 2 "
+            "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi")
+    dev = sp.SaddlePointProblem(ctx, 16, 16, kkt=True, rhs_kind=1)
+    ksp = dev.make_ksp(opts)
+    x = sp.Vec(ctx, dev.n)
+    r1 = ksp.solve(dev.rhs, x)
+    x1 = x.numpy()
+    ksp2 = dev.make_ksp(opts)
+    for m in (dev.K, dev.A, dev.Bt, dev.B, dev.C, dev.Q):     # every caller-side handle goes away before the second KSP is even set up
+        m.destroy()
+    r2 = ksp2.solve(dev.rhs, x)
+    assert r2["its"] == r1["its"] and np.array_equal(x.numpy(), x1)
+
+
+def test_options_that_would_silently_change_the_solver_are_errors(ctx):
+    """-options_left promoted to an error, PETSc defaults this library does not have, unsupported sides / norms."""
+    import pytest
+    import saddle_point_petsc_b200 as sp
+    dev = sp.SaddlePointProblem(ctx, 8, 8)
+    for bad in ("-ksp_type gmres",                                        # no -pc_type: PETSc would use ILU(0)
+                "-ksp_type gmres -pc_type jacobi -ksp_gmres_restrat 5",   # mistyped option
+                "-ksp_type gmres -pc_type jacobi -ksp_pc_side right",     # GMRES is implemented left-preconditioned only
+                "-ksp_type fgmres -pc_type jacobi -ksp_norm_type preconditioned",
+                "-ksp_type gmres -pc_type jacobi -pc_mg_levels 3",        # option of a PC that is not in use
+                "-ksp_type gmres -pc_type mg -pc_mg_levels 2 -mg_levels_pc_type sor"):
+        with pytest.raises(sp.B200spError) as e:
+            dev.make_ksp(bad).setup()
+        assert e.value.code == 4, (bad, str(e.value))                     # B200SP_ERR_UNSUPPORTED
+    dev.make_ksp("-ksp_type gmres -pc_type jacobi -ksp_monitor -ksp_converged_reason -ksp_pc_side left -ksp_norm_type preconditioned").setup()
