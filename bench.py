@@ -563,6 +563,40 @@ def main():
                             and parity["max_rel_velocity_diff"] <= tol_x and parity["max_rel_pressure_diff_mean_removed"] <= tol_x)
         del osolver, oprob
 
+    # ---- the A-block MatMult in every storage format the library has (N=1, after the last solve: switching formats drops
+    # the derived storage the recorded CUDA graphs point at), and on a variable-coefficient operator, whose values do not
+    # repeat: what a general matrix gets.  Bare launches, CUDA events, 20 after 3 warm-ups; results are bit-identical.
+    if world == 1 and args.config not in CONFIGS_3D and not args.no_secondary:
+        def time_mult(m, rows, cols):
+            xv, yv = sp.Vec(ctx, cols), sp.Vec(ctx, rows)
+            xv.set(1.0)
+            for _ in range(3):
+                m.mult(xv, yv)
+            ctx.synchronize()
+            ctx.timer_start()
+            for _ in range(20):
+                m.mult(xv, yv)
+            t = ctx.timer_stop() / 20
+            f = m.spmv_format()
+            moved = f["matrix_bytes"] + 8 * rows + 8 * cols
+            xv.destroy(); yv.destroy()
+            return {"ms": round(t, 5), "block": list(f["block"]), "value_dict": f["value_dict"], "moved_bytes": moved,
+                    "moved_gbs": round(moved / t / 1e6, 1), "frac": round(moved / t / 1e6 / pk, 4),
+                    "csr_algorithmic_gbs": round(bytes_A / t / 1e6, 1)}
+        formats = {"tile dictionaries (default)": time_mult(prob.A, rA, cA)}
+        prob.A.set_spmv_format(True, False)
+        formats["block column index + plain values"] = time_mult(prob.A, rA, cA)
+        prob.A.set_spmv_format(False, False)
+        formats["plain CSR"] = time_mult(prob.A, rA, cA)
+        prob.A.set_spmv_format(True, True)
+        try:
+            Av = prob.da.assemble_stress_coeff(1)
+            formats["variable-coefficient operator, default policy"] = time_mult(Av, rA, cA)
+            Av.destroy()
+        except Exception as e:  # noqa: BLE001
+            formats["variable-coefficient operator, default policy"] = {"error": repr(e)}
+        roofline["formats_bare_matmult"] = formats
+
     secondary = None
     if world == 1 and not args.no_secondary and args.config == "fgmres_schur_mg":
         secondary = []

@@ -181,6 +181,10 @@ int b200sp_bench_orthogonalization(b200sp_ctx ctx, int64_t n, int k, int reps, d
  *      the stubbed AssembleOperator_Constraints (src/Discretization.c:130-290) ---- */
 /* A: DMCreateMatrix pattern + element stress matrices summed in the reference's element order */
 int b200sp_assemble_stress(b200sp_dmda da, int as_written, b200sp_mat *A);
+/* the same operator with a coefficient per Gauss point -- an input of FormStressOperatorQ12D (src/Discretization.c:151-157
+ * sets it to 1): coeff_kind 0 = 1.0, 1 = the smooth viscosity 1 + x(1-y)/2 (every stored value distinct: the SpMV's
+ * dictionaries decline and the block-index kernel runs; used for the variable-coefficient measurements) */
+int b200sp_assemble_stress_coeff(b200sp_dmda da, int coeff_kind, b200sp_mat *A);
 /* f: rhs_kind 0 = reference body force (1,2); 1 = rotational force (KKT workloads) */
 int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec f);
 /* KKT blocks on the same nodal grid: Bt (gradient), B = Bt^T (divergence), C (stabilisation, the (2,2)

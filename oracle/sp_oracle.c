@@ -447,6 +447,30 @@ OrCsr *or_assemble_A(int M, int N, int as_written) {
     }
   return A;
 }
+/* The coefficient is an INPUT of FormStressOperatorQ12D (one value per Gauss point, Discretization.c:151-157 sets 1.0).
+ * kind 1 (ours, for the variable-coefficient SpMV measurements): a smooth viscosity 1 + x (1 - y) / 2 evaluated at the
+ * physical Gauss point -- every stored value becomes distinct, so the tile dictionaries of the SpMV decline. */
+OrCsr *or_assemble_A_coeff(int M, int N, int kind) {
+  OrCsr *A = box_pattern(M, N, 2, 2);
+  for (int ej = 0; ej < N - 1; ++ej)
+    for (int ei = 0; ei < M - 1; ++ei) {
+      double ec[8], coeff[4], Ae[64];
+      int nd[4];
+      or_element_coords(M, N, ei, ej, 0, ec);
+      for (int p = 0; p < 4; ++p) {
+        double Ni[4], xp = 0.0, yp = 0.0;
+        q1_Ni(GP_XI[p], Ni);
+        for (int i = 0; i < 4; ++i) { xp += Ni[i] * ec[2 * i]; yp += Ni[i] * ec[2 * i + 1]; }
+        coeff[p] = kind ? 1.0 + 0.5 * xp * (1.0 - yp) : 1.0;
+      }
+      memset(Ae, 0, sizeof(Ae));
+      or_element_stress(ec, coeff, Ae);
+      element_nodes(M, ei, ej, nd);
+      for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b) add_value(A, nd[a >> 1] * 2 + (a & 1), nd[b >> 1] * 2 + (b & 1), Ae[a * 8 + b]);
+    }
+  return A;
+}
 /* AssembleRHS_Laplace, Discretization.c:174-227 */
 void or_assemble_rhs(int M, int N, int as_written, int kind, double *f) {
   v_zero(2 * M * N, f);

@@ -60,6 +60,7 @@ void or_element_rhs(const double ec[8], int kind, double Fe[8]);                
 void or_element_kkt(const double ec[8], double Ge[32], double Ce[16], double Qe[16]);    /* += ; KKT blocks (ours) */
 
 /* ---- global assembly (src/Discretization.c:130-274), single-rank natural ordering ---- */
+OrCsr *or_assemble_A_coeff(int M, int N, int kind);                  /* same with a variable coefficient per Gauss point (kind 1) */
 OrCsr *or_assemble_A(int M, int N, int as_written);                  /* DMCreateMatrix + AssembleOperator_Laplace */
 void or_assemble_rhs(int M, int N, int as_written, int kind, double *f /* 2*M*N */);
 int or_bc_ids(int M, int N, int dof, int *ids /* dof*(2M+2N-4) */);  /* ApplyBC_Laplace ids, ascending */

@@ -72,6 +72,7 @@ def lib():
     sig("or_element_rhs", None, c_dp, C.c_int, c_dp)
     sig("or_element_kkt", None, c_dp, c_dp, c_dp, c_dp)
     sig("or_assemble_A", CsrP, C.c_int, C.c_int, C.c_int)
+    sig("or_assemble_A_coeff", CsrP, C.c_int, C.c_int, C.c_int)
     sig("or_assemble_rhs", None, C.c_int, C.c_int, C.c_int, C.c_int, c_dp)
     sig("or_bc_ids", C.c_int, C.c_int, C.c_int, C.c_int, c_ip)
     sig("or_apply_bc", None, CsrP, c_dp, C.c_int, c_ip)

@@ -97,6 +97,7 @@ _SIGS = {
     "b200sp_mat_zero_columns": [_vp, C.c_int, c_ip],
     "b200sp_mat_create_nest": [_vp, _vp, _vp, _vp, C.POINTER(_vp)],
     "b200sp_assemble_stress": [_vp, C.c_int, C.POINTER(_vp)],
+    "b200sp_assemble_stress_coeff": [_vp, C.c_int, C.POINTER(_vp)],
     "b200sp_assemble_rhs": [_vp, C.c_int, C.c_int, _vp],
     "b200sp_assemble_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_dmda3d_proc_grid": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip],
@@ -547,6 +548,12 @@ class DMDA:
     def assemble_stress(self, as_written=False):
         h = _vp()
         _chk(lib().b200sp_assemble_stress(self.h, int(as_written), C.byref(h)))
+        return Mat(self.ctx, h)
+
+    def assemble_stress_coeff(self, coeff_kind=1):
+        """A with a coefficient per Gauss point (1 = smooth viscosity 1 + x(1-y)/2)"""
+        h = _vp()
+        _chk(lib().b200sp_assemble_stress_coeff(self.h, coeff_kind, C.byref(h)))
         return Mat(self.ctx, h)
 
     def assemble_rhs(self, f, rhs_kind=0, as_written=False):

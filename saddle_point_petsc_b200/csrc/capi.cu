@@ -633,6 +633,13 @@ int b200sp_mat_create_nest(b200sp_mat A00, b200sp_mat A01, b200sp_mat A10, b200s
 }
 
 // ---------------------------------------------------------------- assembly
+int b200sp_assemble_stress_coeff(b200sp_dmda da, int coeff_kind, b200sp_mat *A) {
+  API_BEGIN
+  B2_REQUIRE(da && A && (coeff_kind == 0 || coeff_kind == 1), "assemble_stress_coeff: bad arguments");
+  use_device(da->d.ctx);
+  *A = wrap(da->d.ctx, assemble_stress(da->d, 0, coeff_kind));
+  API_END
+}
 int b200sp_assemble_stress(b200sp_dmda da, int as_written, b200sp_mat *A) { API_BEGIN use_device(da->d.ctx); *A = wrap(da->d.ctx, assemble_stress(da->d, as_written)); API_END }
 int b200sp_assemble_rhs(b200sp_dmda da, int as_written, int rhs_kind, b200sp_vec f) {
   API_BEGIN

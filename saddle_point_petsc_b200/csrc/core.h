@@ -410,7 +410,7 @@ void dense_inverse_from_csr(const Csr &A, double *Ainv); // n x n row-major, dev
 void dense_matvec(Ctx *c, int n, const double *Ainv, const double *x, double *y);
 
 // assembly (kernels_assembly.cu)
-std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written);
+std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written, int coeff_kind = 0);
 void assemble_rhs(const Dmda &da, int as_written, int kind, double *f);
 void assemble_kkt(const Dmda &da, std::shared_ptr<Csr> *Bt, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *C, std::shared_ptr<Csr> *Q);
 void assemble_constraints(const Dmda &da, std::shared_ptr<Csr> *B, std::shared_ptr<Csr> *Bt); // the reference's 4 dense constraint rows

@@ -82,7 +82,7 @@ __device__ __forceinline__ void element_coords(int M, int N, int ei, int ej, int
   }
 }
 
-enum { WANT_K = 1, WANT_F = 2, WANT_KKT = 4 };
+enum { WANT_K = 1, WANT_F = 2, WANT_KKT = 4, WANT_COEFF = 8 }; // COEFF: variable coefficient 1 + x(1-y)/2 at the Gauss point
 
 // one thread per element; outputs entry-major: X[entry * nel + e]
 __global__ void __launch_bounds__(128) k_elements(int M, int N, ElemBox eb, int as_written, int rhs_kind, int want,
@@ -110,7 +110,15 @@ __global__ void __launch_bounds__(128) k_elements(int M, int N, ElemBox eb, int 
         B[1][2 * i] = 0.0;       B[1][2 * i + 1] = GNx[1][i];
         B[2][2 * i] = GNx[1][i]; B[2][2 * i + 1] = GNx[0][i];
       }
-      const double coeff = 1.0, w = 1.0;
+      double coeff = 1.0; // an input of FormStressOperatorQ12D, one value per Gauss point (:151-157 sets 1.0)
+      if (want & WANT_COEFF) {
+        double Ni[4], xp = 0.0, yp = 0.0;
+        q1_Ni(xi, Ni);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xp += Ni[i] * ec[2 * i]; yp += Ni[i] * ec[2 * i + 1]; }
+        coeff = 1.0 + 0.5 * xp * (1.0 - yp);
+      }
+      const double w = 1.0;
       tD[0] = 2.0 * w * detJ * coeff;
       tD[1] = 2.0 * w * detJ * coeff;
       tD[2] = w * detJ * coeff;
@@ -596,9 +604,9 @@ std::shared_ptr<Csr> build_box_matrix(const Dmda &da, const ElemArrays &ea, int 
 
 } // namespace
 
-std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written) {
+std::shared_ptr<Csr> assemble_stress(const Dmda &da, int as_written, int coeff_kind) {
   ElemArrays ea;
-  run_elements(da, as_written, 0, WANT_K, ea);
+  run_elements(da, as_written, 0, WANT_K | (coeff_kind ? WANT_COEFF : 0), ea);
   auto A = build_box_matrix(da, ea, 2, 2, 0, ea.Ke.p);
   A->tag = "spmv:A";
   csr_try_block_index(*A, 2, 2);

@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
   unsigned char *s_first = reinterpret_cast<unsigned char *>(s_val + (size_t)PMAX * PD_NB);         // [PMAX][PD_NB] first row with this value
   unsigned char *s_rank = s_first + (size_t)PMAX * PD_NB;                                          // [PMAX][PD_NB] rank of a first occurrence
   __shared__ int s_pfirst[PD_NB], s_prank[PD_NB], s_cnt[PMAX], s_posoff[PMAX + 1], s_w[4], s_base[PD_NB];
+  __shared__ unsigned long long s_hkey[8][256];
+  __shared__ int s_hmin[8][256];
   __shared__ int s_nbmax, s_bad, s_npat;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
   const int I0 = tile * PD_NB;
@@ -485,17 +487,40 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
     s_prank[tid] += base;
     if (tid == 0) s_npat = s_w[0] + s_w[1] + s_w[2] + s_w[3];
   }
-  // values: first row of the tile that holds the same bits at the same position
-  for (int idx = tid; idx < P * PD_NB; idx += 256) {
-    const int p = idx / PD_NB, i = idx % PD_NB, k = p / BRBC;
-    int first = 255; // absent
-    if (k < s_delta[i * (PD_MAX_K + 1)]) {
-      const unsigned long long v = s_val[idx];
-      first = i;
-      for (int j = 0; j < i; ++j)
-        if (k < s_delta[j * (PD_MAX_K + 1)] && s_val[p * PD_NB + j] == v) { first = j; break; }
+  // values: first row of the tile that holds the same bits at the same position.  One warp per position, a 256-slot
+  // hash set of the position's (at most 128) values in shared memory: insert with atomicCAS, keep the smallest row per
+  // key with atomicMin -- the result (first occurrence) does not depend on the order of insertion.
+  for (int p = warp; p < P; p += 8) {
+    unsigned long long *hk = s_hkey[warp];
+    int *hm = s_hmin[warp];
+    for (int q = lane; q < 256; q += 32) { hk[q] = ~0ull; hm[q] = 0x7fffffff; }
+    __syncwarp();
+    const int k = p / BRBC;
+    int slot[PD_NB / 32];
+#pragma unroll
+    for (int c = 0; c < PD_NB / 32; ++c) {
+      const int i = c * 32 + lane;
+      slot[c] = -1;
+      if (k < s_delta[i * (PD_MAX_K + 1)]) {
+        const unsigned long long v = s_val[p * PD_NB + i];
+        if (v == ~0ull) { s_bad = 1; continue; } // the one bit pattern the set cannot hold (a NaN payload): no dictionary
+        unsigned h = (unsigned)((v * 0x9E3779B97F4A7C15ull) >> 56);
+        for (;;) {
+          const unsigned long long prev = atomicCAS(&hk[h], ~0ull, v);
+          if (prev == ~0ull || prev == v) break;
+          h = (h + 1) & 255u;
+        }
+        atomicMin(&hm[h], i);
+        slot[c] = (int)h;
+      }
     }
-    s_first[idx] = (unsigned char)first;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < PD_NB / 32; ++c) {
+      const int i = c * 32 + lane;
+      s_first[p * PD_NB + i] = (unsigned char)(slot[c] >= 0 ? hm[slot[c]] : 255);
+    }
+    __syncwarp();
   }
   __syncthreads();
   for (int p = warp; p < P; p += 8) { // one warp per position: ranks of the first occurrences, in row order

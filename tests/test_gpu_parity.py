@@ -620,3 +620,23 @@ def test_constrained_problem_solve_parity(ctx, name):
         assert np.max(np.abs(xs[:-4] - ro["x"][:-4])) <= tol_u * np.max(np.abs(ro["x"][:-4])), tol_u
         assert np.max(np.abs(xs[-4:] - ro["x"][-4:])) <= tol_l * np.max(np.abs(ro["x"][-4:])), tol_l
     assert np.allclose(orc.B.scipy() @ xs[:-4], G_CON, atol=1e-9)           # the constraints hold
+
+
+def test_variable_coefficient_operator_bit_exact_and_uncompressed(ctx):
+    """The coefficient is an input of FormStressOperatorQ12D (src/Discretization.c:151-157): with a smooth viscosity the
+    assembly is still bit-exact, every value is distinct, the tile dictionaries decline and the block-index kernel gives the
+    same bits as the oracle's sequential MatMult."""
+    nx, ny = 200, 160
+    da = sp.DMDA(ctx, nx, ny)
+    D = da.assemble_stress_coeff(1)
+    O = so.Csr(so.lib().or_assemble_A_coeff(nx + 1, ny + 1, 1))
+    rp, col, val = D.csr()
+    assert np.array_equal(rp, O.rowptr) and np.array_equal(col, O.col) and same_bits(val, O.val)
+    base = so.Csr(so.lib().or_assemble_A(nx + 1, ny + 1, 0))
+    assert np.max(np.abs(O.val - base.val)) > 0.1                 # it really is another operator
+    x = rand_vec(O.ncols, 41)
+    y = sp.Vec(ctx, O.nrows)
+    D.mult(sp.Vec.from_numpy(ctx, x), y)
+    fmt = D.spmv_format()
+    assert fmt["block"] == (2, 2) and not fmt["value_dict"], fmt
+    assert same_bits(y.numpy(), O.mult(x))
