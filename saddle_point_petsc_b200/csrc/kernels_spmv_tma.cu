@@ -773,6 +773,9 @@ static bool build_pd_mode(const Csr &A, int force, int rel, bool only_if_small) 
     c->sync();
     A.h_pd_gstart = gs;
     A.pd_cap = (int)((capg + 127) & ~127LL);
+    static const bool dbg = getenv("B200SP_PD_DEBUG") && atoi(getenv("B200SP_PD_DEBUG"));
+    if (dbg) fprintf(stderr, "[b200sp pd] %s: %dx%d blocks, rel %d, %d tiles, %.2f B/nnz, largest tile %d B, %d groups, stage %d B\n", A.tag.c_str(), BR, BC, rel,
+                     ntiles, total / (double)std::max<int64_t>(A.nnz, 1), h_stat[1], A.pd_ngroups, A.pd_cap);
   }
   A.dict_rows = PD_NB * BR;
   A.dict_bytes = (int64_t)total16 * 16 + 4 * (int64_t)(ntiles + 1);
@@ -822,6 +825,19 @@ static int ctas_per_sm(size_t smem, int threads) {
   if (n > 32) n = 32;
   return n;
 }
+// ... and the register file: the persistent grids are sized to exactly one wave, so the number of co-resident CTAs must be
+// what the hardware will really schedule for THIS kernel (registers included), not a shared-memory estimate -- one CTA too
+// many per SM and 1/8 of the grid runs as a second, nearly empty wave (measured: 0.195 instead of 0.133 ms on the A block
+// when the stage size dropped just below the 8-CTA shared-memory threshold while 72 registers allow 7).
+template <class K>
+static int ctas_per_sm(K kernel, size_t smem, int threads) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  return std::min(n, ctas_per_sm(smem, threads));
+}
 
 bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list, int nlist) {
   Ctx *c = A.ctx;
@@ -851,7 +867,7 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
   if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
   const int ntiles = tile_list ? nlist : (A.nrows + R - 1) / R;
   if (ntiles <= 0) return true;
-  const int per_sm = ctas_per_sm(smem, R);
+  const int per_sm = (env_U ? env_U == 6 : true) ? ctas_per_sm(k_spmv_tma<6>, smem, R) : ctas_per_sm(k_spmv_tma<3>, smem, R);
   int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
   if (A.dict_state == 0) { // lazily, never while a CUDA graph is being recorded
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -865,12 +881,21 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     const size_t smem_d = (size_t)A.pd_cap * pd_stages + 8 * TMA_MAX_STAGES;
     if (!(c->attr_mask & 8u)) {
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<2, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<1, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       B2_CUDA(cudaFuncSetAttribute(k_spmv_pd<1, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       c->attr_mask |= 8u;
     }
-    int psm = ctas_per_sm(smem_d, PD_NB);
+    static const int env_ub = getenv("B200SP_PD_UB") ? atoi(getenv("B200SP_PD_UB")) : 0; // blocks in flight per thread (tuning)
+    int psm;
+    if (dbr == 2 && dbc == 2) psm = env_ub == 5 ? ctas_per_sm(k_spmv_pd<2, 2, 5>, smem_d, PD_NB) : env_ub == 9 ? ctas_per_sm(k_spmv_pd<2, 2, 9>, smem_d, PD_NB)
+                                  : env_ub == 2 ? ctas_per_sm(k_spmv_pd<2, 2, 2>, smem_d, PD_NB) : ctas_per_sm(k_spmv_pd<2, 2, 3>, smem_d, PD_NB);
+    else if (dbr == 2 && dbc == 1) psm = ctas_per_sm(k_spmv_pd<2, 1, 3>, smem_d, PD_NB);
+    else if (dbr == 1 && dbc == 2) psm = ctas_per_sm(k_spmv_pd<1, 2, 3>, smem_d, PD_NB);
+    else psm = ctas_per_sm(k_spmv_pd<1, 1, 3>, smem_d, PD_NB);
     static const int env_psm = getenv("B200SP_TMA_CTAS") ? atoi(getenv("B200SP_TMA_CTAS")) : 0;
     if (env_psm && env_psm < psm) psm = env_psm;
     const int nbrows = A.nrows / dbr;
@@ -884,7 +909,10 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     e2.vec2 = dbr == 2 && al16(y) && al16(epi.z) && al16(epi.pm1) && al16(epi.pk) && al16(epi.dinv);
 #define B200SP_PD_LAUNCH(BR_, BC_, UB_) \
   k_spmv_pd<BR_, BC_, UB_><<<gridd, PD_NB, smem_d, c->stream>>>(nbrows, A.pd_gstart.p, ntd, order, A.pd_goff.p, A.pd_blob.p, xs, y, e2, A.pd_cap, pd_stages, n_nowait)
-    if (dbr == 2 && dbc == 2) B200SP_PD_LAUNCH(2, 2, 3);
+    if (dbr == 2 && dbc == 2 && env_ub == 5) B200SP_PD_LAUNCH(2, 2, 5);
+    else if (dbr == 2 && dbc == 2 && env_ub == 9) B200SP_PD_LAUNCH(2, 2, 9);
+    else if (dbr == 2 && dbc == 2 && env_ub == 2) B200SP_PD_LAUNCH(2, 2, 2);
+    else if (dbr == 2 && dbc == 2) B200SP_PD_LAUNCH(2, 2, 3);
     else if (dbr == 2 && dbc == 1) B200SP_PD_LAUNCH(2, 1, 3);
     else if (dbr == 1 && dbc == 2) B200SP_PD_LAUNCH(1, 2, 3);
     else B200SP_PD_LAUNCH(1, 1, 3);
@@ -903,7 +931,8 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
       B2_CUDA(cudaFuncSetAttribute(k_spmv_tma_blk<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       c->attr_mask |= 16u;
     }
-    const int psm = ctas_per_sm(smem_b, R);
+    const int psm = A.blk_r == 2 && A.blk_c == 2 ? ctas_per_sm(k_spmv_tma_blk<2, 2, 6>, smem_b, R)
+                    : A.blk_r == 1 && A.blk_c == 2 ? ctas_per_sm(k_spmv_tma_blk<1, 2, 6>, smem_b, R) : ctas_per_sm(k_spmv_tma_blk<2, 1, 6>, smem_b, R);
     const int gridb = ntiles < c->num_sms * psm ? ntiles : c->num_sms * psm;
     if (A.blk_r == 2 && A.blk_c == 2)
       k_spmv_tma_blk<2, 2, 6><<<gridb, R, smem_b, c->stream>>>(A.nrows, ntiles, tile_list, A.rowptr.p, A.bptr.p, A.bcol.p, A.val.p, xs, y, epi, cap, capb, stages, n_nowait);

@@ -60,6 +60,12 @@ def sweep_point(sp, ctx, nx, pk1, reduce_max, reduce_sum):
                              "csr_algorithmic_gbs": round(alg / ms / 1e6, 1), "bytes_per_nnz": round(fmt["matrix_bytes"] / max(nnz, 1), 2),
                              "format": "block %dx%d%s" % (fmt["block"] + (", tile dictionaries" if fmt["value_dict"] else "",)),
                              "l2": bool(moved / max(ctx.size, 1) < L2_BYTES)}
+        # the same MatMult through the general (uncompressed CSR) kernel: what a matrix without repeating values gets
+        m.set_spmv_format(False, False)
+        ms_csr = reduce_max(time_ms(ctx, lambda: m.mult(x, y)))
+        m.set_spmv_format(True, True)
+        row["spmv"][name]["plain_csr_ms"] = round(ms_csr, 5)
+        row["spmv"][name]["plain_csr_frac"] = round(alg / ms_csr / 1e6 / pk, 4)
         x.destroy(); y.destroy()
     n = prob.n
     a, b, w = sp.Vec(ctx, n), sp.Vec(ctx, n), sp.Vec(ctx, n)
