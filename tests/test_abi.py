@@ -194,3 +194,20 @@ def test_petsc_plugin_source_is_carried_and_guarded():
         assert needle in text, needle
     p = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+
+
+def test_dmda3d_process_grid_matches_petsc_decide():
+    """DMDACreate3d(PETSC_DECIDE x 3): the squarish factorisation of PETSc's da3.c (host index arithmetic, no GPU)."""
+    import ctypes as C
+    def grid(M, N, P, size):
+        m, n, p = C.c_int(), C.c_int(), C.c_int()
+        assert sp.lib().b200sp_dmda3d_proc_grid(M, N, P, size, C.byref(m), C.byref(n), C.byref(p)) == 0
+        return m.value, n.value, p.value
+    assert grid(252, 252, 252, 1) == (1, 1, 1)
+    assert grid(252, 252, 252, 8) == (2, 2, 2)
+    assert sorted(grid(252, 252, 252, 2)) == [1, 1, 2]
+    assert sorted(grid(252, 252, 252, 4)) == [1, 2, 2]
+    for size in (1, 2, 3, 4, 6, 8, 12, 16):
+        m, n, p = grid(65, 33, 17, size)
+        assert m * n * p == size
+        assert m >= n >= p or size < 4            # the longer direction gets at least as many ranks

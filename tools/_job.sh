@@ -1,5 +1,2 @@
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -q -x) > gpurun_out/r02_pytest15.log 2>&1
-grep -E "^E   |^FAILED|passed|failed|rror" gpurun_out/r02_pytest15.log | cut -c1-300 | head -20
-(time python bench.py --config sweep) > gpurun_out/r02_sweep_1gpu.json 2> gpurun_out/r02_sweep_1gpu.err; echo "sweep rc=$?"
-python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench8.json 2> gpurun_out/r02_bench8.err; echo "bench rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r02_bench_16M_8gpu.json 2> gpurun_out/r02_bench_16M_8gpu.err; echo "b8 rc=$?"
