@@ -606,11 +606,10 @@ def main():
             except Exception as e:  # noqa: BLE001
                 secondary.append({"config": name, "grid_elements": [nx2, nx2], "error": repr(e)})
 
-    cfg = workload(args, n_global, opts)
-    cfg["dof_per_gpu"] = n
+    cfg = workload(args, n_global, opts)   # identical to the reference arm's `config` (same keys, same values)
     line = {"metric": "time_to_solve_rtol1e-8", "value": t_solve, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_solve * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": cfg, "iterations": res["its"], "converged_reason": res["reason"],
+            "data": "synthetic", "config": cfg, "dof_per_gpu_rank0": n, "iterations": res["its"], "converged_reason": res["reason"],
             "iterations_per_s": res["its"] / t_solve, "true_relative_residual": true_rel,
             "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "dist_check": dcheck,
