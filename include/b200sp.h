@@ -194,6 +194,8 @@ int b200sp_assemble_kkt(b200sp_dmda da, b200sp_mat *Bt, b200sp_mat *B, b200sp_ma
  *      nodes, box stencil, PETSC_DECIDE process grid, and the Q1-hexahedron analogue of the 2-D assembly (definition:
  *      oracle/sp_oracle3d.c).  Velocity 3 dof per node, pressure 1; rows are local, columns local (ghosts after the owned). ---- */
 int b200sp_dmda3d_proc_grid(int M, int N, int P, int size, int *m, int *n, int *p);
+int b200sp_dmda3d_corners(int M, int N, int P, int size, int rank, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm); /* host only */
+int b200sp_dmda3d_global_node(int M, int N, int P, int size, int i, int j, int k, int *gnode, int *owner);                /* host only */
 int b200sp_dmda3d_create(b200sp_ctx ctx, int M, int N, int P, b200sp_dmda3d *da);
 int b200sp_dmda3d_destroy(b200sp_dmda3d da);
 int b200sp_dmda3d_get_info(b200sp_dmda3d da, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm, int64_t *first_global_node);

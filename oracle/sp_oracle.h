@@ -78,6 +78,8 @@ OrCsr *or3_assemble_A(int M, int N, int P);
 void or3_assemble_rhs(int M, int N, int P, int kind, double *f);
 void or3_assemble_kkt(int M, int N, int P, OrCsr **Bt, OrCsr **B, OrCsr **C, OrCsr **Q);
 int or3_bc_ids(int M, int N, int P, int dof, int *ids); /* ids may be NULL to query the count */
+void or3_dmda_proc_grid(int M, int N, int P, int size, int *pm, int *pn, int *pp);
+void or3_dmda_natural_to_petsc(int M, int N, int P, int size, int *node_map, int *node_owner);
 void or_element_constraints(const double ec[8], double Be[32]);               /* += ; the reference's 4 constraint rows (ours) */
 void or_assemble_constraints(int M, int N, OrCsr **B, OrCsr **Bt);            /* B: 4 x 2MN, Bt = B^T */
 void or_zero_rows(OrCsr *A, int n, const int *rows);

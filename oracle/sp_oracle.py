@@ -81,6 +81,8 @@ def lib():
     sig("or3_assemble_rhs", None, C.c_int, C.c_int, C.c_int, C.c_int, c_dp)
     sig("or3_assemble_kkt", None, C.c_int, C.c_int, C.c_int, C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP), C.POINTER(CsrP))
     sig("or3_bc_ids", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip)
+    sig("or3_dmda_proc_grid", None, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip)
+    sig("or3_dmda_natural_to_petsc", None, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip)
     sig("or3_element_coords", None, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp)
     sig("or3_element_stress", None, c_dp, c_dp)
     sig("or3_element_rhs", None, c_dp, C.c_int, c_dp)
@@ -193,6 +195,13 @@ def dmda_natural_to_petsc(M, N, size):
     nm = np.zeros(M * N, dtype=np.int32)
     ow = np.zeros(M * N, dtype=np.int32)
     lib().or_dmda_natural_to_petsc(M, N, size, iptr(nm), iptr(ow))
+    return nm, ow
+
+
+def dmda3d_natural_to_petsc(M, N, P, size):
+    nm = np.zeros(M * N * P, dtype=np.int32)
+    ow = np.zeros(M * N * P, dtype=np.int32)
+    lib().or3_dmda_natural_to_petsc(M, N, P, size, iptr(nm), iptr(ow))
     return nm, ow
 
 

@@ -245,3 +245,41 @@ int or3_bc_ids(int M, int N, int P, int dof, int *ids) {
           for (int d = 0; d < dof; ++d) { if (ids) ids[n] = ((k * N + j) * M + i) * dof + d; ++n; }
   return n;
 }
+
+/* DMDACreate3d(PETSC_DECIDE x 3): process grid (PETSc da3.c), ownership M/m + (M % m > i) per direction, rank r at
+ * (r % m, (r / m) % n, r / (m n)); PETSc global numbering = rank-contiguous, x fastest inside a rank. */
+void or3_dmda_proc_grid(int M, int N, int P, int size, int *pm, int *pn, int *pp) {
+  int n = (int)(0.5 + pow(((double)N * N) * ((double)size) / ((double)P * M), 1.0 / 3.0)), m, p = 1;
+  if (!n) n = 1;
+  while (n > 0) { int pmn = size / n; if (n * pmn == size) break; n--; }
+  if (!n) n = 1;
+  m = (int)(0.5 + sqrt(((double)M) * ((double)size) / ((double)P * n)));
+  if (!m) m = 1;
+  while (m > 0) { p = size / (m * n); if (m * n * p == size) break; m--; }
+  if (M > P && m < p) { int t = m; m = p; p = t; }
+  *pm = m; *pn = n; *pp = p;
+}
+void or3_dmda_natural_to_petsc(int M, int N, int P, int size, int *node_map, int *node_owner) {
+  int m, n, p;
+  or3_dmda_proc_grid(M, N, P, size, &m, &n, &p);
+  int *lx = (int *)malloc(sizeof(int) * (size_t)m), *ly = (int *)malloc(sizeof(int) * (size_t)n), *lz = (int *)malloc(sizeof(int) * (size_t)p);
+  or_dmda_ownership(M, m, lx);
+  or_dmda_ownership(N, n, ly);
+  or_dmda_ownership(P, p, lz);
+  int start = 0;
+  for (int r = 0; r < size; ++r) {
+    int pi = r % m, pj = (r / m) % n, pk = r / (m * n), xs = 0, ys = 0, zs = 0;
+    for (int i = 0; i < pi; ++i) xs += lx[i];
+    for (int j = 0; j < pj; ++j) ys += ly[j];
+    for (int k = 0; k < pk; ++k) zs += lz[k];
+    for (int k = 0; k < lz[pk]; ++k)
+      for (int j = 0; j < ly[pj]; ++j)
+        for (int i = 0; i < lx[pi]; ++i) {
+          int nat = ((zs + k) * N + ys + j) * M + xs + i;
+          node_map[nat] = start + (k * ly[pj] + j) * lx[pi] + i;
+          if (node_owner) node_owner[nat] = r;
+        }
+    start += lx[pi] * ly[pj] * lz[pk];
+  }
+  free(lx); free(ly); free(lz);
+}

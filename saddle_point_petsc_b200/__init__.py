@@ -101,6 +101,8 @@ _SIGS = {
     "b200sp_assemble_rhs": [_vp, C.c_int, C.c_int, _vp],
     "b200sp_assemble_kkt": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "b200sp_dmda3d_proc_grid": [C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip],
+    "b200sp_dmda3d_corners": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip],
+    "b200sp_dmda3d_global_node": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip],
     "b200sp_dmda3d_create": [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
     "b200sp_dmda3d_destroy": [_vp],
     "b200sp_dmda3d_get_info": [_vp, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)],

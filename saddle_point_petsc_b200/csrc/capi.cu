@@ -686,6 +686,47 @@ static void dmda3_proc_grid(int M, int N, int P, int size, int *pm, int *pn, int
 int b200sp_dmda3d_proc_grid(int M, int N, int P, int size, int *m, int *n, int *p) {
   API_BEGIN B2_REQUIRE(M > 0 && N > 0 && P > 0 && size > 0, "bad args"); dmda3_proc_grid(M, N, P, size, m, n, p); API_END
 }
+// host-only index arithmetic of the 3-D partition (no device needed): owned box of a rank, PETSc global id and owner of a node
+struct Part3 {
+  int m, n, p;
+  std::vector<int> lx, ly, lz, xo, yo, zo, rstart;
+  Part3(int M, int N, int P, int size) {
+    dmda3_proc_grid(M, N, P, size, &m, &n, &p);
+    B2_REQUIRE(m * n * p == size && m <= M && n <= N && p <= P, "dmda3d: size does not factor into a process grid for this mesh");
+    lx.resize((size_t)m); ly.resize((size_t)n); lz.resize((size_t)p);
+    dmda_ownership(M, m, lx.data()); dmda_ownership(N, n, ly.data()); dmda_ownership(P, p, lz.data());
+    xo.assign((size_t)m + 1, 0); yo.assign((size_t)n + 1, 0); zo.assign((size_t)p + 1, 0);
+    for (int i = 0; i < m; ++i) xo[(size_t)i + 1] = xo[(size_t)i] + lx[(size_t)i];
+    for (int i = 0; i < n; ++i) yo[(size_t)i + 1] = yo[(size_t)i] + ly[(size_t)i];
+    for (int i = 0; i < p; ++i) zo[(size_t)i + 1] = zo[(size_t)i] + lz[(size_t)i];
+    rstart.assign((size_t)size + 1, 0);
+    for (int r = 0; r < size; ++r) rstart[(size_t)r + 1] = rstart[(size_t)r] + lx[(size_t)(r % m)] * ly[(size_t)((r / m) % n)] * lz[(size_t)(r / (m * n))];
+  }
+  void box(int r, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm) const {
+    const int pi = r % m, pj = (r / m) % n, pk = r / (m * n);
+    *xs = xo[(size_t)pi]; *ys = yo[(size_t)pj]; *zs = zo[(size_t)pk]; *xm = lx[(size_t)pi]; *ym = ly[(size_t)pj]; *zm = lz[(size_t)pk];
+  }
+  static int owner_of(const std::vector<int> &off, int v) { return (int)(std::upper_bound(off.begin(), off.end(), v) - off.begin()) - 1; }
+  int owner(int i, int j, int k) const { return (owner_of(zo, k) * n + owner_of(yo, j)) * m + owner_of(xo, i); }
+  int gnode(int i, int j, int k) const {
+    const int pi = owner_of(xo, i), pj = owner_of(yo, j), pk = owner_of(zo, k), r = (pk * n + pj) * m + pi;
+    return rstart[(size_t)r] + ((k - zo[(size_t)pk]) * ly[(size_t)pj] + (j - yo[(size_t)pj])) * lx[(size_t)pi] + (i - xo[(size_t)pi]);
+  }
+};
+int b200sp_dmda3d_corners(int M, int N, int P, int size, int rank, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm) {
+  API_BEGIN
+  B2_REQUIRE(M > 0 && N > 0 && P > 0 && size > 0 && rank >= 0 && rank < size, "dmda3d_corners: bad arguments");
+  Part3(M, N, P, size).box(rank, xs, ys, zs, xm, ym, zm);
+  API_END
+}
+int b200sp_dmda3d_global_node(int M, int N, int P, int size, int i, int j, int k, int *gnode, int *owner) {
+  API_BEGIN
+  B2_REQUIRE(i >= 0 && i < M && j >= 0 && j < N && k >= 0 && k < P && size > 0, "dmda3d_global_node: node out of range");
+  Part3 pt(M, N, P, size);
+  if (gnode) *gnode = pt.gnode(i, j, k);
+  if (owner) *owner = pt.owner(i, j, k);
+  API_END
+}
 int b200sp_dmda3d_create(b200sp_ctx ctx, int M, int N, int P, b200sp_dmda3d *da) {
   API_BEGIN
   B2_REQUIRE(ctx && da && M >= 2 && N >= 2 && P >= 2, "dmda3d_create: bad arguments");
@@ -696,27 +737,13 @@ int b200sp_dmda3d_create(b200sp_ctx ctx, int M, int N, int P, b200sp_dmda3d *da)
     Dmda3 &d = h->d;
     d.ctx = c; d.M = M; d.N = N; d.P = P;
     const int size = c->size, rank = c->rank;
-    dmda3_proc_grid(M, N, P, size, &d.pm, &d.pn, &d.pp);
-    B2_REQUIRE(d.pm * d.pn * d.pp == size && d.pm <= M && d.pn <= N && d.pp <= P, "dmda3d: size does not factor into a process grid for this mesh");
-    std::vector<int> lx((size_t)d.pm), ly((size_t)d.pn), lz((size_t)d.pp), xo((size_t)d.pm + 1, 0), yo((size_t)d.pn + 1, 0), zo((size_t)d.pp + 1, 0);
-    dmda_ownership(M, d.pm, lx.data()); dmda_ownership(N, d.pn, ly.data()); dmda_ownership(P, d.pp, lz.data());
-    for (int i = 0; i < d.pm; ++i) xo[(size_t)i + 1] = xo[(size_t)i] + lx[(size_t)i];
-    for (int i = 0; i < d.pn; ++i) yo[(size_t)i + 1] = yo[(size_t)i] + ly[(size_t)i];
-    for (int i = 0; i < d.pp; ++i) zo[(size_t)i + 1] = zo[(size_t)i] + lz[(size_t)i];
-    auto box = [&](int r, int *xs, int *ys, int *zs, int *xm, int *ym, int *zm) {
-      const int pi = r % d.pm, pj = (r / d.pm) % d.pn, pk = r / (d.pm * d.pn);
-      *xs = xo[(size_t)pi]; *ys = yo[(size_t)pj]; *zs = zo[(size_t)pk]; *xm = lx[(size_t)pi]; *ym = ly[(size_t)pj]; *zm = lz[(size_t)pk];
-    };
-    std::vector<int> rstart((size_t)size + 1, 0);
-    for (int r = 0; r < size; ++r) { int a, b, e, xm, ym, zm; box(r, &a, &b, &e, &xm, &ym, &zm); rstart[(size_t)r + 1] = rstart[(size_t)r] + xm * ym * zm; }
-    box(rank, &d.xs, &d.ys, &d.zs, &d.xm, &d.ym, &d.zm);
+    const Part3 part(M, N, P, size);
+    d.pm = part.m; d.pn = part.n; d.pp = part.p;
+    const std::vector<int> &rstart = part.rstart;
+    part.box(rank, &d.xs, &d.ys, &d.zs, &d.xm, &d.ym, &d.zm);
     B2_REQUIRE(size == 1 || (d.xm >= 2 && d.ym >= 2 && d.zm >= 2), "dmda3d: every rank must own at least 2 x 2 x 2 nodes");
     d.g0 = rstart[(size_t)rank];
-    auto owner_of = [&](const std::vector<int> &off, int v) { return (int)(std::upper_bound(off.begin(), off.end(), v) - off.begin()) - 1; };
-    auto gnode = [&](int i, int j, int k) {
-      const int pi = owner_of(xo, i), pj = owner_of(yo, j), pk = owner_of(zo, k), r = (pk * d.pn + pj) * d.pm + pi;
-      return rstart[(size_t)r] + ((k - zo[(size_t)pk]) * ly[(size_t)pj] + (j - yo[(size_t)pj])) * lx[(size_t)pi] + (i - xo[(size_t)pi]);
-    };
+    auto gnode = [&](int i, int j, int k) { return part.gnode(i, j, k); };
     // ghost nodes: the one-node layer around the owned box, clipped to the domain, sorted by global id (MPIAIJ garray order)
     const int ex = d.xm + 2, ey = d.ym + 2, ez = d.zm + 2;
     std::vector<std::pair<int, int>> gh; // (global node id, ext index)

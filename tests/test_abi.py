@@ -211,3 +211,29 @@ def test_dmda3d_process_grid_matches_petsc_decide():
         m, n, p = grid(65, 33, 17, size)
         assert m * n * p == size
         assert m >= n >= p or size < 4            # the longer direction gets at least as many ranks
+
+
+@pytest.mark.parametrize("M,N,P,size", [(9, 8, 7, 2), (12, 10, 9, 4), (13, 11, 9, 8), (20, 9, 6, 6), (7, 7, 7, 1)])
+def test_dmda3d_partition_map_matches_the_oracle(M, N, P, size):
+    """3-D partition maps must match exactly (host index arithmetic through the C ABI vs the oracle): owned boxes tile the
+    grid, PETSc global numbering is rank-contiguous with x fastest inside a rank."""
+    import ctypes as C
+    nm, ow = so.dmda3d_natural_to_petsc(M, N, P, size)
+    L = sp.lib()
+    seen = np.zeros(M * N * P, dtype=np.int32)
+    for r in range(size):
+        v = [C.c_int() for _ in range(6)]
+        assert L.b200sp_dmda3d_corners(M, N, P, size, r, *[C.byref(x) for x in v]) == 0
+        xs, ys, zs, xm, ym, zm = [x.value for x in v]
+        for k in range(zs, zs + zm):
+            for j in range(ys, ys + ym):
+                for i in range(xs, xs + xm):
+                    seen[(k * N + j) * M + i] += 1
+                    assert ow[(k * N + j) * M + i] == r
+    assert np.all(seen == 1)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        i, j, k = int(rng.integers(M)), int(rng.integers(N)), int(rng.integers(P))
+        g, o = C.c_int(), C.c_int()
+        assert L.b200sp_dmda3d_global_node(M, N, P, size, i, j, k, C.byref(g), C.byref(o)) == 0
+        assert g.value == nm[(k * N + j) * M + i] and o.value == ow[(k * N + j) * M + i]
