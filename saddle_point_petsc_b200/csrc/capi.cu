@@ -504,8 +504,8 @@ int b200sp_mat_get_spmv_format(b200sp_mat A, int *block_r, int *block_c, int *va
   API_BEGIN
   Csr &M = plain(A);
   const bool blk = M.bcol.p != nullptr, dict = M.dict_state == 1;
-  if (block_r) *block_r = blk ? M.blk_r : 1;
-  if (block_c) *block_c = blk ? M.blk_c : 1;
+  if (block_r) *block_r = dict ? M.pd_br : blk ? M.blk_r : 1;
+  if (block_c) *block_c = dict ? M.pd_bc : blk ? M.blk_c : 1;
   if (value_dict) *value_dict = dict ? 1 : 0;
   if (matrix_bytes) {
     const int br = blk ? M.blk_r : 1, bc = blk ? M.blk_c : 1;

@@ -166,6 +166,7 @@ int spmv_tma_tile_rows();
 bool csr_try_block_index(struct Csr &A, int br, int bc); // build the block-compressed column index if the pattern allows
 void csr_drop_value_dict(struct Csr &A);                 // the values changed: forget the value dictionary (rebuilt lazily)
 bool csr_spmv_tma(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list = nullptr, int nlist = 0);
+bool csr_spmv_pd(const struct Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi); // tile-local dictionaries; false: matrix has none
 
 struct Csr {
   Ctx *ctx = nullptr;
@@ -197,6 +198,7 @@ struct Csr {
   mutable DevBuf<int> pd_gstart, pd_goff;     // first tile / blob offset (16-byte units) of every group of consecutive tiles (one group per pipeline stage)
   mutable std::vector<int> h_pd_gstart;
   mutable int dict_state = 0, pd_cap = 0, pd_ngroups = 0, dict_rows = 0; // pd_cap: largest group (bytes); dict_rows: rows per tile
+  mutable int pd_br = 1, pd_bc = 1;           // block shape the blobs were built for
   mutable int64_t dict_bytes = 0;
   bool no_value_dict = false;                 // b200sp_mat_set_spmv_format: keep the plain value stream
   // tile order for kernels that wait for the halo themselves: tiles (of wait_order_rows rows) without ghost columns first

@@ -290,6 +290,8 @@ static bool csr_spmv_launch(const Csr &A, const double *x, double *y, SpmvEpi &e
   if (A.kernel == SPMV_TMA && csr_spmv_tma(A, xs, y, epi)) return epi.push.grp != nullptr;
   epi.push = PushOut(); // the kernels below do not push
   if (pending_wait) { A.halo->end(); xs.wait_flags = nullptr; } // the TMA kernel declined: wait with the separate kernel
+  // long rows with repeating values (the 3-D operators: 81 entries per row): scalar-row tile dictionaries
+  if ((A.kernel == SPMV_NODE || A.kernel == SPMV_VECTOR) && A.max_row_nnz <= 96 && csr_spmv_pd(A, xs, y, epi)) return false;
   if (A.kernel == SPMV_STREAM || A.kernel == SPMV_TMA) {
     int tile = (A.max_group_nnz + 1) & ~1;
     size_t smem = (size_t)tile * sizeof(double) * STREAM_WARPS;

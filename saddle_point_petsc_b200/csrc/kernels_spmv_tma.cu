@@ -254,8 +254,10 @@ __global__ void k_spmv_tma_blk(int nrows, int ntiles, const int *__restrict__ ti
 // instead of random entries of a tile-wide dictionary (the measured limiter of the previous format: 40 % of the
 // shared-memory wavefronts were bank-conflict replays).  Matrices whose tiles do not compress keep the plain streams.
 constexpr int PD_NB = 128;         // block rows per tile (= blockDim.x of the SpMV kernel)
-constexpr int PD_MAX_K = 16;       // blocks per block row
-constexpr int PD_MAX_DICT = 2048;  // (position, value) pairs per tile
+constexpr int PD_MAX_K = 16;       // blocks per block row (node-block matrices)
+constexpr int PD_MAX_K_SCALAR = 96; // entries per row of a scalar (1 x 1) matrix: covers the 81 of the 3-D operators
+template <int BR, int BC> __host__ __device__ constexpr int pd_max_k() { return BR * BC == 1 ? PD_MAX_K_SCALAR : PD_MAX_K; }
+constexpr int PD_MAX_DICT = 3072;  // (position, value) pairs per tile
 
 __host__ __device__ inline int pd_pad16(int bytes) { return (bytes + 15) & ~15; }
 // rel: what the pattern's block-column offsets are relative to.  0: the block row index itself (square stencil matrices:
@@ -417,13 +419,16 @@ __global__ void __launch_bounds__(PD_NB) k_spmv_pd(int nbrows, const int *__rest
 // k_blk_check when BR*BC > 1.
 template <int BR, int BC>
 __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-                                                  int write, int rel, int *tsize16, const int *__restrict__ toff, unsigned char *blob, int *stat) {
+                                                  int write, int rel, int KS, int *tsize16, const int *__restrict__ toff, unsigned char *blob, int *stat) {
+  // KS: capacity in blocks per row of the shared arrays (>= the longest row of THIS matrix, odd so that KS + 1 is even and
+  // the 8-byte array behind s_delta stays aligned); the static per-position arrays are sized for the template's maximum
   extern __shared__ __align__(16) unsigned char s_raw[];
-  constexpr int BRBC = BR * BC, PMAX = PD_MAX_K * BRBC;
-  int *s_delta = reinterpret_cast<int *>(s_raw);                                                   // [PD_NB][PD_MAX_K + 1]: nb, offsets
-  unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_delta + PD_NB * (PD_MAX_K + 1)); // [PMAX][PD_NB] value bits
-  unsigned char *s_first = reinterpret_cast<unsigned char *>(s_val + (size_t)PMAX * PD_NB);         // [PMAX][PD_NB] first row with this value
-  unsigned char *s_rank = s_first + (size_t)PMAX * PD_NB;                                          // [PMAX][PD_NB] rank of a first occurrence
+  constexpr int BRBC = BR * BC, PMAX = pd_max_k<BR, BC>() * BRBC;
+  const int PS = KS * BRBC;
+  int *s_delta = reinterpret_cast<int *>(s_raw);                                                   // [PD_NB][KS + 1]: nb, offsets
+  unsigned long long *s_val = reinterpret_cast<unsigned long long *>(s_delta + PD_NB * (KS + 1));  // [PS][PD_NB] value bits
+  unsigned char *s_first = reinterpret_cast<unsigned char *>(s_val + (size_t)PS * PD_NB);           // [PS][PD_NB] first row with this value
+  unsigned char *s_rank = s_first + (size_t)PS * PD_NB;                                            // [PS][PD_NB] rank of a first occurrence
   __shared__ int s_pfirst[PD_NB], s_prank[PD_NB], s_cnt[PMAX], s_posoff[PMAX + 1], s_w[4], s_base[PD_NB];
   __shared__ unsigned long long s_hkey[8][256];
   __shared__ int s_hmin[8][256];
@@ -438,14 +443,14 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
     if (I < nbrows) {
       const int rs = rowptr[I * BR];
       nb = (rowptr[I * BR + 1] - rs) / BC;
-      if (nb > PD_MAX_K) { s_bad = 1; nb = 0; }
+      if (nb > KS) { s_bad = 1; nb = 0; }
       const int ref = rel ? (nb > 0 ? col[rs] / BC : 0) : I;
       s_base[tid] = ref;
-      for (int k = 0; k < nb; ++k) s_delta[tid * (PD_MAX_K + 1) + 1 + k] = col[rs + k * BC] / BC - ref;
+      for (int k = 0; k < nb; ++k) s_delta[tid * (KS + 1) + 1 + k] = col[rs + k * BC] / BC - ref;
     } else {
       s_base[tid] = 0;
     }
-    s_delta[tid * (PD_MAX_K + 1)] = nb;
+    s_delta[tid * (KS + 1)] = nb;
     atomicMax(&s_nbmax, nb);
   }
   __syncthreads();
@@ -458,15 +463,15 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
   for (int idx = tid; idx < P * PD_NB; idx += 256) {
     const int p = idx / PD_NB, i = idx % PD_NB, k = p / BRBC, e = p % BRBC, rr = e / BC, cc = e % BC;
     unsigned long long bits = 0ull;
-    if (k < s_delta[i * (PD_MAX_K + 1)]) bits = (unsigned long long)__double_as_longlong(val[rowptr[(I0 + i) * BR + rr] + k * BC + cc]);
+    if (k < s_delta[i * (KS + 1)]) bits = (unsigned long long)__double_as_longlong(val[rowptr[(I0 + i) * BR + rr] + k * BC + cc]);
     s_val[idx] = bits;
   }
   // column patterns: first row with the same {nb, offsets}
   if (tid < PD_NB) {
-    const int *mine = s_delta + tid * (PD_MAX_K + 1);
+    const int *mine = s_delta + tid * (KS + 1);
     int first = tid;
     for (int j = 0; j < tid; ++j) {
-      const int *o = s_delta + j * (PD_MAX_K + 1);
+      const int *o = s_delta + j * (KS + 1);
       bool same = o[0] == mine[0];
       for (int k = 0; k < mine[0] && same; ++k) same = o[1 + k] == mine[1 + k];
       if (same) { first = j; break; }
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
     for (int c = 0; c < PD_NB / 32; ++c) {
       const int i = c * 32 + lane;
       slot[c] = -1;
-      if (k < s_delta[i * (PD_MAX_K + 1)]) {
+      if (k < s_delta[i * (KS + 1)]) {
         const unsigned long long v = s_val[p * PD_NB + i];
         if (v == ~0ull) { s_bad = 1; continue; } // the one bit pattern the set cannot hold (a NaN payload): no dictionary
         unsigned h = (unsigned)((v * 0x9E3779B97F4A7C15ull) >> 56);
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(256) k_pd_build(int nbrows, const int *__restr
   if (tid < PD_NB) {
     out[L.o_pid + tid] = (unsigned char)s_prank[s_pfirst[tid]];
     if (s_pfirst[tid] == tid) {
-      const int *mine = s_delta + tid * (PD_MAX_K + 1);
+      const int *mine = s_delta + tid * (KS + 1);
       int *q = pat + s_prank[tid] * (nbmax + 1);
       q[0] = mine[0];
       for (int k = 0; k < nbmax; ++k) q[1 + k] = k < mine[0] ? mine[1 + k] : 0;
@@ -723,11 +728,14 @@ static bool build_pd_mode(const Csr &A, int force, int rel, bool only_if_small) 
   const int nbrows = A.nrows / BR, ntiles = (nbrows + PD_NB - 1) / PD_NB;
   DevBuf<int> tsize((size_t)ntiles + 1), stat(2);
   stat.zero(c->stream);
-  constexpr int PMAX = PD_MAX_K * BR * BC;
-  const size_t smem = (size_t)PD_NB * (PD_MAX_K + 1) * 4 + (size_t)PMAX * PD_NB * 10;
+  // capacity of the build kernel's shared arrays: the longest row of this matrix (odd), at most the template's maximum
+  int KS = (A.max_row_nnz + BC - 1) / BC;
+  if (KS > pd_max_k<BR, BC>()) return false;
+  KS |= 1;
+  const size_t smem = (size_t)PD_NB * (KS + 1) * 4 + (size_t)KS * BR * BC * PD_NB * 10;
   // (the attribute is per device and this kernel has four instantiations: set it on every build, setup path only)
   B2_CUDA(cudaFuncSetAttribute(k_pd_build<BR, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 0, rel, tsize.p, nullptr, nullptr, stat.p); check_launch("k_pd_build"); }
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 0, rel, KS, tsize.p, nullptr, nullptr, stat.p); check_launch("k_pd_build"); }
   int h_stat[2] = {0, 0};
   B2_CUDA(cudaMemcpyAsync(h_stat, stat.p, sizeof(h_stat), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
@@ -743,7 +751,7 @@ static bool build_pd_mode(const Csr &A, int force, int rel, bool only_if_small) 
   A.pd_off = std::move(off);
   A.pd_blob.alloc((size_t)total16 * 16 + 256);
   A.pd_blob.zero(c->stream);
-  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 1, rel, nullptr, A.pd_off.p, A.pd_blob.p, stat.p); check_launch("k_pd_build"); }
+  { LaunchScope ls(c, "setup"); k_pd_build<BR, BC><<<ntiles, 256, smem, c->stream>>>(nbrows, A.rowptr.p, A.col.p, A.val.p, 1, rel, KS, nullptr, A.pd_off.p, A.pd_blob.p, stat.p); check_launch("k_pd_build"); }
   c->sync();
   { // groups of consecutive tiles, ~8 KB of blobs and at most 8 tiles each (measured: profiles/r02_pd_group_sweep.txt);
     // the stage capacity is the largest group
@@ -797,10 +805,11 @@ static void build_value_dict(const Csr &A) {
   A.dict_state = -1;
   if (off || A.no_value_dict || A.nrows == 0 || A.nnz < 4096) return;
   const int br = A.bcol.p ? A.blk_r : 1, bc = A.bcol.p ? A.blk_c : 1;
-  if (br == 2 && bc == 2) build_pd<2, 2>(A, force);
-  else if (br == 2 && bc == 1) build_pd<2, 1>(A, force);
-  else if (br == 1 && bc == 2) build_pd<1, 2>(A, force);
-  else build_pd<1, 1>(A, force);
+  A.pd_br = A.pd_bc = 1;
+  if (br == 2 && bc == 2) { A.pd_br = 2; A.pd_bc = 2; build_pd<2, 2>(A, force); }
+  else if (br == 2 && bc == 1) { A.pd_br = 2; A.pd_bc = 1; build_pd<2, 1>(A, force); }
+  else if (br == 1 && bc == 2) { A.pd_br = 1; A.pd_bc = 2; build_pd<1, 2>(A, force); }
+  else build_pd<1, 1>(A, force); // scalar rows: also the 3 x 3 / 1 x 3 node-block matrices of the 3-D problem
 }
 void csr_drop_value_dict(Csr &A) {
   A.pd_blob.release(); A.pd_off.release();
@@ -839,43 +848,18 @@ static int ctas_per_sm(K kernel, size_t smem, int threads) {
   return std::min(n, ctas_per_sm(smem, threads));
 }
 
-bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list, int nlist) {
+// SpMV through the tile-local pattern/value dictionaries.  Builds them lazily (never while a CUDA graph is being recorded);
+// returns false when the matrix has none (declined, or not built yet during a capture) -- the caller then uses its plain kernel.
+// Serves the short-row matrices of the TMA class and, as scalar rows of up to 96 entries, the long-row 3-D operators.
+bool csr_spmv_pd(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi) {
   Ctx *c = A.ctx;
-  const size_t budget = 225 * 1024;
-  int R = 0, stages = 0, cap = 0;
-  static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;           // tuning overrides
-  static const int env_S = getenv("B200SP_TMA_STAGES") ? atoi(getenv("B200SP_TMA_STAGES")) : 0;
-  static const int env_U = getenv("B200SP_TMA_UNROLL") ? atoi(getenv("B200SP_TMA_UNROLL")) : 0;
-  // Measured on B200 (profiles/r01_tma_tile_sweep.txt): small tiles with exactly two stages and as many
-  // co-resident CTAs as shared memory allows beat large tiles / deeper pipelines for every block
-  // (A 18 nnz/row: R=128,S=2 -> 97% of the measured HBM peak; R=512,S=2 -> 93%; any S>=3 -> <= 62%).
-  for (int r : {128, 256, 512}) {
-    if (env_R && r != env_R) continue;
-    const int capr = (((r / 32) * A.max_group_nnz + 8) + 3) & ~3;
-    const size_t sb = (size_t)capr * 12;
-    int s = (int)((budget - 64) / sb);
-    if (s >= 2) { R = r; stages = 2; cap = capr; if (env_S && env_S <= s && env_S <= TMA_MAX_STAGES) stages = env_S; break; }
-    if (!env_R) break; // rows too long for a 128-row tile: the vector kernel is the right tool
-  }
-  if (!R) return false;
-  const size_t smem = (size_t)cap * 12 * stages + 8 * TMA_MAX_STAGES;
-  if (!(c->attr_mask & 4u)) {
-    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    c->attr_mask |= 4u;
-  }
-  if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
-  const int ntiles = tile_list ? nlist : (A.nrows + R - 1) / R;
-  if (ntiles <= 0) return true;
-  const int per_sm = (env_U ? env_U == 6 : true) ? ctas_per_sm(k_spmv_tma<6>, smem, R) : ctas_per_sm(k_spmv_tma<3>, smem, R);
-  int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
   if (A.dict_state == 0) { // lazily, never while a CUDA graph is being recorded
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     B2_CUDA(cudaStreamIsCapturing(c->stream, &st));
     if (st == cudaStreamCaptureStatusNone) build_value_dict(A);
   }
-  const int dbr = A.bcol.p ? A.blk_r : 1, dbc = A.bcol.p ? A.blk_c : 1;
-  if (A.dict_state == 1 && !tile_list && (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // tile-local dictionaries, one thread per block row
+  const int dbr = A.pd_br, dbc = A.pd_bc; // the block shape the blobs were built for (1 x 1 for shapes without a pd kernel, e.g. 3 x 3)
+  if (A.dict_state == 1 && (dbc == 1 || (reinterpret_cast<uintptr_t>(xs.x) & 15) == 0)) { // one thread per block row
     static const int env_st = getenv("B200SP_PD_STAGES") ? atoi(getenv("B200SP_PD_STAGES")) : 0;
     const int pd_stages = env_st >= 2 && env_st <= TMA_MAX_STAGES ? env_st : 2;
     const size_t smem_d = (size_t)A.pd_cap * pd_stages + 8 * TMA_MAX_STAGES;
@@ -920,6 +904,40 @@ bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, c
     check_launch("k_spmv_pd");
     return true;
   }
+  return false;
+}
+
+bool csr_spmv_tma(const Csr &A, const XSrc &xs, double *y, const SpmvEpi &epi, const int *tile_list, int nlist) {
+  Ctx *c = A.ctx;
+  const size_t budget = 225 * 1024;
+  int R = 0, stages = 0, cap = 0;
+  static const int env_R = getenv("B200SP_TMA_R") ? atoi(getenv("B200SP_TMA_R")) : 0;           // tuning overrides
+  static const int env_S = getenv("B200SP_TMA_STAGES") ? atoi(getenv("B200SP_TMA_STAGES")) : 0;
+  static const int env_U = getenv("B200SP_TMA_UNROLL") ? atoi(getenv("B200SP_TMA_UNROLL")) : 0;
+  // Measured on B200 (profiles/r01_tma_tile_sweep.txt): small tiles with exactly two stages and as many
+  // co-resident CTAs as shared memory allows beat large tiles / deeper pipelines for every block
+  // (A 18 nnz/row: R=128,S=2 -> 97% of the measured HBM peak; R=512,S=2 -> 93%; any S>=3 -> <= 62%).
+  for (int r : {128, 256, 512}) {
+    if (env_R && r != env_R) continue;
+    const int capr = (((r / 32) * A.max_group_nnz + 8) + 3) & ~3;
+    const size_t sb = (size_t)capr * 12;
+    int s = (int)((budget - 64) / sb);
+    if (s >= 2) { R = r; stages = 2; cap = capr; if (env_S && env_S <= s && env_S <= TMA_MAX_STAGES) stages = env_S; break; }
+    if (!env_R) break; // rows too long for a 128-row tile: the vector kernel is the right tool
+  }
+  if (!R) return false;
+  const size_t smem = (size_t)cap * 12 * stages + 8 * TMA_MAX_STAGES;
+  if (!(c->attr_mask & 4u)) {
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    c->attr_mask |= 4u;
+  }
+  if (tile_list && R != TMA_TILE_ROWS) return false; // the lists were built for TMA_TILE_ROWS-row tiles
+  const int ntiles = tile_list ? nlist : (A.nrows + R - 1) / R;
+  if (ntiles <= 0) return true;
+  const int per_sm = (env_U ? env_U == 6 : true) ? ctas_per_sm(k_spmv_tma<6>, smem, R) : ctas_per_sm(k_spmv_tma<3>, smem, R);
+  int grid = ntiles < c->num_sms * per_sm ? ntiles : c->num_sms * per_sm;
+  if (!tile_list && csr_spmv_pd(A, xs, y, epi)) return true; // tile-local dictionaries (built lazily)
   int n_nowait = 0;
   if (xs.wait_flags && !tile_list) { ensure_wait_order(A, R); if (A.wait_order_rows == R) { tile_list = A.wait_order.p; n_nowait = A.wait_n_nowait; } }
   if (A.bcol.p) { // block-compressed column index: 8 + 4/(BR*BC) bytes per nonzero (R is a multiple of BR)
