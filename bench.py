@@ -341,9 +341,6 @@ def main():
     # line on stdout.  Everything else goes to stderr: fd 1 is pointed at fd 2 and the result is written to the
     # saved descriptor at the end.
     global _REAL_STDOUT
-    # load every kernel of libb200sp.so when the CUDA context is created, not lazily at its first launch: otherwise the
-    # first process on a fresh box charges ~0.25 s of module loading to `assembly_s` / `ksp_setup_s` (measured 0.08 vs 0.32 s)
-    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
@@ -408,6 +405,16 @@ def main():
     if world > 1 and not args.no_dist_check and args.config not in CONFIGS_3D:
         dcheck = dist_check(sp, ctx, dist)
         barrier()
+    # CUDA loads kernels lazily at their first launch: run the whole path once on a tiny grid so that `assembly_s` and
+    # `ksp_setup_s` below measure the work, not ~0.25 s of first-launch module loading (measured 0.32 vs 0.08 s on a fresh box)
+    if args.config not in CONFIGS_3D:
+        wp = sp.SaddlePointProblem(ctx, 32, 32, kkt=True, rhs_kind=1)
+        wk = wp.make_ksp(options_for(args.config, 32))
+        wk.solve(wp.rhs, sp.Vec(ctx, wp.n))
+        wk.destroy()
+        del wp, wk
+    ctx.synchronize()
+    barrier()
     t0 = time.perf_counter()
     prob = make_problem(sp, ctx, args.config, args.nx)
     ctx.synchronize()
