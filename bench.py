@@ -407,7 +407,8 @@ def main():
         barrier()
     # CUDA loads kernels lazily at their first launch: run the whole path once on a tiny grid so that `assembly_s` and
     # `ksp_setup_s` below measure the work, not ~0.25 s of first-launch module loading (measured 0.32 vs 0.08 s on a fresh box)
-    if args.config not in CONFIGS_3D:
+    # (N > 1: dist_check above has already run every kernel)
+    if args.config not in CONFIGS_3D and world == 1:
         wp = sp.SaddlePointProblem(ctx, 32, 32, kkt=True, rhs_kind=1)
         wk = wp.make_ksp(options_for(args.config, 32))
         wk.solve(wp.rhs, sp.Vec(ctx, wp.n))
