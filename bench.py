@@ -405,13 +405,15 @@ def main():
     if world > 1 and not args.no_dist_check and args.config not in CONFIGS_3D:
         dcheck = dist_check(sp, ctx, dist)
         barrier()
-    # CUDA loads kernels lazily at their first launch: run the whole path once on a tiny grid so that `assembly_s` and
-    # `ksp_setup_s` below measure the work, not ~0.25 s of first-launch module loading (measured 0.32 vs 0.08 s on a fresh box)
+    # A fresh box starts cold (lazy kernel loading, clocks, allocator): run the whole path once on a 1M-DOF grid so that
+    # `assembly_s` and `ksp_setup_s` below measure the work (measured on a fresh box: 0.32 s cold vs 0.08 s warm)
     # (N > 1: dist_check above has already run every kernel)
     if args.config not in CONFIGS_3D and world == 1:
-        wp = sp.SaddlePointProblem(ctx, 32, 32, kkt=True, rhs_kind=1)
-        wk = wp.make_ksp(options_for(args.config, 32))
-        wk.solve(wp.rhs, sp.Vec(ctx, wp.n))
+        wnx = 576 if args.nx >= 576 else 32
+        wp = sp.SaddlePointProblem(ctx, wnx, wnx, kkt=True, rhs_kind=1)
+        wk = wp.make_ksp(options_for(args.config, wnx))
+        for _ in range(3):
+            wk.solve(wp.rhs, sp.Vec(ctx, wp.n))
         wk.destroy()
         del wp, wk
     ctx.synchronize()
