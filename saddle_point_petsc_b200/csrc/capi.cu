@@ -522,6 +522,7 @@ int b200sp_mat_set_spmv_format(b200sp_mat A, int block_index, int value_dict) {
   use_device(M.ctx);
   M.ctx->sync();
   csr_drop_value_dict(M);
+  M.state++; // derived storage changed: a KSP that recorded CUDA graphs on the old storage sets up again at its next solve
   M.no_value_dict = value_dict == 0;
   if (!block_index) { M.bcol.release(); M.bptr.release(); M.blk_r = M.blk_c = 1; }
   else if (!M.bcol.p && M.dof_r > 0 && M.dof_c > 0 && M.dof_r * M.dof_c > 1) csr_try_block_index(M, M.dof_r, M.dof_c);
