@@ -613,7 +613,9 @@ def main():
     secondary = None
     if world == 1 and not args.no_secondary and args.config == "fgmres_schur_mg":
         secondary = []
-        for name, nx2 in (("gmres_schur_mg", 576), ("fgmres_schur_lsc", 96), ("minres_diag_mg", args.nx)):
+        # config 2 with multigrid (1M DOF) and AS NAMED with plain Jacobi for A00 (at the size where it still converges),
+        # config 3 AS NAMED (LSC, largest size converging in <= 500 iterations), config 4's solver in 2-D at the full size
+        for name, nx2 in (("gmres_schur_mg", 576), ("gmres_schur_jacobi", 64), ("fgmres_schur_lsc", 96), ("minres_diag_mg", args.nx)):
             try:
                 secondary.append(secondary_config(sp, ctx, name, nx2))
             except Exception as e:  # noqa: BLE001
