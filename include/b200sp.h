@@ -167,6 +167,15 @@ int b200sp_mat_matmult(b200sp_mat A, b200sp_mat B, b200sp_mat *C);          /* M
 int b200sp_mat_scale_columns(b200sp_mat A, b200sp_vec d, b200sp_mat *C);
 int b200sp_mat_add_scaled(b200sp_mat A, double s, b200sp_mat B, b200sp_mat *C);
 /* MatZeroRowsColumns(A,n,rows,diag,NULL,NULL): local row ids; pattern preserved (Appendix A.4) */
+/* Aggregation multigrid set-up (-pc_type gamg; PETSc analogue PCGAMG, -pc_gamg_type agg).
+ * aggregate: agg_host[node] = aggregate id of every bs-dof node of the square matrix A, -1 for nodes without
+ * neighbours (the identity rows MatZeroRowsColumns leaves, src/Discretization.c:268); *nagg = number of aggregates.
+ * prolongator: P = P_t - omega D^-1 A P_t with P_t[(i,c),(agg(i),c)] = sqrt(w_i / W_agg(i))   (omega = 0: P_t itself);
+ * node_weight[i] = w_i = number of finest-level nodes behind node i (NULL: ones, i.e. A is the finest level),
+ * coarse_weight[a] = W_a = sum of w over aggregate a (NULL: not wanted).
+ * The algorithm is defined by oracle/sp_oracle_amg.c; aggregates, weights and P_t are bit-identical to it. */
+int b200sp_amg_aggregate(b200sp_mat A, int bs, double theta, int *agg_host, int *nagg);
+int b200sp_amg_prolongator(b200sp_mat A, int bs, double theta, double omega, const int *node_weight, int *coarse_weight, b200sp_mat *P);
 int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag);
 int b200sp_mat_zero_rows(b200sp_mat A, int n, const int *rows, double diag); /* MatZeroRows (diag only if square) */
 int b200sp_mat_zero_columns(b200sp_mat A, int n, const int *cols);

@@ -35,8 +35,8 @@ KspP = C.POINTER(KspStruct)
 
 def build(force=False):
     so = os.path.join(_HERE, "libsp_oracle.so")
-    src = os.path.join(_HERE, "sp_oracle.c")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+    srcs = [os.path.join(_HERE, f) for f in ("sp_oracle.c", "sp_oracle3d.c", "sp_oracle_amg.c", "sp_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsp_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -91,6 +91,11 @@ def lib():
     sig("or_element_constraints", None, c_dp, c_dp)
     sig("or_zero_rows", None, CsrP, C.c_int, c_ip)
     sig("or_zero_cols", None, CsrP, C.c_int, c_ip)
+    sig("or_amg_aggregate", C.c_int, CsrP, C.c_int, C.c_double, c_ip)
+    sig("or_amg_tentative", CsrP, C.c_int, C.c_int, c_ip, C.c_int, c_ip, c_ip)
+    sig("or_csr_scale_rows", CsrP, CsrP, c_dp)
+    sig("or_amg_smooth_prolongator", CsrP, CsrP, CsrP, C.c_double)
+    sig("or_amg_galerkin", CsrP, CsrP, CsrP)
     sig("or_interp_q1", CsrP, C.c_int, C.c_int, C.c_int, C.c_int)
     sig("or_op_apply", None, vp, c_dp, c_dp)
     sig("or_op_free", None, vp)
@@ -322,6 +327,42 @@ class Problem3D:
         return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy()]], format="csr")
 
 
+def amg_aggregate(mat, bs, theta=0.0):
+    """(aggregate id per node, -1 = left out; number of aggregates) -- or_amg_aggregate."""
+    nn = mat.nrows // bs
+    agg = np.zeros(max(nn, 1), dtype=np.int32)
+    nagg = lib().or_amg_aggregate(mat.ptr, bs, float(theta), iptr(agg))
+    return agg[:nn], nagg
+
+
+def amg_hierarchy(mat, bs, theta=0.0, nsmooths=1, coarse_limit=50, max_levels=30):
+    """Level matrices [A_0 .. A_L], prolongators [P_0 .. P_{L-1}] (P_l: level l+1 -> l) and the aggregates per level."""
+    L = lib()
+    mats, interps, aggs = [mat], [], []
+    w = None   # finest-level nodes behind every node of the current level (None: ones)
+    while len(mats) < max_levels and mats[-1].nrows > coarse_limit:
+        A = mats[-1]
+        n = A.nrows
+        agg, nagg = amg_aggregate(A, bs, theta)
+        if nagg == 0 or nagg * bs >= n:
+            break
+        wc = np.zeros(nagg, dtype=np.int32)
+        Pt = Csr(L.or_amg_tentative(n // bs, bs, iptr(agg), nagg, iptr(w) if w is not None else None, iptr(wc)))
+        if nsmooths:
+            Aop = L.or_op_csr(A.ptr)
+            Jop = L.or_op_jacobi(A.ptr)
+            lam = L.or_estimate_lambda_max(Aop, Jop, 10)
+            L.or_op_free(Aop); L.or_op_free(Jop)
+            P = Csr(L.or_amg_smooth_prolongator(A.ptr, Pt.ptr, 4.0 / (3.0 * lam)))
+        else:
+            P = Pt
+        interps.append(P)
+        aggs.append((agg, nagg, w))
+        w = wc
+        mats.append(Csr(L.or_amg_galerkin(A.ptr, P.ptr)))
+    return mats, interps, aggs
+
+
 # ------------------------------------------------------------- option wiring
 KSP_TYPES = {"preonly": 0, "richardson": 1, "chebyshev": 2, "gmres": 3, "fgmres": 4, "minres": 5}
 FACT = {"diag": 0, "lower": 1, "upper": 2, "full": 3}
@@ -419,6 +460,8 @@ class Solver:
             op = L.or_op_dense_lu(mat.ptr)
         elif t == "mg":
             op = self._make_mg(prefix, mat, grid, dof)
+        elif t == "gamg":
+            op = self._make_gamg(prefix, mat, dof)
         else:
             raise ValueError("oracle: unsupported pc_type %r for %r" % (t, prefix))
         self.keep.append(op)
@@ -443,6 +486,13 @@ class Solver:
                 raise ValueError("oracle mg: only the velocity block (dof 2) is rediscretised")
             mats.append(Ac)
             Ml, Nl = Mc, Nc
+        return self._mg_from_levels(prefix, mats, interps)
+
+    def _mg_from_levels(self, prefix, mats, interps):
+        """or_op_mg on given level matrices / prolongators with the -<prefix>mg_levels_ smoothers and a dense coarse solve."""
+        L = self.L
+        nlev = len(mats)
+        smooth = []
         self.keep += mats + interps
         for l in range(nlev - 1):
             Aop = L.or_op_csr(mats[l].ptr)
@@ -459,11 +509,20 @@ class Solver:
         smooth.append(KspP())
         coarse = L.or_op_dense_lu(mats[-1].ptr)
         self.keep.append(coarse)
-        self.mg_smooth = smooth
+        self.mg_smooth = getattr(self, "mg_smooth", []) + smooth
         Aarr = (CsrP * nlev)(*[m.ptr for m in mats])
         Parr = (CsrP * nlev)(*([p.ptr for p in interps] + [CsrP()]))
         Sarr = (KspP * nlev)(*smooth)
         return L.or_op_mg(nlev, Aarr, Parr, Sarr, coarse)
+
+    def _make_gamg(self, prefix, mat, bs):
+        """Aggregation multigrid (sp_oracle_amg.c): levels by MIS-2 aggregation until n <= -pc_gamg_coarse_eq_limit."""
+        mats, interps, self.gamg_aggregates = amg_hierarchy(
+            mat, bs, theta=float(self._get(prefix + "pc_gamg_threshold", 0.0)),
+            nsmooths=int(self._get(prefix + "pc_gamg_agg_nsmooths", 1)),
+            coarse_limit=int(self._get(prefix + "pc_gamg_coarse_eq_limit", 50)),
+            max_levels=int(self._get(prefix + "pc_mg_levels", 30)))
+        return self._mg_from_levels(prefix, mats, interps)
 
     def _make_pc(self, prefix, prob):
         L = self.L

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sp.so")
-SOURCES = ["kernels_vec.cu", "kernels_spmv.cu", "kernels_spmv_tma.cu", "kernels_setup.cu", "kernels_assembly.cu", "kernels_assembly3d.cu", "dist.cu", "dist_spgemm.cu", "solver.cu", "capi.cu"]
+SOURCES = ["kernels_vec.cu", "kernels_spmv.cu", "kernels_spmv_tma.cu", "kernels_setup.cu", "kernels_assembly.cu", "kernels_assembly3d.cu", "kernels_amg.cu", "dist.cu", "dist_spgemm.cu", "solver.cu", "capi.cu"]
 HEADERS = ["core.h", "dev.cuh", "solver.h", "nccl_dyn.h", "dist.h", os.path.join("..", "..", "include", "b200sp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -233,7 +233,7 @@ void MgOp::cycle(int l, const double *b, double *x) {
 void MgOp::apply(const double *b, double *x) { cycle(0, b, x); } // level 0 works on the caller's vectors: no copies
 std::string MgOp::view(int indent) const {
   std::ostringstream o;
-  o << pad(indent) << "PC mg: multiplicative V-cycle, " << lev.size() << " levels (rediscretised coarse operators, Q1 interpolation)\n";
+  o << pad(indent) << "PC mg: multiplicative V-cycle, " << lev.size() << " levels (" << kind << ")\n";
   for (size_t l = 0; l < lev.size(); ++l) {
     o << pad(indent + 1) << "level " << l << ": n=" << lev[l]->A->nrows << " nnz=" << lev[l]->A->nnz << "\n";
     if (lev[l]->smooth) o << lev[l]->smooth->view(indent + 3);
@@ -769,12 +769,13 @@ Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, 
   // on this library's kernel list: an unspecified -pc_type is an error, not a silent substitute
   if (!has(prefix + "pc_type") && std::string(default_type) == "petsc-default")
     throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "pc_type not given: PETSc would use ILU(0) here, which this library does not provide; "
-                                        "choose one of none, jacobi, mg, lu" + (prefix.empty() ? ", fieldsplit" : ""));
+                                        "choose one of none, jacobi, mg, gamg, lu" + (prefix.empty() ? ", fieldsplit" : ""));
   const std::string t = opt(prefix + "pc_type", default_type);
   if (t == "none") return nullptr;
   if (t == "jacobi") return add_op<JacobiOp>(*mat);
   if (t == "lu") return add_op<DenseInvOp>(*mat);
   if (t == "mg") return make_mg(prefix, mat);
+  if (t == "gamg") return make_gamg(prefix, mat);
   throw Error(B200SP_ERR_UNSUPPORTED, "unsupported -" + prefix + "pc_type " + t);
 }
 
@@ -783,7 +784,7 @@ Op *Solver::make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, 
 // Builds levels [first .. first+nlev-1] of a single-rank (or replicated) hierarchy into mg; A0 may be null
 // (then the first level is assembled too).  local_only: the data is replicated on every rank, so the eigenvalue
 // estimates must not be all-reduced.
-static void smoother_setup(Solver *S, Ksp *k, const std::string &sp, Op *Aop, Op *jac, bool local_only,
+static double smoother_setup(Solver *S, Ksp *k, const std::string &sp, Op *Aop, Op *jac, bool local_only,
                            const std::map<std::string, std::string> &opts) {
   auto opt = [&](const std::string &key, const std::string &def) { S->used[key] = true; auto it = opts.find(key); return it == opts.end() ? def : it->second; };
   // PETSc's PCMG default smoother is Chebyshev + SOR; SOR is not on this library's kernel list, so the level PC is
@@ -800,6 +801,7 @@ static void smoother_setup(Solver *S, Ksp *k, const std::string &sp, Op *Aop, Op
   const double lam = estimate_lambda_max(S->ctx, Aop, jac, 10, local_only);
   k->emin = 0.1 * lam;
   k->emax = 1.1 * lam;
+  return lam;
 }
 
 void Solver::build_levels_single(MgOp *mg, std::shared_ptr<Csr> A0, int Ml, int Nl, int nlev, const std::string &prefix, bool local_only) {
@@ -924,6 +926,60 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
   mg->g_all.alloc((size_t)cnt_max * Lc.size + 2);
   mg->nat_b.alloc((size_t)2 * Lc.M * Lc.N + 2); mg->nat_x.alloc((size_t)2 * Lc.M * Lc.N + 2);
   ctx->sync();
+  return mg;
+}
+
+// PCGAMG analogue: smoothed-aggregation hierarchy built on the device (kernels_amg.cu) from the assembled block alone
+// -- no grid needed, so it also serves matrices that did not come from a DMDA (selfp / LSC products, user CSR).
+// Options (PETSc's names): -pc_gamg_threshold (0), -pc_gamg_agg_nsmooths (1), -pc_gamg_coarse_eq_limit (50),
+// -pc_mg_levels (30, the maximum), -pc_gamg_block_size (the matrix block size), smoothers under -mg_levels_.
+Op *Solver::make_gamg(const std::string &prefix, std::shared_ptr<Csr> mat) {
+  if (mat->halo || ctx->dcomm) throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "pc_type gamg: the aggregation set-up is single-rank; use -" + prefix + "pc_type mg on row-partitioned DMDA matrices");
+  B2_REQUIRE(mat->nrows == mat->ncols, "pc gamg: square matrix expected");
+  const int bs0 = mat->dof_r > 0 && mat->dof_r == mat->dof_c ? mat->dof_r : 1;
+  const int bs = std::stoi(opt(prefix + "pc_gamg_block_size", std::to_string(bs0)));
+  const double theta = std::stod(opt(prefix + "pc_gamg_threshold", "0"));
+  const int nsmooths = std::stoi(opt(prefix + "pc_gamg_agg_nsmooths", "1"));
+  const int coarse_limit = std::stoi(opt(prefix + "pc_gamg_coarse_eq_limit", "50"));
+  const int max_levels = std::stoi(opt(prefix + "pc_mg_levels", "30"));
+  B2_REQUIRE(nsmooths == 0 || nsmooths == 1, "pc gamg: -pc_gamg_agg_nsmooths must be 0 or 1");
+  B2_REQUIRE(max_levels >= 1 && coarse_limit >= 1, "pc gamg: bad -pc_mg_levels / -pc_gamg_coarse_eq_limit");
+  const std::string sp = prefix + "mg_levels_";
+  MgOp *mg = add_op<MgOp>(ctx, (int64_t)mat->nrows);
+  mg->kind = "smoothed aggregation, Galerkin coarse operators";
+  std::shared_ptr<Csr> Al = mat;
+  DevBuf<int> w, wc; // finest-level nodes behind every node of the current / next level (empty: ones)
+  for (;;) {
+    auto L = std::make_unique<MgOp::Level>();
+    L->A = Al;
+    L->b.alloc((size_t)Al->nrows + 2); L->x.alloc((size_t)Al->nrows + 2); L->r.alloc((size_t)Al->nrows + 2);
+    bool coarsen = (int)mg->lev.size() + 1 < max_levels && Al->nrows > coarse_limit;
+    DevBuf<int> agg;
+    int nagg = 0;
+    if (coarsen) {
+      nagg = amg_aggregate(*Al, bs, theta, agg);
+      if (nagg == 0 || (int64_t)nagg * bs >= Al->nrows) coarsen = false; // nothing left to aggregate: this level is the coarse one
+    }
+    if (!coarsen) { mg->lev.push_back(std::move(L)); break; }
+    L->jac = std::make_unique<JacobiOp>(*Al);
+    L->Aop = std::make_unique<CsrOp>(Al);
+    L->smooth = std::make_unique<Ksp>(ctx, sp);
+    const double lam = smoother_setup(this, L->smooth.get(), sp, L->Aop.get(), L->jac.get(), false, opts);
+    auto Pt = amg_tentative(ctx, Al->nrows / bs, bs, agg, nagg, w.p, wc);
+    w = std::move(wc);
+    // omega = 4 / (3 lambda), lambda = the smoother's estimate of lambda_max(D^-1 A)
+    L->P = nsmooths ? amg_smooth_prolongator(*Al, *Pt, 4.0 / (3.0 * lam)) : Pt;
+    L->R = csr_transpose(*L->P);
+    L->P->tag = "spmv:P"; L->R->tag = "spmv:R";
+    auto AP = csr_matmat(*Al, *L->P);
+    auto Ac = csr_matmat(*L->R, *AP);
+    Ac->tag = "spmv:A_coarse";
+    mg->lev.push_back(std::move(L));
+    Al = Ac;
+  }
+  B2_REQUIRE(mg->lev.back()->A->nrows <= 8192, "pc gamg: the coarsest level has " + std::to_string(mg->lev.back()->A->nrows) +
+             " rows, too many for the dense coarse solve; raise -" + prefix + "pc_mg_levels or lower -" + prefix + "pc_gamg_threshold");
+  mg->coarse = std::make_unique<DenseInvOp>(*mg->lev.back()->A);
   return mg;
 }
 

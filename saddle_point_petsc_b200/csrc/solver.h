@@ -124,6 +124,7 @@ struct MgOp : Op { // PCMG multiplicative V-cycle
   };
   std::vector<std::unique_ptr<Level>> lev;
   std::unique_ptr<DenseInvOp> coarse;
+  std::string kind = "rediscretised coarse operators, Q1 interpolation";
   // row-partitioned runs: `lev` holds the distributed smoothing levels; the levels below are replicated on every rank
   std::unique_ptr<MgOp> replicated;
   DevBuf<double> loc_b, loc_x, g_all, nat_b, nat_x;
@@ -231,6 +232,7 @@ private:
   Ksp *make_ksp(const std::string &prefix, Op *A, Op *M, const char *default_type);
   Op *make_simple_pc(const std::string &prefix, std::shared_ptr<Csr> mat, const char *default_type);
   Op *make_mg(const std::string &prefix, std::shared_ptr<Csr> mat);
+  Op *make_gamg(const std::string &prefix, std::shared_ptr<Csr> mat); // aggregation multigrid (kernels_amg.cu)
 
 public:
   void build_levels_single(MgOp *mg, std::shared_ptr<Csr> A0, int Ml, int Nl, int nlev, const std::string &prefix, bool local_only);
