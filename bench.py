@@ -62,6 +62,13 @@ CONFIGS = {
     "gmres_schur_jacobi": ("-ksp_type gmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -ksp_max_it 20000 -pc_type fieldsplit -pc_fieldsplit_type schur "
                            "-pc_fieldsplit_schur_fact_type full -pc_fieldsplit_schur_precondition user "
                            "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type jacobi -fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
+    # config 3's solver with the A00 hierarchy built algebraically (smoothed aggregation on the device)
+    # instead of from the grid: the route for matrices without a DMDA; one V-cycle per application like the default
+    "fgmres_schur_gamg": ("-ksp_type fgmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -ksp_max_it 2000 -pc_type fieldsplit -pc_fieldsplit_type schur "
+                          "-pc_fieldsplit_schur_fact_type upper -pc_fieldsplit_schur_precondition user "
+                          "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type gamg "
+                          "-fieldsplit_0_mg_levels_ksp_type chebyshev -fieldsplit_0_mg_levels_ksp_max_it 3 -fieldsplit_0_mg_levels_pc_type jacobi "
+                          "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
 }
 # BASELINE config 4: 3-D Stokes-type KKT (Q1 hexahedra, 4 dof per node), MINRES + block-diagonal preconditioner with a
 # Chebyshev/Jacobi A00 solve and the pressure-mass-matrix Schur approximation.  --nx = elements per side of the cube.
@@ -564,7 +571,7 @@ def main():
                   "max_rel_history_diff": hist_dev,
                   "tolerances": {"iterations": TOL_ITS, "rel_residual": TOL_RES, "solution": TOL_X}}
         tol_its, tol_x = TOL_ITS, TOL_X
-        if args.config in ("fgmres_schur_lsc", "gmres_schur_jacobi"):
+        if args.config in ("fgmres_schur_lsc", "gmres_schur_jacobi", "fgmres_schur_gamg"):
             # hundreds of unrefined classical-Gram-Schmidt steps on a weak preconditioner: the iteration COUNT itself moves by a
             # few percent under any change of summation order (the oracle moves by as much under a mathematically neutral
             # rescaling, tests/test_gpu_parity.py), and two valid rtol-1e-8 iterates then differ by about the last correction
@@ -615,7 +622,8 @@ def main():
         secondary = []
         # config 2 with multigrid (1M DOF) and AS NAMED with plain Jacobi for A00 (at the size where it still converges),
         # config 3 AS NAMED (LSC, largest size converging in <= 500 iterations), config 4's solver in 2-D at the full size
-        for name, nx2 in (("gmres_schur_mg", 576), ("gmres_schur_jacobi", 64), ("fgmres_schur_lsc", 96), ("minres_diag_mg", args.nx)):
+        for name, nx2 in (("gmres_schur_mg", 576), ("gmres_schur_jacobi", 64), ("fgmres_schur_lsc", 96), ("fgmres_schur_gamg", 576),
+                          ("minres_diag_mg", args.nx)):
             try:
                 secondary.append(secondary_config(sp, ctx, name, nx2))
             except Exception as e:  # noqa: BLE001

@@ -288,6 +288,6 @@ def test_gamg_large_grid_properties(ctx, spmod):
     assert rd["reason"] == 2 and rd["its"] <= 40
     # same solution as the geometric hierarchy's solve (both stop at rtol 1e-8 of their own preconditioned norm)
     x2 = sp.Vec(ctx, dev.n)
-    r2 = dev.make_ksp("-ksp_type gmres -ksp_rtol 1e-8 -pc_type mg -pc_mg_levels 4 -mg_levels_ksp_max_it 2").solve(dev.rhs, x2)
+    r2 = dev.make_ksp("-ksp_type gmres -ksp_rtol 1e-8 -pc_type mg -pc_mg_levels 6 -mg_levels_ksp_max_it 2").solve(dev.rhs, x2)
     assert r2["reason"] == 2
     assert np.max(np.abs(x.numpy() - x2.numpy())) <= 1e-5 * np.max(np.abs(x2.numpy()))
