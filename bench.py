@@ -66,7 +66,7 @@ CONFIGS = {
     # instead of from the grid: the route for matrices without a DMDA; one V-cycle per application like the default
     "fgmres_schur_gamg": ("-ksp_type fgmres -ksp_gmres_restart 30 -ksp_rtol 1e-8 -ksp_max_it 2000 -pc_type fieldsplit -pc_fieldsplit_type schur "
                           "-pc_fieldsplit_schur_fact_type upper -pc_fieldsplit_schur_precondition user "
-                          "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type gamg "
+                          "-fieldsplit_0_ksp_type preonly -fieldsplit_0_pc_type gamg -fieldsplit_0_pc_gamg_mis_ordering natural "
                           "-fieldsplit_0_mg_levels_ksp_type chebyshev -fieldsplit_0_mg_levels_ksp_max_it 3 -fieldsplit_0_mg_levels_pc_type jacobi "
                           "-fieldsplit_1_ksp_type preonly -fieldsplit_1_pc_type jacobi"),
 }

@@ -173,9 +173,11 @@ int b200sp_mat_add_scaled(b200sp_mat A, double s, b200sp_mat B, b200sp_mat *C);
  * prolongator: P = P_t - omega D^-1 A P_t with P_t[(i,c),(agg(i),c)] = sqrt(w_i / W_agg(i))   (omega = 0: P_t itself);
  * node_weight[i] = w_i = number of finest-level nodes behind node i (NULL: ones, i.e. A is the finest level),
  * coarse_weight[a] = W_a = sum of w over aggregate a (NULL: not wanted).
+ * order: priority of the independent-set selection, 0 = hashed node number (-pc_gamg_mis_ordering hash, the default),
+ * 1 = the node number itself (natural: regular aggregates on lexicographically numbered grids, O(grid side) rounds).
  * The algorithm is defined by oracle/sp_oracle_amg.c; aggregates, weights and P_t are bit-identical to it. */
-int b200sp_amg_aggregate(b200sp_mat A, int bs, double theta, int *agg_host, int *nagg);
-int b200sp_amg_prolongator(b200sp_mat A, int bs, double theta, double omega, const int *node_weight, int *coarse_weight, b200sp_mat *P);
+int b200sp_amg_aggregate(b200sp_mat A, int bs, double theta, int order, int *agg_host, int *nagg);
+int b200sp_amg_prolongator(b200sp_mat A, int bs, double theta, int order, double omega, const int *node_weight, int *coarse_weight, b200sp_mat *P);
 int b200sp_mat_zero_rows_columns(b200sp_mat A, int n, const int *rows, double diag);
 int b200sp_mat_zero_rows(b200sp_mat A, int n, const int *rows, double diag); /* MatZeroRows (diag only if square) */
 int b200sp_mat_zero_columns(b200sp_mat A, int n, const int *cols);

@@ -85,7 +85,7 @@ void or_assemble_constraints(int M, int N, OrCsr **B, OrCsr **Bt);            /*
 void or_zero_rows(OrCsr *A, int n, const int *rows);
 void or_zero_cols(OrCsr *A, int n, const int *cols);
 /* ---- aggregation multigrid set-up (sp_oracle_amg.c; ours -- PCGAMG analogue, deterministic MIS-2 aggregation) ---- */
-int or_amg_aggregate(const OrCsr *A, int bs, double theta, int *agg /* nrows/bs; -1 = left out */); /* returns #aggregates */
+int or_amg_aggregate(const OrCsr *A, int bs, double theta, int order /* 0 hashed, 1 natural */, int *agg /* nrows/bs; -1 = left out */); /* returns #aggregates */
 OrCsr *or_amg_tentative(int nn, int bs, const int *agg, int nagg, const int *w /* NULL: ones */, int *wc /* nagg, may be NULL */);
 OrCsr *or_csr_scale_rows(const OrCsr *A, const double *d);                    /* diag(d)*A (copy) */
 OrCsr *or_amg_smooth_prolongator(const OrCsr *A, const OrCsr *Pt, double omega); /* Pt - omega D^-1 A Pt */

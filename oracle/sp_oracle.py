@@ -91,7 +91,7 @@ def lib():
     sig("or_element_constraints", None, c_dp, c_dp)
     sig("or_zero_rows", None, CsrP, C.c_int, c_ip)
     sig("or_zero_cols", None, CsrP, C.c_int, c_ip)
-    sig("or_amg_aggregate", C.c_int, CsrP, C.c_int, C.c_double, c_ip)
+    sig("or_amg_aggregate", C.c_int, CsrP, C.c_int, C.c_double, C.c_int, c_ip)
     sig("or_amg_tentative", CsrP, C.c_int, C.c_int, c_ip, C.c_int, c_ip, c_ip)
     sig("or_csr_scale_rows", CsrP, CsrP, c_dp)
     sig("or_amg_smooth_prolongator", CsrP, CsrP, CsrP, C.c_double)
@@ -327,15 +327,18 @@ class Problem3D:
         return sp.bmat([[self.A.scipy(), self.Bt.scipy()], [self.B.scipy(), self.C.scipy()]], format="csr")
 
 
-def amg_aggregate(mat, bs, theta=0.0):
+MIS_ORDER = {"hash": 0, "natural": 1}
+
+
+def amg_aggregate(mat, bs, theta=0.0, order="hash"):
     """(aggregate id per node, -1 = left out; number of aggregates) -- or_amg_aggregate."""
     nn = mat.nrows // bs
     agg = np.zeros(max(nn, 1), dtype=np.int32)
-    nagg = lib().or_amg_aggregate(mat.ptr, bs, float(theta), iptr(agg))
+    nagg = lib().or_amg_aggregate(mat.ptr, bs, float(theta), MIS_ORDER[order], iptr(agg))
     return agg[:nn], nagg
 
 
-def amg_hierarchy(mat, bs, theta=0.0, nsmooths=1, coarse_limit=50, max_levels=30):
+def amg_hierarchy(mat, bs, theta=0.0, nsmooths=1, coarse_limit=50, max_levels=30, order="hash"):
     """Level matrices [A_0 .. A_L], prolongators [P_0 .. P_{L-1}] (P_l: level l+1 -> l) and the aggregates per level."""
     L = lib()
     mats, interps, aggs = [mat], [], []
@@ -343,7 +346,7 @@ def amg_hierarchy(mat, bs, theta=0.0, nsmooths=1, coarse_limit=50, max_levels=30
     while len(mats) < max_levels and mats[-1].nrows > coarse_limit:
         A = mats[-1]
         n = A.nrows
-        agg, nagg = amg_aggregate(A, bs, theta)
+        agg, nagg = amg_aggregate(A, bs, theta, order)
         if nagg == 0 or nagg * bs >= n:
             break
         wc = np.zeros(nagg, dtype=np.int32)
@@ -521,7 +524,8 @@ class Solver:
             mat, bs, theta=float(self._get(prefix + "pc_gamg_threshold", 0.0)),
             nsmooths=int(self._get(prefix + "pc_gamg_agg_nsmooths", 1)),
             coarse_limit=int(self._get(prefix + "pc_gamg_coarse_eq_limit", 50)),
-            max_levels=int(self._get(prefix + "pc_mg_levels", 30)))
+            max_levels=int(self._get(prefix + "pc_mg_levels", 30)),
+            order=self._get(prefix + "pc_gamg_mis_ordering", "hash"))
         return self._mg_from_levels(prefix, mats, interps)
 
     def _make_pc(self, prefix, prob):

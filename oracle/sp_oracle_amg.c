@@ -11,7 +11,7 @@
  *                  (theta > 0:  s_ij > theta * sqrt(s_ii * s_jj)); nodes without neighbours (Dirichlet rows,
  *                  src/Discretization.c:268 leaves them as identity rows) are left out of the coarse space
  *   roots        : maximal independent set of distance 2 (Bell, Dalton, Olson: "Exposing fine-grained parallelism in
- *                  algebraic multigrid methods", SISC 2012, algorithm 5) with the priority key hash(i):i
+ *                  algebraic multigrid methods", SISC 2012, algorithm 5) with the priority key hash(i):i, or i itself
  *   aggregates   : root + its neighbours, then every remaining node joins the aggregate of its highest-key
  *                  aggregated neighbour; aggregates are numbered by ascending root index
  *   prolongator  : tentative P_t[(i,c),(agg(i),c)] = sqrt(w_i / sum of w over the aggregate), w_i = number of finest-level
@@ -31,7 +31,12 @@ static void *amalloc(size_t n) {
   return p;
 }
 
-static uint64_t amg_key(int i) { /* distinct for distinct i; < 2^62 */
+/* priority of node i in the independent-set selection, distinct for distinct i and < 2^62.
+ * order 0: hashed (a pseudo-random permutation: ~10 rounds whatever the numbering; aggregates of irregular size)
+ * order 1: the node number itself (greedy in descending natural order: on a lexicographically numbered grid the roots
+ *          form a regular lattice, 3 x 3 aggregates, at the price of O(grid side) rounds) */
+static uint64_t amg_key(int i, int order) {
+  if (order == 1) return (uint64_t)(uint32_t)i + 1;
   unsigned int h = (unsigned int)i * 2654435761u;
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13;
   return ((uint64_t)(h >> 2) << 32) | (uint32_t)i;
@@ -77,7 +82,7 @@ static void amg_graph(const OrCsr *A, int bs, double theta, int **grp, int **gco
   *grp = rp; *gcol = gc;
 }
 
-int or_amg_aggregate(const OrCsr *A, int bs, double theta, int *agg) {
+int or_amg_aggregate(const OrCsr *A, int bs, double theta, int order, int *agg) {
   int nn = A->nrows / bs;
   int *rp, *gc;
   amg_graph(A, bs, theta, &rp, &gc);
@@ -85,7 +90,7 @@ int or_amg_aggregate(const OrCsr *A, int bs, double theta, int *agg) {
   uint64_t *t = (uint64_t *)amalloc(8 * (size_t)nn), *m1 = (uint64_t *)amalloc(8 * (size_t)nn), *m2 = (uint64_t *)amalloc(8 * (size_t)nn);
   long undecided = 0;
   for (int i = 0; i < nn; ++i) {
-    if (rp[i + 1] > rp[i]) { t[i] = ((uint64_t)1 << 62) | amg_key(i); ++undecided; }
+    if (rp[i + 1] > rp[i]) { t[i] = ((uint64_t)1 << 62) | amg_key(i, order); ++undecided; }
     else t[i] = 0;
   }
   while (undecided) {
@@ -93,7 +98,7 @@ int or_amg_aggregate(const OrCsr *A, int bs, double theta, int *agg) {
     for (int i = 0; i < nn; ++i) { uint64_t m = m1[i]; for (int k = rp[i]; k < rp[i + 1]; ++k) if (m1[gc[k]] > m) m = m1[gc[k]]; m2[i] = m; }
     for (int i = 0; i < nn; ++i) {
       if ((t[i] >> 62) != 1) continue;
-      if (m2[i] == t[i]) { t[i] = ((uint64_t)2 << 62) | amg_key(i); --undecided; }
+      if (m2[i] == t[i]) { t[i] = ((uint64_t)2 << 62) | amg_key(i, order); --undecided; }
       else if ((m2[i] >> 62) == 2) { t[i] = 0; --undecided; }
     }
   }
@@ -105,14 +110,14 @@ int or_amg_aggregate(const OrCsr *A, int bs, double theta, int *agg) {
   for (int i = 0; i < nn; ++i) {
     if (a1[i] >= 0 || rp[i + 1] == rp[i]) continue;
     uint64_t best = 0; int who = -1;
-    for (int k = rp[i]; k < rp[i + 1]; ++k) { int j = gc[k]; if ((t[j] >> 62) == 2 && amg_key(j) >= best) { best = amg_key(j); who = j; } }
+    for (int k = rp[i]; k < rp[i + 1]; ++k) { int j = gc[k]; if ((t[j] >> 62) == 2 && amg_key(j, order) >= best) { best = amg_key(j, order); who = j; } }
     if (who >= 0) agg[i] = a1[who];
   }
   memcpy(a1, agg, sizeof(int) * (size_t)nn);
   for (int i = 0; i < nn; ++i) {
     if (a1[i] >= 0 || rp[i + 1] == rp[i]) continue;
     uint64_t best = 0; int who = -1;
-    for (int k = rp[i]; k < rp[i + 1]; ++k) { int j = gc[k]; if (a1[j] >= 0 && amg_key(j) >= best) { best = amg_key(j); who = j; } }
+    for (int k = rp[i]; k < rp[i + 1]; ++k) { int j = gc[k]; if (a1[j] >= 0 && amg_key(j, order) >= best) { best = amg_key(j, order); who = j; } }
     if (who >= 0) agg[i] = a1[who];
   }
   free(a1); free(t); free(m1); free(m2); free(rp); free(gc);

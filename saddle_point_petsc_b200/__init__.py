@@ -92,8 +92,8 @@ _SIGS = {
     "b200sp_mat_matmult": [_vp, _vp, C.POINTER(_vp)],
     "b200sp_mat_scale_columns": [_vp, _vp, C.POINTER(_vp)],
     "b200sp_mat_add_scaled": [_vp, C.c_double, _vp, C.POINTER(_vp)],
-    "b200sp_amg_aggregate": [_vp, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)],
-    "b200sp_amg_prolongator": [_vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_vp)],
+    "b200sp_amg_aggregate": [_vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "b200sp_amg_prolongator": [_vp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_vp)],
     "b200sp_mat_zero_rows_columns": [_vp, C.c_int, c_ip, C.c_double],
     "b200sp_mat_zero_rows": [_vp, C.c_int, c_ip, C.c_double],
     "b200sp_mat_zero_columns": [_vp, C.c_int, c_ip],
@@ -511,21 +511,21 @@ class Mat:
         _chk(lib().b200sp_mat_add_scaled(self.h, float(s), B.h, C.byref(h)))
         return Mat(self.ctx, h)
 
-    def amg_aggregate(self, bs=1, theta=0.0):
+    def amg_aggregate(self, bs=1, theta=0.0, order="hash"):
         """(aggregate id per bs-dof node, -1 = left out; number of aggregates) of the -pc_type gamg set-up."""
         nrows, _, _ = self.size()
         agg = np.zeros(max(nrows // bs, 1), dtype=np.int32)
         nagg = C.c_int()
-        _chk(lib().b200sp_amg_aggregate(self.h, int(bs), float(theta), _iptr(agg), C.byref(nagg)))
+        _chk(lib().b200sp_amg_aggregate(self.h, int(bs), float(theta), {"hash": 0, "natural": 1}[order], _iptr(agg), C.byref(nagg)))
         return agg[:nrows // bs], nagg.value
 
-    def amg_prolongator(self, bs=1, theta=0.0, omega=0.0, node_weight=None, nagg=None):
+    def amg_prolongator(self, bs=1, theta=0.0, omega=0.0, node_weight=None, nagg=None, order="hash"):
         """Tentative (omega = 0) or smoothed aggregation prolongator P_t - omega D^-1 A P_t; with nagg given also
         returns the coarse node weights (finest-level nodes per aggregate)."""
         h = _vp()
         w = None if node_weight is None else np.ascontiguousarray(node_weight, dtype=np.int32)
         wc = None if nagg is None else np.zeros(max(nagg, 1), dtype=np.int32)
-        _chk(lib().b200sp_amg_prolongator(self.h, int(bs), float(theta), float(omega), None if w is None else _iptr(w),
+        _chk(lib().b200sp_amg_prolongator(self.h, int(bs), float(theta), {"hash": 0, "natural": 1}[order], float(omega), None if w is None else _iptr(w),
                                           None if wc is None else _iptr(wc), C.byref(h)))
         return Mat(self.ctx, h) if nagg is None else (Mat(self.ctx, h), wc[:nagg])
 

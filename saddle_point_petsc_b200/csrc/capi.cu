@@ -597,21 +597,21 @@ int b200sp_mat_add_scaled(b200sp_mat A, double s, b200sp_mat B, b200sp_mat *C) {
   *C = wrap(A->m.ctx, csr_add_scaled(plain(A), s, plain(B)));
   API_END
 }
-int b200sp_amg_aggregate(b200sp_mat A, int bs, double theta, int *agg_host, int *nagg) {
+int b200sp_amg_aggregate(b200sp_mat A, int bs, double theta, int order, int *agg_host, int *nagg) {
   API_BEGIN
   Csr &M = plain(A);
   use_device(M.ctx);
   DevBuf<int> agg;
-  *nagg = amg_aggregate(M, bs, theta, agg);
+  *nagg = amg_aggregate(M, bs, theta, order, agg);
   if (agg_host && M.nrows / bs > 0) B2_CUDA(cudaMemcpy(agg_host, agg.p, sizeof(int) * (size_t)(M.nrows / bs), cudaMemcpyDeviceToHost));
   API_END
 }
-int b200sp_amg_prolongator(b200sp_mat A, int bs, double theta, double omega, const int *node_weight, int *coarse_weight, b200sp_mat *P) {
+int b200sp_amg_prolongator(b200sp_mat A, int bs, double theta, int order, double omega, const int *node_weight, int *coarse_weight, b200sp_mat *P) {
   API_BEGIN
   Csr &M = plain(A);
   use_device(M.ctx);
   DevBuf<int> agg, w, wc;
-  const int nagg = amg_aggregate(M, bs, theta, agg);
+  const int nagg = amg_aggregate(M, bs, theta, order, agg);
   const int nn = M.nrows / bs;
   if (node_weight && nn > 0) {
     for (int i = 0; i < nn; ++i) B2_REQUIRE(node_weight[i] >= 1, "amg_prolongator: node weights must be positive");

@@ -409,7 +409,7 @@ std::shared_ptr<Csr> csr_extract_fields(const Csr &A, int bs, const std::vector<
 std::shared_ptr<Csr> csr_scale_cols(const Csr &A, const double *d);            // A * diag(d)
 std::shared_ptr<Csr> csr_scale_rows(const Csr &A, const double *d);            // diag(d) * A
 // aggregation multigrid set-up (kernels_amg.cu; the algorithm oracle/sp_oracle_amg.c defines)
-int amg_aggregate(const Csr &A, int bs, double theta, DevBuf<int> &agg);        // agg[node] = aggregate id or -1; returns the number of aggregates
+int amg_aggregate(const Csr &A, int bs, double theta, int order, DevBuf<int> &agg);        // agg[node] = aggregate id or -1; returns the number of aggregates
 std::shared_ptr<Csr> amg_tentative(Ctx *c, int nn, int bs, const DevBuf<int> &agg, int nagg, const int *w, DevBuf<int> &wc);
 std::shared_ptr<Csr> amg_smooth_prolongator(const Csr &A, const Csr &Pt, double omega); // Pt - omega D^-1 A Pt
 std::shared_ptr<Csr> csr_add_scaled(const Csr &A, double a, const Csr &B);     // A + a B (same pattern required)

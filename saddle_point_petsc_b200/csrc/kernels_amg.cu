@@ -12,7 +12,11 @@
 namespace b200sp {
 namespace {
 
-__host__ __device__ inline unsigned long long amg_key(int i) { // distinct per node, < 2^62
+// priority of a node, distinct per node, < 2^62.  order 0: hashed (pseudo-random permutation, ~10 rounds); order 1: the
+// node number (greedy in descending natural order: a regular root lattice on lexicographically numbered grids, at
+// the price of O(grid side) rounds)
+__host__ __device__ inline unsigned long long amg_key(int i, int order) {
+  if (order == 1) return (unsigned long long)(unsigned int)i + 1ull;
   unsigned int h = (unsigned int)i * 2654435761u;
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13;
   return ((unsigned long long)(h >> 2) << 32) | (unsigned int)i;
@@ -66,11 +70,11 @@ __global__ void __launch_bounds__(256) k_amg_graph(int nn, int bs, const int *__
     if (!FILL) cnt[i] = n;
   }
 }
-__global__ void __launch_bounds__(256) k_amg_init(int nn, const int *__restrict__ grp, unsigned long long *t, int *counter) {
+__global__ void __launch_bounds__(256) k_amg_init(int nn, int order, const int *__restrict__ grp, unsigned long long *t, int *counter) {
   for (int base = blockIdx.x * blockDim.x; base < nn; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     bool u = false;
-    if (i < nn) { u = grp[i + 1] > grp[i]; t[i] = u ? (ST_UNDECIDED | amg_key(i)) : 0ull; }
+    if (i < nn) { u = grp[i + 1] > grp[i]; t[i] = u ? (ST_UNDECIDED | amg_key(i, order)) : 0ull; }
     const int c = __syncthreads_count(u);
     if (threadIdx.x == 0 && c) atomicAdd(counter, c);
   }
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(256) k_amg_prop(int nn, const int *__restrict_
   }
 }
 // undecided node: largest key among the undecided within distance 2 and no root there -> root; a root there -> out
-__global__ void __launch_bounds__(256) k_amg_decide(int nn, unsigned long long *t, const unsigned long long *__restrict__ m2, int *counter) {
+__global__ void __launch_bounds__(256) k_amg_decide(int nn, int order, unsigned long long *t, const unsigned long long *__restrict__ m2, int *counter) {
   for (int base = blockIdx.x * blockDim.x; base < nn; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     bool u = false;
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256) k_amg_decide(int nn, unsigned long long *
       const unsigned long long ti = t[i];
       if ((ti >> 62) == 1ull) {
         const unsigned long long m = m2[i];
-        if (m == ti) t[i] = ST_ROOT | amg_key(i);
+        if (m == ti) t[i] = ST_ROOT | amg_key(i, order);
         else if ((m >> 62) == 2ull) t[i] = 0ull;
         else u = true;
       }
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(256) k_amg_decide(int nn, unsigned long long *
 __global__ void __launch_bounds__(256) k_amg_rootflag(int nn, const unsigned long long *__restrict__ t, int *flag) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) flag[i] = (t[i] >> 62) == 2ull ? 1 : 0;
 }
-__global__ void __launch_bounds__(256) k_amg_join1(int nn, const int *__restrict__ grp, const int *__restrict__ gcol, const unsigned long long *__restrict__ t,
+__global__ void __launch_bounds__(256) k_amg_join1(int nn, int order, const int *__restrict__ grp, const int *__restrict__ gcol, const unsigned long long *__restrict__ t,
                                                    const int *__restrict__ rootid, int *agg1) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
     int a = -1;
@@ -113,14 +117,14 @@ __global__ void __launch_bounds__(256) k_amg_join1(int nn, const int *__restrict
       int who = -1;
       for (int k = grp[i]; k < grp[i + 1]; ++k) {
         const int j = gcol[k];
-        if ((t[j] >> 62) == 2ull && amg_key(j) >= best) { best = amg_key(j); who = j; }
+        if ((t[j] >> 62) == 2ull && amg_key(j, order) >= best) { best = amg_key(j, order); who = j; }
       }
       if (who >= 0) a = rootid[who];
     }
     agg1[i] = a;
   }
 }
-__global__ void __launch_bounds__(256) k_amg_join2(int nn, const int *__restrict__ grp, const int *__restrict__ gcol, const int *__restrict__ agg1, int *agg) {
+__global__ void __launch_bounds__(256) k_amg_join2(int nn, int order, const int *__restrict__ grp, const int *__restrict__ gcol, const int *__restrict__ agg1, int *agg) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
     int a = agg1[i];
     if (a < 0) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256) k_amg_join2(int nn, const int *__restrict
       int who = -1;
       for (int k = grp[i]; k < grp[i + 1]; ++k) {
         const int j = gcol[k];
-        if (agg1[j] >= 0 && amg_key(j) >= best) { best = amg_key(j); who = j; }
+        if (agg1[j] >= 0 && amg_key(j, order) >= best) { best = amg_key(j, order); who = j; }
       }
       if (who >= 0) a = agg1[who];
     }
@@ -158,9 +162,10 @@ __global__ void __launch_bounds__(256) k_scale_rows(int nrows, const int *__rest
 }
 } // namespace
 
-int amg_aggregate(const Csr &A, int bs, double theta, DevBuf<int> &agg) {
+int amg_aggregate(const Csr &A, int bs, double theta, int order, DevBuf<int> &agg) {
   Ctx *c = A.ctx;
   B2_REQUIRE(!A.halo, "gamg: row-partitioned matrices are not aggregated (single-rank set-up only)");
+  B2_REQUIRE(order == 0 || order == 1, "gamg: unknown independent-set ordering");
   B2_REQUIRE(bs >= 1 && bs <= 4 && A.nrows == A.ncols && A.nrows % bs == 0, "gamg: square matrix with block size 1..4 expected");
   const int nn = A.nrows / bs;
   agg.alloc((size_t)nn + 1);
@@ -184,18 +189,18 @@ int amg_aggregate(const Csr &A, int bs, double theta, DevBuf<int> &agg) {
     LaunchScope ls(c, "setup");
     k_amg_graph<true><<<g, 256, 0, c->stream>>>(nn, bs, A.rowptr.p, A.col.p, A.val.p, sd.p, theta, grp.p, gcol.p, nullptr);
     B2_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(int), c->stream));
-    k_amg_init<<<g, 256, 0, c->stream>>>(nn, grp.p, t.p, counter.p);
+    k_amg_init<<<g, 256, 0, c->stream>>>(nn, order, grp.p, t.p, counter.p);
     check_launch("k_amg_init");
   }
   B2_CUDA(cudaMemcpyAsync(&undecided, counter.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
   for (int round = 0; undecided > 0; ++round) {
-    B2_REQUIRE(round < 10000, "gamg: the independent-set selection did not terminate");
+    B2_REQUIRE(round < 200000, "gamg: the independent-set selection did not terminate");
     LaunchScope ls(c, "setup");
     B2_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(int), c->stream));
     k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, t.p, m1.p);
     k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, m1.p, m2.p);
-    k_amg_decide<<<g, 256, 0, c->stream>>>(nn, t.p, m2.p, counter.p);
+    k_amg_decide<<<g, 256, 0, c->stream>>>(nn, order, t.p, m2.p, counter.p);
     check_launch("k_amg_decide");
     B2_CUDA(cudaMemcpyAsync(&undecided, counter.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
@@ -210,8 +215,8 @@ int amg_aggregate(const Csr &A, int bs, double theta, DevBuf<int> &agg) {
   exclusive_scan_i32(c, flag.p, rootid.p, nn, &nagg);
   {
     LaunchScope ls(c, "setup");
-    k_amg_join1<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, t.p, rootid.p, agg1.p);
-    k_amg_join2<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, agg1.p, agg.p);
+    k_amg_join1<<<g, 256, 0, c->stream>>>(nn, order, grp.p, gcol.p, t.p, rootid.p, agg1.p);
+    k_amg_join2<<<g, 256, 0, c->stream>>>(nn, order, grp.p, gcol.p, agg1.p, agg.p);
     check_launch("k_amg_join");
   }
   c->sync();

@@ -932,7 +932,8 @@ Op *Solver::make_mg(const std::string &prefix, std::shared_ptr<Csr> mat) {
 // PCGAMG analogue: smoothed-aggregation hierarchy built on the device (kernels_amg.cu) from the assembled block alone
 // -- no grid needed, so it also serves matrices that did not come from a DMDA (selfp / LSC products, user CSR).
 // Options (PETSc's names): -pc_gamg_threshold (0), -pc_gamg_agg_nsmooths (1), -pc_gamg_coarse_eq_limit (50),
-// -pc_mg_levels (30, the maximum), -pc_gamg_block_size (the matrix block size), smoothers under -mg_levels_.
+// -pc_mg_levels (30, the maximum), smoothers under -mg_levels_; ours: -pc_gamg_block_size (the matrix block size),
+// -pc_gamg_mis_ordering {hash,natural} (PETSc's greedy MIS uses a random permutation = hash).
 Op *Solver::make_gamg(const std::string &prefix, std::shared_ptr<Csr> mat) {
   if (mat->halo || ctx->dcomm) throw Error(B200SP_ERR_UNSUPPORTED, "-" + prefix + "pc_type gamg: the aggregation set-up is single-rank; use -" + prefix + "pc_type mg on row-partitioned DMDA matrices");
   B2_REQUIRE(mat->nrows == mat->ncols, "pc gamg: square matrix expected");
@@ -940,6 +941,9 @@ Op *Solver::make_gamg(const std::string &prefix, std::shared_ptr<Csr> mat) {
   const int bs = std::stoi(opt(prefix + "pc_gamg_block_size", std::to_string(bs0)));
   const double theta = std::stod(opt(prefix + "pc_gamg_threshold", "0"));
   const int nsmooths = std::stoi(opt(prefix + "pc_gamg_agg_nsmooths", "1"));
+  const std::string ord = opt(prefix + "pc_gamg_mis_ordering", "hash");
+  B2_REQUIRE(ord == "hash" || ord == "natural", "pc gamg: -pc_gamg_mis_ordering must be hash or natural");
+  const int order = ord == "natural" ? 1 : 0;
   const int coarse_limit = std::stoi(opt(prefix + "pc_gamg_coarse_eq_limit", "50"));
   const int max_levels = std::stoi(opt(prefix + "pc_mg_levels", "30"));
   B2_REQUIRE(nsmooths == 0 || nsmooths == 1, "pc gamg: -pc_gamg_agg_nsmooths must be 0 or 1");
@@ -957,7 +961,7 @@ Op *Solver::make_gamg(const std::string &prefix, std::shared_ptr<Csr> mat) {
     DevBuf<int> agg;
     int nagg = 0;
     if (coarsen) {
-      nagg = amg_aggregate(*Al, bs, theta, agg);
+      nagg = amg_aggregate(*Al, bs, theta, order, agg);
       if (nagg == 0 || (int64_t)nagg * bs >= Al->nrows) coarsen = false; // nothing left to aggregate: this level is the coarse one
     }
     if (!coarsen) { mg->lev.push_back(std::move(L)); break; }

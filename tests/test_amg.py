@@ -20,7 +20,9 @@ GAMG_PLAIN = GAMG + " -fieldsplit_0_pc_gamg_agg_nsmooths 0"
 VELOCITY_GAMG = "-ksp_type gmres -ksp_rtol 1e-8 -pc_type gamg -mg_levels_ksp_max_it 2"
 
 
-def key(i):
+def key(i, order="hash"):
+    if order == "natural":
+        return int(i) + 1
     h = (int(i) * 2654435761) & 0xFFFFFFFF
     h ^= h >> 16
     h = (h * 0x85EBCA6B) & 0xFFFFFFFF
@@ -39,10 +41,11 @@ def node_graph(A, bs):
     return G
 
 
-def aggregate_by_definition(A, bs):
+def aggregate_by_definition(A, bs, order="hash"):
     """Sequential restatement: repeat {largest-key undecided node with no root within distance 2 becomes a root}."""
     G = node_graph(A, bs)
     nn = G.shape[0]
+    key = lambda i: globals()["key"](i, order)  # noqa: E731
     nb = [G.indices[G.indptr[i]:G.indptr[i + 1]] for i in range(nn)]
     live = [i for i in range(nn) if len(nb[i])]
     # MIS-2 by hashed priority == greedy in descending key order (a node is a root iff no higher-key root is within 2)
@@ -72,11 +75,12 @@ def aggregate_by_definition(A, bs):
     return agg.astype(np.int32), int(root.sum())
 
 
+@pytest.mark.parametrize("order", ["hash", "natural"])
 @pytest.mark.parametrize("nx,ny", [(8, 8), (21, 13), (40, 40)])
-def test_oracle_aggregates_follow_the_definition(nx, ny):
+def test_oracle_aggregates_follow_the_definition(nx, ny, order):
     pr = so.Problem(nx, ny, kkt=True)
-    agg, nagg = so.amg_aggregate(pr.A, 2)
-    ref, nref = aggregate_by_definition(pr.A.scipy(), 2)
+    agg, nagg = so.amg_aggregate(pr.A, 2, order=order)
+    ref, nref = aggregate_by_definition(pr.A.scipy(), 2, order)
     assert nagg == nref and np.array_equal(agg, ref)
     # Dirichlet nodes (identity rows) are left out, every other node belongs to exactly one aggregate
     M, N = nx + 1, ny + 1
@@ -85,8 +89,8 @@ def test_oracle_aggregates_follow_the_definition(nx, ny):
     assert np.all(agg[boundary] == -1) and np.all(agg[~boundary] >= 0)
     assert sorted(set(agg[agg >= 0])) == list(range(nagg))
     # scalar (pressure) block with the same routine
-    aggp, naggp = so.amg_aggregate(pr.Q, 1)
-    refp, nrefp = aggregate_by_definition(pr.Q.scipy(), 1)
+    aggp, naggp = so.amg_aggregate(pr.Q, 1, order=order)
+    refp, nrefp = aggregate_by_definition(pr.Q.scipy(), 1, order)
     assert naggp == nrefp and np.array_equal(aggp, refp) and np.all(aggp >= 0)
 
 
@@ -158,6 +162,23 @@ def test_oracle_gamg_iterations_grow_slowly_with_the_grid():
     assert its[-1] <= its[0] + 8 and its[-1] <= 30, its
 
 
+def test_oracle_natural_ordering_gives_regular_aggregates_and_grid_independent_iterations():
+    """-pc_gamg_mis_ordering natural on the lexicographically numbered grid: the roots form a lattice with spacing 3
+    (aggregates of ~9 nodes instead of ~13) and the iteration count stops growing with the grid."""
+    pr = so.Problem(61, 61, kkt=False)
+    agg_h, nagg_h = so.amg_aggregate(pr.A, 2, order="hash")
+    agg_n, nagg_n = so.amg_aggregate(pr.A, 2, order="natural")
+    live = int((agg_n >= 0).sum())
+    assert live == 60 * 60 and nagg_n == 20 * 20 and nagg_h < 0.8 * nagg_n
+    sizes = np.bincount(agg_n[agg_n >= 0])
+    assert np.count_nonzero(sizes == 9) >= 18 * 18          # all but the rows of aggregates along two sides
+    its = {}
+    for order in ("hash", "natural"):
+        its[order] = [so.Solver(so.Problem(nx, nx, kkt=False, rhs_kind=1), VELOCITY_GAMG + " -pc_gamg_mis_ordering " + order).solve()["its"]
+                      for nx in (32, 64, 128)]
+    assert max(its["natural"]) - min(its["natural"]) <= 2 and its["natural"][-1] < its["hash"][-1], its
+
+
 # ------------------------------------------------------------------ GPU parity
 sp = None
 
@@ -177,24 +198,25 @@ def same_bits(a, b):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", ["hash", "natural"])
 @pytest.mark.parametrize("nx,ny", [(3, 3), (21, 13), (64, 48), (300, 200)])
-def test_aggregates_and_tentative_prolongator_bit_exact(ctx, spmod, nx, ny):
+def test_aggregates_and_tentative_prolongator_bit_exact(ctx, spmod, nx, ny, order):
     dev = sp.SaddlePointProblem(ctx, nx, ny, kkt=True)
     orc = so.Problem(nx, ny, kkt=True)
     for D, O, bs in ((dev.A, orc.A, 2), (dev.Q, orc.Q, 1), (dev.C, orc.C, 1)):
-        agg_d, nagg_d = D.amg_aggregate(bs)
-        agg_o, nagg_o = so.amg_aggregate(O, bs)
+        agg_d, nagg_d = D.amg_aggregate(bs, order=order)
+        agg_o, nagg_o = so.amg_aggregate(O, bs, order=order)
         assert nagg_d == nagg_o and np.array_equal(agg_d, agg_o)
         if nagg_o == 0:
             continue
-        rp, col, val = D.amg_prolongator(bs).csr()
+        rp, col, val = D.amg_prolongator(bs, order=order).csr()
         Pt = so.Csr(so.lib().or_amg_tentative(len(agg_o), bs, so.iptr(agg_o), nagg_o, None, None))
         assert np.array_equal(rp, Pt.rowptr) and np.array_equal(col, Pt.col) and same_bits(val, Pt.val)
         # with node weights (a level below the finest one)
         w = (1 + np.arange(len(agg_o)) % 17).astype(np.int32)
         wc_o = np.zeros(nagg_o, dtype=np.int32)
         Pw = so.Csr(so.lib().or_amg_tentative(len(agg_o), bs, so.iptr(agg_o), nagg_o, so.iptr(w), so.iptr(wc_o)))
-        Pd, wc_d = D.amg_prolongator(bs, node_weight=w, nagg=nagg_o)
+        Pd, wc_d = D.amg_prolongator(bs, node_weight=w, nagg=nagg_o, order=order)
         rp, col, val = Pd.csr()
         assert np.array_equal(wc_d, wc_o)
         assert np.array_equal(rp, Pw.rowptr) and np.array_equal(col, Pw.col) and same_bits(val, Pw.val)
@@ -230,8 +252,11 @@ def test_smoothed_prolongator_and_galerkin_operator(ctx, spmod):
     assert np.max(np.abs(val - Ao.val)) <= 1e-13 * np.max(np.abs(Ao.val))
 
 
+GAMG_NATURAL = GAMG + " -fieldsplit_0_pc_gamg_mis_ordering natural"
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("opts", [GAMG, GAMG_PLAIN])
+@pytest.mark.parametrize("opts", [GAMG, GAMG_PLAIN, GAMG_NATURAL])
 @pytest.mark.parametrize("nx", [16, 40])
 def test_gamg_pc_apply_and_solve_parity(ctx, spmod, opts, nx):
     dev = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)

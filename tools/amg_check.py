@@ -12,7 +12,8 @@ ctx = sp.Context(device=0)
 for nx in [int(a) for a in sys.argv[1:]] or [576]:
     prob = sp.SaddlePointProblem(ctx, nx, nx, kkt=True, rhs_kind=1)
     base = bench.options_for("fgmres_schur_mg", nx)
-    for name, extra in (("mg", ""), ("gamg", " -fieldsplit_0_pc_type gamg"), ("gamg_plain", " -fieldsplit_0_pc_type gamg -fieldsplit_0_pc_gamg_agg_nsmooths 0")):
+    for name, extra in (("mg", ""), ("gamg", " -fieldsplit_0_pc_type gamg"),
+                        ("gamg_natural", " -fieldsplit_0_pc_type gamg -fieldsplit_0_pc_gamg_mis_ordering natural"), ("gamg_plain", " -fieldsplit_0_pc_type gamg -fieldsplit_0_pc_gamg_agg_nsmooths 0")):
         ksp = prob.make_ksp(base + extra)
         x = sp.Vec(ctx, prob.n)
         t0 = time.time(); ksp.setup(); ctx.synchronize(); t_setup = time.time() - t0
