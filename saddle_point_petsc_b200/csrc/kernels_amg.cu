@@ -8,6 +8,7 @@
 // The Dirichlet rows the reference leaves as identity rows (src/Discretization.c:268, MatZeroRowsColumns) have no
 // neighbours and stay out of the coarse space; the level smoother handles them.
 #include "core.h"
+#include <cstdlib>
 
 namespace b200sp {
 namespace {
@@ -194,13 +195,19 @@ int amg_aggregate(const Csr &A, int bs, double theta, int order, DevBuf<int> &ag
   }
   B2_CUDA(cudaMemcpyAsync(&undecided, counter.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
-  for (int round = 0; undecided > 0; ++round) {
+  // rounds per host read-back of the undecided count: a round after the last decision changes nothing, so running a
+  // few too many is harmless and saves a synchronisation per round (the natural ordering needs O(grid side) rounds)
+  const char *eb = getenv("B200SP_AMG_BATCH"); // rounds per read-back (tuning knob)
+  const int batch = eb && atoi(eb) > 0 ? atoi(eb) : (order == 1 ? 8 : 2);
+  for (int round = 0; undecided > 0; round += batch) {
     B2_REQUIRE(round < 200000, "gamg: the independent-set selection did not terminate");
     LaunchScope ls(c, "setup");
-    B2_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(int), c->stream));
-    k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, t.p, m1.p);
-    k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, m1.p, m2.p);
-    k_amg_decide<<<g, 256, 0, c->stream>>>(nn, order, t.p, m2.p, counter.p);
+    for (int b = 0; b < batch; ++b) {
+      B2_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(int), c->stream));
+      k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, t.p, m1.p);
+      k_amg_prop<<<g, 256, 0, c->stream>>>(nn, grp.p, gcol.p, m1.p, m2.p);
+      k_amg_decide<<<g, 256, 0, c->stream>>>(nn, order, t.p, m2.p, counter.p);
+    }
     check_launch("k_amg_decide");
     B2_CUDA(cudaMemcpyAsync(&undecided, counter.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
